@@ -1,0 +1,59 @@
+"""ctypes binding of libhdn_b200.so (the C ABI in include/hdn_b200.h).
+
+The product path has NO CPU fallback: if the shared library is missing or a call returns a
+non-zero status this module raises.  (The oracle under oracle/ is test infrastructure and is
+never imported from here.)
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "libhdn_b200.so")
+
+# name -> (restype, argtypes); mirrors include/hdn_b200.h one to one.
+_vp, _ci, _i64, _f, _d = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double
+SIGNATURES = {
+    "hdn_abi_version": (_ci, []),
+    "hdn_status_string": (ctypes.c_char_p, [_ci]),
+    "hdn_device_info": (_ci, [ctypes.POINTER(_ci)] * 3),
+    "hdn_launch_count": (_i64, []),
+    "hdn_xcorr_dw_f32": (_ci, [_vp, _vp, _vp, _ci, _ci, _ci, _ci, _ci, _ci, _ci, _i64, _vp]),
+    "hdn_xcorr_dw_multi_f32": (_ci, [_ci, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp), _ci, _ci, _ci, _ci, _ci, _ci, _ci,
+                                     _i64, _vp]),
+    "hdn_logpolar_f32": (_ci, [_vp, _vp, _f, _vp, _ci, _ci, _ci, _ci, _ci, _vp]),
+    "hdn_dlt4_f32": (_ci, [_vp, _vp, _vp, _ci, _vp]),
+    "hdn_homo_warp_f32": (_ci, [_vp, _vp, ctypes.POINTER(_f), ctypes.POINTER(_f), _vp, _ci, _ci, _ci, _ci, _vp]),
+    "hdn_dlt_warp_f32": (_ci, [_vp, _vp, _vp, ctypes.POINTER(_f), ctypes.POINTER(_f), _vp, _vp, _ci, _ci, _ci, _ci, _vp]),
+    "hdn_score_argmax_f32": (_ci, [_vp, _vp, _vp, _d, _vp, _vp, _vp, _vp, _ci, _ci, _ci, _vp]),
+}
+
+_lib = None
+
+
+class HdnError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise HdnError("libhdn_b200.so is not built (%s). Run `python -m hdn_b200.build`; there is no CPU fallback." % SO_PATH)
+        L = ctypes.CDLL(SO_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the ABI and the binding drift apart
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = lib().hdn_status_string(status).decode()
+        if status < 0:
+            raise ValueError("%s: %s" % (what, msg))
+        raise HdnError("%s: CUDA error %d (%s)" % (what, status, msg))
+
+
+def launch_count():
+    return int(lib().hdn_launch_count())

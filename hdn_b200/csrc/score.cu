@@ -1,0 +1,80 @@
+// score.cu -- K6: 2-way softmax -> window blend -> first-max arg-max -> offset gather, on device.
+//
+// Replaces the per-frame device->host->NumPy epilogue of the reference:
+//   hdn/tracker/hdn_tracker.py:82-89        _convert_score (softmax over the 2 cls channels, p(fg))
+//   hdn/tracker/hdn_tracker_proj_e2e.py:172-174  pscore = score*(1-w) + window*w ; np.argmax
+//   hdn/tracker/base_tracker.py:54-59 / hdn_tracker.py:51-67  only column idx of loc is consumed
+// so one 8-byte index, two scalars and L floats cross PCIe instead of the whole score/loc maps.
+//
+// Bit-exactness of the index: the reference multiplies the float32 score by the Python float (1-w)
+// in float32, adds the float64 window term in float64 and takes the FIRST maximum.  The kernel
+// does exactly that arithmetic (fp32 product, fp64 sum) and resolves ties towards the smaller index.
+#include "common.cuh"
+
+namespace hdn {
+
+struct Best {
+    double v;
+    int i;
+    float s;
+};
+
+__device__ __forceinline__ Best better(const Best &a, const Best &b) { return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a; }
+
+__global__ void __launch_bounds__(256)
+    score_argmax_kernel(const float *__restrict__ cls, const float *__restrict__ loc, const double *__restrict__ window, double w_infl,
+                        float one_minus_w, long long *__restrict__ idx, double *__restrict__ pscore, float *__restrict__ score,
+                        float *__restrict__ gathered, int L, int n) {
+    const int b = blockIdx.x;
+    const float *c0 = cls + (long long)b * 2 * n, *c1 = c0 + n;
+    Best best{-INFINITY, 0x7fffffff, 0.f};
+    for (int p = threadIdx.x; p < n; p += blockDim.x) {
+        const float a0 = __ldg(c0 + p), a1 = __ldg(c1 + p);
+        const float m = fmaxf(a0, a1);
+        const float e0 = expf(__fsub_rn(a0, m)), e1 = expf(__fsub_rn(a1, m));
+        const float s = __fdiv_rn(e1, __fadd_rn(e0, e1));
+        double ps;
+        if (window) ps = __dadd_rn((double)__fmul_rn(s, one_minus_w), __dmul_rn(__ldg(window + p), w_infl));
+        else ps = (double)s;
+        const Best cand{ps, p, s};
+        best = better(best, cand);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        Best o;
+        o.v = __shfl_xor_sync(0xffffffffu, best.v, off);
+        o.i = __shfl_xor_sync(0xffffffffu, best.i, off);
+        o.s = __shfl_xor_sync(0xffffffffu, best.s, off);
+        best = better(best, o);
+    }
+    __shared__ Best sb[8];
+    __shared__ int s_idx;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) sb[warp] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        Best r = sb[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = better(r, sb[w]);
+        idx[b] = r.i;
+        pscore[b] = r.v;
+        score[b] = r.s;
+        s_idx = r.i;
+    }
+    __syncthreads();
+    for (int l = threadIdx.x; l < L; l += blockDim.x) gathered[b * L + l] = __ldg(loc + ((long long)b * L + l) * n + s_idx);
+}
+
+}  // namespace hdn
+
+using namespace hdn;
+
+extern "C" int hdn_score_argmax_f32(const float *cls, const float *loc, const double *window, double win_influence, int64_t *idx,
+                                    double *pscore, float *score, float *gathered, int B, int L, int N, hdn_stream_t stream) {
+    if (!cls || !loc || !idx || !pscore || !score || !gathered) return HDN_ERR_NULL;
+    if (B < 1 || L < 1 || N < 1) return HDN_ERR_SHAPE;
+    static_assert(sizeof(long long) == sizeof(int64_t), "int64");
+    score_argmax_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(cls, loc, window, win_influence, (float)(1.0 - win_influence),
+                                                            reinterpret_cast<long long *>(idx), pscore, score, gathered, L, N * N);
+    count_launch();
+    return launch_status();
+}

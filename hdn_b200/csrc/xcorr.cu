@@ -1,0 +1,307 @@
+// xcorr.cu -- K1/K2: depth-wise (optionally circular) cross-correlation for sm_100a.
+//
+// Replaces hdn/core/xcorr.py:37-46 (xcorr_depthwise) and :48-61 (xcorr_depthwise_circular).
+//
+// Design (DESIGN.md "K1/K2"):
+//   * A (b,c) plane is tiny (29x29 .. 61x61 fp32) and contiguous in NCHW, so a group of G planes of
+//     x, of k and of out are three contiguous byte ranges.  One persistent CTA per SM walks groups
+//     g = blockIdx.x, += gridDim.x; an elected thread stages x|k of group g+STAGES with 1-D TMA
+//     bulk copies (cp.async.bulk -> UBLKCP) completing on an mbarrier, and drains the finished
+//     output tile with a bulk store from shared memory.  HBM sees only full-line, fully coalesced
+//     traffic, each byte exactly once.
+//   * Compute: one thread owns one OUTPUT ROW: WO accumulators and the WX-wide input row live in
+//     registers, kernel taps are warp-broadcast LDS.  Row pitch is odd for every shape the network
+//     produces, so lanes (= consecutive rows) hit distinct banks without padding.
+//   * The circular variant never materialises the padded tensor: rows wrap with one conditional
+//     add, columns clamp at COMPILE time (the clamped column is just a different register).
+//   * Accumulation order is fixed (u outer, v inner, split-K halves combined in order) -> results
+//     are run-to-run deterministic.
+//   * Shapes outside the table fall back to a plain one-thread-per-output kernel (still on device).
+#include "common.cuh"
+
+namespace hdn {
+
+struct XProblems {
+    const float *x[HDN_MAX_PROBLEMS];
+    const float *k[HDN_MAX_PROBLEMS];
+    float *out[HDN_MAX_PROBLEMS];
+};
+
+template <int KH_, int KW_, int HX_, int WX_, bool CIRC_, int G_, int NT_, int STAGES_, int KSPLIT_, bool SPILL_>
+struct XCfg {
+    static constexpr int KH = KH_, KW = KW_, HX = HX_, WX = WX_, G = G_, NT = NT_, STAGES = STAGES_, KSPLIT = KSPLIT_;
+    static constexpr bool CIRC = CIRC_, SPILL = SPILL_;
+    static constexpr int PH = CIRC ? HX / 2 : 0, PW = CIRC ? WX / 2 : 0;
+    static constexpr int HO = HX + 2 * PH - KH + 1, WO = WX + 2 * PW - KW + 1;
+    static constexpr int XPL = HX * WX, KPL = KH * KW, OPL = HO * WO;
+    static constexpr int STAGE_FLOATS = G * (XPL + KPL);
+    static constexpr int OUT_FLOATS = G * OPL;
+    static constexpr size_t SMEM = (size_t)(STAGES * STAGE_FLOATS + 2 * OUT_FLOATS) * 4 + STAGES * 8 + 16;
+    static_assert(G % 4 == 0, "bulk copies need 16-byte multiples");
+    static_assert(!SPILL || (HO == 33 && NT == 32 * G * KSPLIT), "row-spill mapping is for 33-row outputs");
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
+
+// Accumulate kernel rows [u0,u1) of output row i into acc[WO].
+template <class Cfg>
+__device__ __forceinline__ void row_accumulate(const float *__restrict__ xp, const float *__restrict__ kp, int i, int u0, int u1,
+                                               float (&acc)[Cfg::WO]) {
+#pragma unroll 1
+    for (int u = u0; u < u1; ++u) {
+        int r = i + u - Cfg::PH;
+        if (Cfg::CIRC) {
+            if (r < 0) r += Cfg::HX;
+            else if (r >= Cfg::HX) r -= Cfg::HX;
+        }
+        const float *xr = xp + r * Cfg::WX;
+        float xv[Cfg::WX];
+#pragma unroll
+        for (int c = 0; c < Cfg::WX; ++c) xv[c] = xr[c];
+        const float *kr = kp + u * Cfg::KW;
+#pragma unroll
+        for (int v = 0; v < Cfg::KW; ++v) {
+            const float kv = kr[v];
+#pragma unroll
+            for (int c = 0; c < Cfg::WO; ++c) {
+                int q = c + v - Cfg::PW;  // compile-time after unrolling
+                q = q < 0 ? 0 : (q > Cfg::WX - 1 ? Cfg::WX - 1 : q);
+                acc[c] = fmaf(xv[q], kv, acc[c]);
+            }
+        }
+    }
+}
+
+template <class Cfg>
+__device__ __forceinline__ void compute_group(const float *__restrict__ sx, const float *__restrict__ sk, float *__restrict__ so, int tid) {
+    constexpr int ROWS = Cfg::G * Cfg::HO;
+    if constexpr (!Cfg::SPILL) {
+#pragma unroll 1
+        for (int ks = 0; ks < Cfg::KSPLIT; ++ks) {
+            // split-K slices are combined in slice order (deterministic)
+#pragma unroll 1
+            for (int t = tid; t < ROWS * Cfg::KSPLIT; t += Cfg::NT) {
+                const int myks = t / ROWS;
+                if (myks != ks) continue;
+                const int rrow = t - myks * ROWS;
+                const int p = rrow / Cfg::HO, i = rrow - p * Cfg::HO;
+                float acc[Cfg::WO];
+#pragma unroll
+                for (int c = 0; c < Cfg::WO; ++c) acc[c] = 0.f;
+                row_accumulate<Cfg>(sx + p * Cfg::XPL, sk + p * Cfg::KPL, i, ks * Cfg::KH / Cfg::KSPLIT, (ks + 1) * Cfg::KH / Cfg::KSPLIT, acc);
+                float *o = so + p * Cfg::OPL + i * Cfg::WO;
+                if (ks == 0) {
+#pragma unroll
+                    for (int c = 0; c < Cfg::WO; ++c) o[c] = acc[c];
+                } else {
+#pragma unroll
+                    for (int c = 0; c < Cfg::WO; ++c) o[c] += acc[c];
+                }
+            }
+            if (ks + 1 < Cfg::KSPLIT) __syncthreads();
+        }
+    } else {
+        // 33-row outputs: warp = (plane, K-slice); lane = rows 0..31; row 32 is spread over the lanes
+        // (lane l -> column l, column 32 via a warp reduction) so every lane carries the same load.
+        const int warp = tid >> 5, lane = tid & 31;
+        const int p = warp % Cfg::G, ks = warp / Cfg::G;
+        const int u0 = ks * Cfg::KH / Cfg::KSPLIT, u1 = (ks + 1) * Cfg::KH / Cfg::KSPLIT;
+        const float *xp = sx + p * Cfg::XPL, *kp = sk + p * Cfg::KPL;
+        float acc[Cfg::WO];
+#pragma unroll
+        for (int c = 0; c < Cfg::WO; ++c) acc[c] = 0.f;
+        row_accumulate<Cfg>(xp, kp, lane, u0, u1, acc);
+        float e = 0.f, e32 = 0.f;  // out[32][lane], partial of out[32][32]
+#pragma unroll 1
+        for (int u = u0; u < u1; ++u) {
+            const float *xr = xp + (32 + u) * Cfg::WX;
+            const float *kr = kp + u * Cfg::KW;
+#pragma unroll
+            for (int v = 0; v < Cfg::KW; ++v) e = fmaf(xr[lane + v], kr[v], e);
+            if (lane < Cfg::KW) e32 = fmaf(xr[32 + lane], kr[lane], e32);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) e32 += __shfl_xor_sync(0xffffffffu, e32, off);
+        float *o = so + p * Cfg::OPL;
+#pragma unroll 1
+        for (int s = 0; s < Cfg::KSPLIT; ++s) {
+            if (s == ks) {
+                if (s == 0) {
+#pragma unroll
+                    for (int c = 0; c < Cfg::WO; ++c) o[lane * Cfg::WO + c] = acc[c];
+                    o[32 * Cfg::WO + lane] = e;
+                    if (lane == 0) o[32 * Cfg::WO + 32] = e32;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < Cfg::WO; ++c) o[lane * Cfg::WO + c] += acc[c];
+                    o[32 * Cfg::WO + lane] += e;
+                    if (lane == 0) o[32 * Cfg::WO + 32] += e32;
+                }
+            }
+            if (s + 1 < Cfg::KSPLIT) __syncthreads();
+        }
+    }
+}
+
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::NT, 1)
+    xcorr_staged_kernel(XProblems P, int groups_per_problem, int n_groups, int C, long long k_bstride) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *sin = reinterpret_cast<float *>(smem_raw);
+    float *sout = sin + Cfg::STAGES * Cfg::STAGE_FLOATS;
+    uint64_t *full = reinterpret_cast<uint64_t *>(sout + 2 * Cfg::OUT_FLOATS);
+    const int tid = threadIdx.x;
+
+    if (tid == 0) {
+        for (int s = 0; s < Cfg::STAGES; ++s) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int stage, int g) {  // elected thread only
+        const int prob = g / groups_per_problem;
+        const long long plane0 = (long long)(g - prob * groups_per_problem) * Cfg::G;
+        const long long b = plane0 / C, c0 = plane0 - b * C;
+        float *dst = sin + stage * Cfg::STAGE_FLOATS;
+        mbar_expect_tx(&full[stage], Cfg::STAGE_FLOATS * 4);
+        bulk_g2s(dst, P.x[prob] + plane0 * Cfg::XPL, Cfg::G * Cfg::XPL * 4, &full[stage]);
+        bulk_g2s(dst + Cfg::G * Cfg::XPL, P.k[prob] + b * k_bstride + c0 * Cfg::KPL, Cfg::G * Cfg::KPL * 4, &full[stage]);
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < Cfg::STAGES; ++s) {
+            const int g = blockIdx.x + s * gridDim.x;
+            if (g < n_groups) issue(s, g);
+        }
+    }
+
+    int it = 0;
+    for (int g = blockIdx.x; g < n_groups; g += gridDim.x, ++it) {
+        const int s = it % Cfg::STAGES;
+        mbar_wait(&full[s], (it / Cfg::STAGES) & 1);
+        const float *sx = sin + s * Cfg::STAGE_FLOATS;
+        float *so = sout + (it & 1) * Cfg::OUT_FLOATS;
+        compute_group<Cfg>(sx, sx + Cfg::G * Cfg::XPL, so, tid);
+        if (tid == 0) bulk_wait_read<0>();  // store of iteration it-1 has left its buffer (reused at it+1)
+        fence_proxy_async_smem();           // my so[] writes -> visible to the TMA store
+        __syncthreads();                    // all rows written; all reads of stage s finished
+        if (tid == 0) {
+            const int prob = g / groups_per_problem;
+            const long long plane0 = (long long)(g - prob * groups_per_problem) * Cfg::G;
+            bulk_s2g(P.out[prob] + plane0 * Cfg::OPL, so, Cfg::OUT_FLOATS * 4);
+            bulk_commit();
+            const int gn = g + Cfg::STAGES * gridDim.x;
+            if (gn < n_groups) issue(s, gn);
+        }
+    }
+    if (tid == 0) bulk_wait_all<0>();
+}
+
+// Any shape, any alignment: one thread per output element, straight from global memory.
+__global__ void xcorr_generic_kernel(XProblems P, int nprob, int B, int C, int Hx, int Wx, int Hk, int Wk, int ph, int pw, int Ho, int Wo,
+                                     long long k_bstride, long long plane_begin) {
+    const long long planes = (long long)B * C - plane_begin;
+    const long long per_prob = planes * Ho * Wo;
+    const long long total = per_prob * nprob;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int prob = (int)(e / per_prob);
+        long long r = e - prob * per_prob;
+        const int j = (int)(r % Wo);
+        r /= Wo;
+        const int i = (int)(r % Ho);
+        const long long plane = r / Ho + plane_begin;
+        const long long b = plane / C, c = plane - b * C;
+        const float *xp = P.x[prob] + plane * Hx * Wx;
+        const float *kp = P.k[prob] + b * k_bstride + c * Hk * Wk;
+        float acc = 0.f;
+        for (int u = 0; u < Hk; ++u) {
+            int rr = i + u - ph;
+            if (ph) rr = ((rr % Hx) + Hx) % Hx;
+            for (int v = 0; v < Wk; ++v) {
+                int cc = j + v - pw;
+                cc = cc < 0 ? 0 : (cc > Wx - 1 ? Wx - 1 : cc);
+                acc = fmaf(__ldg(xp + rr * Wx + cc), __ldg(kp + u * Wk + v), acc);
+            }
+        }
+        P.out[prob][(plane * Ho + i) * Wo + j] = acc;
+    }
+}
+
+template <class Cfg>
+static int launch_staged(const XProblems &P, int n, int B, int C, long long kbs, cudaStream_t st) {
+    static bool configured = false;  // benign race: idempotent attribute set
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(xcorr_staged_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    const int gpp = (int)(((long long)B * C) / Cfg::G);
+    const int total = gpp * n;
+    const int grid = total < sm_count() ? total : sm_count();
+    xcorr_staged_kernel<Cfg><<<grid, Cfg::NT, Cfg::SMEM, st>>>(P, gpp, total, C, kbs);
+    count_launch();
+    return launch_status();
+}
+
+//                       KH  KW  HX  WX  circ   G   NT  ST KS spill
+using CfgNative = XCfg<5, 5, 29, 29, false, 12, 320, 3, 1, false>;     // 127/255 crops (HBM-bound)
+using CfgNativeLp = XCfg<13, 13, 13, 13, true, 32, 416, 3, 1, false>;  // lp branch, 127 crops
+using Cfg256 = XCfg<29, 29, 61, 61, false, 4, 256, 2, 2, true>;        // 256/512 crops (FMA-bound)
+using Cfg256Lp = XCfg<29, 29, 29, 29, true, 8, 256, 2, 1, false>;      // lp branch, INSTANCE_SIZE=512
+using CfgWin15 = XCfg<15, 15, 39, 39, false, 8, 224, 2, 1, false>;     // 15x15 window sweep
+
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int xcorr_dispatch(const XProblems &P, int n, int B, int C, int Hx, int Wx, int Hk, int Wk, int circular, long long kbs,
+                          cudaStream_t st) {
+    bool fast = true;
+    for (int i = 0; i < n; ++i) fast = fast && aligned16(P.x[i]) && aligned16(P.k[i]) && aligned16(P.out[i]);
+    fast = fast && (kbs == 0 || kbs == (long long)C * Hk * Wk);
+#define HDN_TRY(CFG)                                                                                                               \
+    if (fast && Hk == CFG::KH && Wk == CFG::KW && Hx == CFG::HX && Wx == CFG::WX && (circular != 0) == CFG::CIRC && C % CFG::G == 0) \
+        return launch_staged<CFG>(P, n, B, C, kbs, st);
+    HDN_TRY(CfgNative)
+    HDN_TRY(CfgNativeLp)
+    HDN_TRY(Cfg256)
+    HDN_TRY(Cfg256Lp)
+    HDN_TRY(CfgWin15)
+#undef HDN_TRY
+    const int ph = circular ? Hx / 2 : 0, pw = circular ? Wx / 2 : 0;
+    const int Ho = Hx + 2 * ph - Hk + 1, Wo = Wx + 2 * pw - Wk + 1;
+    const long long total = (long long)n * B * C * Ho * Wo;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    xcorr_generic_kernel<<<(int)blocks, 256, 0, st>>>(P, n, B, C, Hx, Wx, Hk, Wk, ph, pw, Ho, Wo, kbs, 0);
+    count_launch();
+    return launch_status();
+}
+
+}  // namespace hdn
+
+using namespace hdn;
+
+extern "C" int hdn_xcorr_dw_multi_f32(int n, const float *const *x_host, const float *const *k_host, float *const *out_host, int B, int C,
+                                      int Hx, int Wx, int Hk, int Wk, int circular, int64_t k_batch_stride, hdn_stream_t stream) {
+    if (!x_host || !k_host || !out_host) return HDN_ERR_NULL;
+    if (n < 1 || n > HDN_MAX_PROBLEMS) return HDN_ERR_UNSUPPORTED;
+    if (B < 1 || C < 1 || Hx < 1 || Wx < 1 || Hk < 1 || Wk < 1) return HDN_ERR_SHAPE;
+    const int ph = circular ? Hx / 2 : 0, pw = circular ? Wx / 2 : 0;
+    if (Hk > Hx + 2 * ph || Wk > Wx + 2 * pw) return HDN_ERR_SHAPE;
+    if (k_batch_stride != 0 && k_batch_stride < (int64_t)C * Hk * Wk) return HDN_ERR_SHAPE;
+    XProblems P;
+    for (int i = 0; i < n; ++i) {
+        if (!x_host[i] || !k_host[i] || !out_host[i]) return HDN_ERR_NULL;
+        if ((reinterpret_cast<uintptr_t>(x_host[i]) | reinterpret_cast<uintptr_t>(k_host[i]) | reinterpret_cast<uintptr_t>(out_host[i])) & 3u)
+            return HDN_ERR_ALIGN;
+        P.x[i] = x_host[i];
+        P.k[i] = k_host[i];
+        P.out[i] = out_host[i];
+    }
+    for (int i = n; i < HDN_MAX_PROBLEMS; ++i) P.x[i] = P.k[i] = P.out[i] = nullptr;
+    return xcorr_dispatch(P, n, B, C, Hx, Wx, Hk, Wk, circular, (long long)k_batch_stride, (cudaStream_t)stream);
+}
+
+extern "C" int hdn_xcorr_dw_f32(const float *x, const float *k, float *out, int B, int C, int Hx, int Wx, int Hk, int Wk, int circular,
+                                int64_t k_batch_stride, hdn_stream_t stream) {
+    return hdn_xcorr_dw_multi_f32(1, &x, &k, &out, B, C, Hx, Wx, Hk, Wk, circular, k_batch_stride, stream);
+}

@@ -1,0 +1,236 @@
+"""Drop-in operators: the reference's names and signatures on top of libhdn_b200's C ABI.
+
+Each callable replaces the reference function cited in its docstring; torch is used only for
+device memory and the current stream.  CPU tensors are rejected -- there is no CPU fallback.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+
+_vp = ctypes.c_void_p
+
+
+def _stream():
+    return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev(t, name, dtype=torch.float32):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise RuntimeError("%s is on %s: hdn_b200 kernels run on CUDA only (no CPU fallback)" % (name, t.device))
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def _ptr(t):
+    return _vp(t.data_ptr())
+
+
+def xcorr_out_hw(Hx, Wx, Hk, Wk, circular):
+    ph, pw = (Hx // 2, Wx // 2) if circular else (0, 0)
+    return Hx + 2 * ph - Hk + 1, Wx + 2 * pw - Wk + 1
+
+
+def _xcorr(x, kernel, circular, out=None):
+    x, kernel = _dev(x, "x"), _dev(kernel, "kernel")
+    if x.dim() != 4 or kernel.dim() != 4:
+        raise RuntimeError("xcorr expects 4-D NCHW tensors")
+    B, C, Hx, Wx = x.shape
+    Bk, Ck, Hk, Wk = kernel.shape
+    if Ck != C or (Bk != B and Bk != 1):
+        raise RuntimeError("xcorr: x %s and kernel %s disagree in batch/channels" % (tuple(x.shape), tuple(kernel.shape)))
+    Ho, Wo = xcorr_out_hw(Hx, Wx, Hk, Wk, circular)
+    if Ho < 1 or Wo < 1:
+        raise RuntimeError("xcorr: kernel %dx%d larger than (padded) input %dx%d" % (Hk, Wk, Hx, Wx))
+    if out is None:
+        out = torch.empty((B, C, Ho, Wo), device=x.device, dtype=torch.float32)
+    kbs = 0 if (Bk == 1 and B > 1) else C * Hk * Wk
+    st = _lib.lib().hdn_xcorr_dw_f32(_ptr(x), _ptr(kernel), _ptr(out), B, C, Hx, Wx, Hk, Wk, int(circular), kbs, _stream())
+    _lib.check(st, "hdn_xcorr_dw_f32")
+    return out
+
+
+def xcorr_depthwise(x, kernel, out=None):
+    """hdn/core/xcorr.py:37-46.  x [B,C,Hx,Wx], kernel [B,C,h,w] (or [1,C,h,w] = template shared by the batch)."""
+    return _xcorr(x, kernel, False, out)
+
+
+def xcorr_depthwise_circular(x, kernel, out=None):
+    """hdn/core/xcorr.py:48-61: rows wrap by H//2, columns replicate by W//2, then depth-wise correlation."""
+    return _xcorr(x, kernel, True, out)
+
+
+def xcorr_depthwise_multi(xs, kernels, circular=False, outs=None):
+    """n <= 8 same-shape correlations in ONE launch (the 3 levels x {cls,loc} loop of MultiBAN.forward,
+    hdn/models/head/ban.py:102-127 / ban_lp.py:65-92)."""
+    n = len(xs)
+    xs = [_dev(x, "x") for x in xs]
+    kernels = [_dev(k, "kernel") for k in kernels]
+    B, C, Hx, Wx = xs[0].shape
+    Bk, _, Hk, Wk = kernels[0].shape
+    for x, k in zip(xs, kernels):
+        if tuple(x.shape) != (B, C, Hx, Wx) or tuple(k.shape) != (Bk, C, Hk, Wk):
+            raise RuntimeError("xcorr_depthwise_multi: all problems must share one shape")
+    Ho, Wo = xcorr_out_hw(Hx, Wx, Hk, Wk, circular)
+    if outs is None:
+        outs = [torch.empty((B, C, Ho, Wo), device=xs[0].device, dtype=torch.float32) for _ in range(n)]
+    arr = _vp * n
+    kbs = 0 if (Bk == 1 and B > 1) else C * Hk * Wk
+    st = _lib.lib().hdn_xcorr_dw_multi_f32(n, arr(*[x.data_ptr() for x in xs]), arr(*[k.data_ptr() for k in kernels]),
+                                           arr(*[o.data_ptr() for o in outs]), B, C, Hx, Wx, Hk, Wk, int(circular), kbs, _stream())
+    _lib.check(st, "hdn_xcorr_dw_multi_f32")
+    return outs
+
+
+def logpolar_sample(x, polar=None, rot_delta=0.0, out_size=None, out=None):
+    """Functional form of STN_Polar.forward (hdn/models/logpolar.py:120-134)."""
+    x = _dev(x, "x")
+    B, Ch, H, W = x.shape
+    S = int(out_size)
+    if polar is not None:
+        polar = _dev(polar, "polar")
+        if tuple(polar.shape) != (B, 2):
+            raise RuntimeError("polar must be [B,2]")
+    if out is None:
+        out = torch.empty((B, Ch, S, S), device=x.device, dtype=torch.float32)
+    st = _lib.lib().hdn_logpolar_f32(_ptr(x), _ptr(polar) if polar is not None else None, float(rot_delta), _ptr(out), B, Ch, H, W, S,
+                                     _stream())
+    _lib.check(st, "hdn_logpolar_f32")
+    return out
+
+
+class STN_Polar(torch.nn.Module):
+    """hdn/models/logpolar.py:50-134.  forward(x, polar, delta=[0,0]) -> (x_lp, grid).
+
+    The sampling grid is analytic inside the kernel, so nothing is built on the host or uploaded.
+    `grid` (which no caller on the tracking path reads) is returned only when `return_grid` is set,
+    and is then produced by the same formulas with torch ops on the device."""
+
+    def __init__(self, image_sz, return_grid=False):
+        super().__init__()
+        self._orignal_sz = [image_sz // 2, image_sz // 2]
+        self.return_grid = return_grid
+
+    def forward(self, x, polar, delta=[0, 0]):
+        S = self._orignal_sz[0]
+        out = logpolar_sample(x, polar, float(delta[1]), S)
+        grid = self._grid(x, polar, float(delta[1])) if self.return_grid else None
+        return out, grid
+
+    def _grid(self, x, polar, rot):
+        S = self._orignal_sz[0]
+        dev = x.device
+        j = torch.arange(S, device=dev, dtype=torch.float32)
+        rho = torch.exp(math.log(S / 2) / S * j) - 1.0
+        th = j * 2.0 * math.pi / S + rot
+        gx = rho[None, :] * torch.cos(th)[:, None]
+        gy = rho[None, :] * torch.sin(th)[:, None]
+        gx = gx[None] + polar[:, 0].reshape(-1, 1, 1)
+        gy = gy[None] + polar[:, 1].reshape(-1, 1, 1)
+        return torch.stack((gx / (x.size(2) // 2), gy / (x.size(3) // 2)), 3)
+
+
+def DLT_solve(src_p, off_set):
+    """Oneline_DLTv1/utils.py:7-67 for 8-vectors: src_p, off_set [B,8] -> H [B,1,3,3]."""
+    src_p, off_set = _dev(src_p, "src_p"), _dev(off_set, "off_set")
+    if src_p.dim() != 2 or src_p.shape[1] != 8 or tuple(off_set.shape) != tuple(src_p.shape):
+        raise RuntimeError("DLT_solve: only the 4-point (8-vector) form is implemented; got %s / %s" % (tuple(src_p.shape), tuple(off_set.shape)))
+    B = src_p.shape[0]
+    H = torch.empty((B, 1, 3, 3), device=src_p.device, dtype=torch.float32)
+    _lib.check(_lib.lib().hdn_dlt4_f32(_ptr(src_p), _ptr(off_set), _ptr(H), B, _stream()), "hdn_dlt4_f32")
+    return H
+
+
+def _m9(t):
+    """[...,3,3] tensor (batch-expanded constant) -> ctypes float[9] from its first matrix (one tiny D2H if on device)."""
+    m = t.reshape(-1, 3, 3)[0].detach().to("cpu", torch.float32).reshape(9).tolist()
+    return (ctypes.c_float * 9)(*m)
+
+
+_M_CACHE = {}
+
+
+def _m9_cached(t):
+    # M / M^-1 are per-model constants; cache by storage so the D2H read happens once, not per frame.
+    key = (t.data_ptr(), t._version, tuple(t.shape), str(t.device))
+    v = _M_CACHE.get(key)
+    if v is None:
+        if len(_M_CACHE) > 64:
+            _M_CACHE.clear()
+        v = _M_CACHE[key] = _m9(t)
+    return v
+
+
+def homo_warp(I1, H_mat, M=None, M_inv=None, out=None):
+    """Projective warp core of `transform` (identity patch_indices). M / M_inv: python lists of 9 floats or None."""
+    I1, H_mat = _dev(I1, "I1"), _dev(H_mat, "H_mat")
+    B, Ch, H, W = I1.shape
+    if H_mat.numel() != B * 9:
+        raise RuntimeError("H_mat must hold one 3x3 per batch item")
+    if out is None:
+        out = torch.empty_like(I1)
+    mp = (ctypes.c_float * 9)(*M) if M is not None and not isinstance(M, ctypes.Array) else M
+    mip = (ctypes.c_float * 9)(*M_inv) if M_inv is not None and not isinstance(M_inv, ctypes.Array) else M_inv
+    st = _lib.lib().hdn_homo_warp_f32(_ptr(I1), _ptr(H_mat), mp, mip, _ptr(out), B, Ch, H, W, _stream())
+    _lib.check(st, "hdn_homo_warp_f32")
+    return out
+
+
+def dlt_warp(src_p, off_set, I1, M=None, M_inv=None):
+    """K5 + K4 in one launch (what track_proj does back to back, model_builder...py:195-210). -> (H [B,3,3], warped)."""
+    src_p, off_set, I1 = _dev(src_p, "src_p"), _dev(off_set, "off_set"), _dev(I1, "I1")
+    B, Ch, H, W = I1.shape
+    Hm = torch.empty((B, 3, 3), device=I1.device, dtype=torch.float32)
+    out = torch.empty_like(I1)
+    mp = (ctypes.c_float * 9)(*M) if M is not None else None
+    mip = (ctypes.c_float * 9)(*M_inv) if M_inv is not None else None
+    st = _lib.lib().hdn_dlt_warp_f32(_ptr(src_p), _ptr(off_set), _ptr(I1), mp, mip, _ptr(Hm), _ptr(out), B, Ch, H, W, _stream())
+    _lib.check(st, "hdn_dlt_warp_f32")
+    return Hm, out
+
+
+def transform(patch_size_h, patch_size_w, M_tile_inv, H_mat, M_tile, I1, patch_indices, batch_indices_tensor):
+    """Oneline_DLTv1/utils.py:257-274.  Same arguments and result ([B,C,ph,pw]).
+
+    `patch_indices=None` (or a tensor tagged `_hdn_identity`) declares the arange(H*W) indices the tracker always
+    passes (get_img_info.py:92): the trailing gather is then the identity and is skipped.  Any other index tensor
+    is honoured with a device-side gather."""
+    B, Ch, H, W = I1.shape
+    warped = homo_warp(I1, H_mat, _m9_cached(M_tile), _m9_cached(M_tile_inv))
+    if patch_indices is None or getattr(patch_indices, "_hdn_identity", False):
+        if patch_size_h * patch_size_w != H * W:
+            raise RuntimeError("identity patch_indices need patch size == image size")
+        return warped.reshape(B, Ch, patch_size_h, patch_size_w)
+    flat = warped.permute(0, 2, 3, 1).reshape(-1, Ch)
+    pix = patch_indices.reshape(-1).long().to(flat.device) + batch_indices_tensor.to(flat.device)
+    return flat.index_select(0, pix).reshape(B, patch_size_h, patch_size_w, Ch).permute(0, 3, 1, 2)
+
+
+def score_argmax(cls, loc, window=None, win_influence=0.0):
+    """K6: fused _convert_score + window blend + np.argmax + column read (hdn_tracker.py:82-89,
+    hdn_tracker_proj_e2e.py:172-174, base_tracker.py:54-59).
+    cls [B,2,N,N], loc [B,L,N,N], window float64 [N*N] on device or None.
+    -> idx int64 [B], pscore float64 [B], score float32 [B], gathered float32 [B,L] (all on device)."""
+    cls, loc = _dev(cls, "cls"), _dev(loc, "loc")
+    B, two, N, N2 = cls.shape
+    if two != 2 or N != N2 or loc.shape[0] != B or tuple(loc.shape[2:]) != (N, N):
+        raise RuntimeError("score_argmax: cls must be [B,2,N,N] and loc [B,L,N,N]")
+    L = loc.shape[1]
+    if window is not None:
+        window = _dev(window, "window", torch.float64)
+        if window.numel() != N * N:
+            raise RuntimeError("window must have N*N entries")
+    dev = cls.device
+    idx = torch.empty(B, device=dev, dtype=torch.int64)
+    ps = torch.empty(B, device=dev, dtype=torch.float64)
+    sc = torch.empty(B, device=dev, dtype=torch.float32)
+    g = torch.empty((B, L), device=dev, dtype=torch.float32)
+    st = _lib.lib().hdn_score_argmax_f32(_ptr(cls), _ptr(loc), _ptr(window) if window is not None else None, float(win_influence), _ptr(idx),
+                                         _ptr(ps), _ptr(sc), _ptr(g), B, L, N, _stream())
+    _lib.check(st, "hdn_score_argmax_f32")
+    return idx, ps, sc, g

@@ -1,0 +1,102 @@
+/*
+ * hdn_b200.h -- C ABI of libhdn_b200.so: the B200 (sm_100a) kernels behind HDN's
+ * per-frame homography hot path.
+ *
+ * The reference (zhanxinrui/HDN) has no FFI layer: its operator boundary is a
+ * set of Python callables on torch tensors.  Each entry point below replaces
+ * one of them; the Python drop-ins that bind these symbols with the
+ * reference's own names and signatures live in hdn_b200/ops.py and
+ * hdn_b200/compat/ (see INTEGRATION.md for the stub a maintainer would add).
+ *
+ * Conventions
+ *   - All tensor pointers are DEVICE pointers to contiguous NCHW fp32 unless
+ *     the parameter name ends in _host.  The caller owns every buffer.
+ *   - Every launcher is asynchronous on the caller's stream (a cudaStream_t
+ *     passed as void*; NULL = legacy default stream) and re-entrant.
+ *   - Return value: 0 on success, a negative hdn_status for a rejected
+ *     argument (nothing was launched), or a positive cudaError_t if the launch
+ *     itself failed.  No function throws, exits or prints.
+ */
+#ifndef HDN_B200_H
+#define HDN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HDN_ABI_VERSION 1
+#define HDN_MAX_PROBLEMS 8
+
+typedef void *hdn_stream_t;
+
+enum hdn_status {
+    HDN_OK = 0,
+    HDN_ERR_NULL = -1,        /* a required pointer is NULL */
+    HDN_ERR_SHAPE = -2,       /* non-positive size, kernel larger than (padded) input, ... */
+    HDN_ERR_ALIGN = -3,       /* pointer not 4-byte aligned */
+    HDN_ERR_UNSUPPORTED = -4, /* argument combination not implemented */
+    HDN_ERR_DEVICE = -5       /* no sm_100 device / driver failure */
+};
+
+int hdn_abi_version(void);
+const char *hdn_status_string(int status);
+/* SM count and compute capability of the current device. */
+int hdn_device_info(int *sm_count, int *cc_major, int *cc_minor);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+int64_t hdn_launch_count(void);
+
+/* K1 + K2.  Replaces hdn/core/xcorr.py:37-46 xcorr_depthwise (circular = 0) and
+ * hdn/core/xcorr.py:48-61 xcorr_depthwise_circular (circular = 1; rows wrap by
+ * Hx/2, columns replicate by Wx/2, no padded copy is materialised).
+ *   x   [B,C,Hx,Wx]      k [B,C,Hk,Wk] with batch stride k_batch_stride elements
+ *   out [B,C,Ho,Wo]      (0 = one template shared by the batch, C*Hk*Wk = dense)
+ *   Ho = Hx + 2*(circular ? Hx/2 : 0) - Hk + 1, likewise Wo.
+ *   out[b,c,i,j] = sum_{u,v} xpad[b,c,i+u,j+v] * k[b,c,u,v]   (no flip, stride 1) */
+int hdn_xcorr_dw_f32(const float *x, const float *k, float *out, int B, int C, int Hx, int Wx, int Hk, int Wk, int circular,
+                     int64_t k_batch_stride, hdn_stream_t stream);
+
+/* The same operator for n <= HDN_MAX_PROBLEMS problems of identical shape in ONE launch
+ * (the 3 levels x {cls,loc} correlations of MultiBAN.forward, hdn/models/head/ban.py:102-127,
+ * and of MultiCircBAN.forward, ban_lp.py:65-92).  x_host/k_host/out_host are HOST arrays of n device pointers. */
+int hdn_xcorr_dw_multi_f32(int n, const float *const *x_host, const float *const *k_host, float *const *out_host, int B, int C, int Hx,
+                           int Wx, int Hk, int Wk, int circular, int64_t k_batch_stride, hdn_stream_t stream);
+
+/* K3.  Replaces hdn/models/logpolar.py:50-134 STN_Polar.forward: analytic log-polar
+ * grid (rows = angle, cols = log-radius) + bilinear border sampling, align_corners=False.
+ *   img [B,Ch,H,W] -> out [B,Ch,S,S];  S = INSTANCE_SIZE//2;  polar [B,2] or NULL (= zeros);
+ *   rot_delta = delta[1] of the reference call. */
+int hdn_logpolar_f32(const float *img, const float *polar, float rot_delta, float *out, int B, int Ch, int H, int W, int S,
+                     hdn_stream_t stream);
+
+/* K5.  Replaces Oneline_DLTv1/utils.py:7-67 DLT_solve for 8-vectors (one quad per item).
+ *   src4, off4 [B,8] (x0,y0,...,x3,y3) -> Hm [B,9] row-major 3x3 with Hm[8] = 1. */
+int hdn_dlt4_f32(const float *src4, const float *off4, float *Hm, int B, hdn_stream_t stream);
+
+/* K4.  Replaces Oneline_DLTv1/utils.py:257-274 transform (-> transformer :70-254) for the
+ * identity patch_indices the tracker passes (get_img_info.py:92).
+ *   img [B,Ch,H,W], Hm [B,9] -> out [B,Ch,H,W];  theta = (Minv Hm) M.
+ *   M_host / Minv_host: HOST float[9] (the reference passes M = [[63.5,0,63.5],[0,63.5,63.5],[0,0,1]]
+ *   and torch.inverse(M), model_builder_e2e_unconstrained_v2.py:196-205); NULL = built from W/2, H/2. */
+int hdn_homo_warp_f32(const float *img, const float *Hm, const float *M_host, const float *Minv_host, float *out, int B, int Ch, int H,
+                      int W, hdn_stream_t stream);
+
+/* K5 + K4 in one launch: offsets -> H -> warped image (what ModelBuilder.track_proj does back to back,
+ * model_builder_e2e_unconstrained_v2.py:195-210).  Hm [B,9] is also written. */
+int hdn_dlt_warp_f32(const float *src4, const float *off4, const float *img, const float *M_host, const float *Minv_host, float *Hm,
+                     float *out, int B, int Ch, int H, int W, hdn_stream_t stream);
+
+/* K6.  Replaces the device->host->NumPy epilogue: hdn/tracker/hdn_tracker.py:82-89 _convert_score,
+ * hdn_tracker_proj_e2e.py:172-174 window blend + np.argmax, and the column read of
+ * base_tracker.py:54-59 _convert_c / hdn_tracker.py:51-67 _convert_logpolar_simi.
+ *   cls [B,2,N,N], loc [B,L,N,N], window [N*N] float64 or NULL (lp branch: no window)
+ *   idx [B] int64 (first maximum), pscore [B] float64 (the value the 0.05 / 0.25 gates test),
+ *   score [B] fp32 softmax p(fg) at idx ('best_score'), gathered [B,L] = loc[b,:,idx]. */
+int hdn_score_argmax_f32(const float *cls, const float *loc, const double *window, double win_influence, int64_t *idx, double *pscore,
+                         float *score, float *gathered, int B, int L, int N, hdn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HDN_B200_H */

@@ -1,0 +1,74 @@
+"""CPU-only: the C-ABI library loads, exports every symbol include/hdn_b200.h declares, and rejects bad
+arguments before touching a device."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+from hdn_b200 import _lib, build
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()
+    return _lib.lib()
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "hdn_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(hdn_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(lib):
+    names = declared_symbols()
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(lib, n), "missing export " + n
+        assert n in _lib.SIGNATURES, "ctypes binding lacks " + n
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_version_and_status_strings(lib):
+    assert lib.hdn_abi_version() == 1
+    assert lib.hdn_status_string(0) == b"ok"
+    for code in (-1, -2, -3, -4, -5):
+        assert len(lib.hdn_status_string(code)) > 3
+    assert lib.hdn_launch_count() >= 0
+
+
+def test_argument_validation_without_device(lib):
+    null = ctypes.c_void_p(0)
+    one = ctypes.c_void_p(16)  # never dereferenced: validation fails first
+    assert lib.hdn_xcorr_dw_f32(null, one, one, 1, 4, 8, 8, 3, 3, 0, 36, null) == -1
+    assert lib.hdn_xcorr_dw_f32(one, one, one, 1, 4, 8, 8, 9, 3, 0, 108, null) == -2   # kernel larger than input
+    assert lib.hdn_xcorr_dw_f32(one, one, one, 0, 4, 8, 8, 3, 3, 0, 36, null) == -2
+    assert lib.hdn_xcorr_dw_f32(ctypes.c_void_p(18), one, one, 1, 4, 8, 8, 3, 3, 0, 36, null) == -3
+    assert lib.hdn_xcorr_dw_f32(one, one, one, 1, 4, 8, 8, 3, 3, 0, 7, null) == -2     # batch stride smaller than a template
+    assert lib.hdn_logpolar_f32(null, null, 0.0, one, 1, 1, 8, 8, 4, null) == -1
+    assert lib.hdn_logpolar_f32(one, null, 0.0, one, 1, 1, 8, 8, 1, null) == -2
+    assert lib.hdn_dlt4_f32(one, one, null, 1, null) == -1
+    assert lib.hdn_dlt4_f32(one, one, one, 0, null) == -2
+    assert lib.hdn_homo_warp_f32(one, null, None, None, one, 1, 1, 8, 8, null) == -1
+    assert lib.hdn_score_argmax_f32(one, one, null, 0.0, one, one, one, null, 1, 2, 5, null) == -1
+    with pytest.raises(ValueError):
+        _lib.check(-2, "x")
+
+
+def test_ops_reject_cpu_tensors():
+    import torch
+    from hdn_b200 import ops
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.xcorr_depthwise(torch.zeros(1, 4, 8, 8), torch.zeros(1, 4, 3, 3))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.DLT_solve(torch.zeros(1, 8), torch.zeros(1, 8))
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "SO_PATH", "/nonexistent/libhdn_b200.so")
+    with pytest.raises(_lib.HdnError, match="no CPU fallback"):
+        _lib.lib()

@@ -1,0 +1,239 @@
+"""GPU parity: the CUDA path (through the C ABI, via hdn_b200.ops) against
+  (1) goldens produced by the real reference (tests/golden/ops_*.npz),
+  (2) the C oracle on seeded inputs at sizes it finishes in seconds,
+  (3) size-independent properties at BASELINE.json's full sizes.
+Tolerances are SURVEY.md 8(d): rtol 1e-3, atol 1e-4*max|ref|; arg-max indices bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close, golden_names, load_golden, regen_image
+from oracle import c_oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def g2d(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def ops():
+    from hdn_b200 import ops as o
+    return o
+
+
+# ------------------------------------------------------------------ K1 / K2
+@pytest.mark.parametrize("name", golden_names("ops_k1_") + golden_names("ops_k2_"))
+def test_xcorr_golden(name):
+    g = load_golden(name)
+    fn = ops().xcorr_depthwise_circular if int(g["circular"]) else ops().xcorr_depthwise
+    out = fn(g2d(g["x"]), g2d(g["k"])).cpu().numpy()
+    assert_close(out, g["out"], what=name)
+
+
+FAST_SHAPES = [  # (B, C, Hx, Wx, Hk, Wk, circular)  -- the shapes with staged TMA kernels, C = 256 as in the network
+    (2, 256, 29, 29, 5, 5, 0),
+    (3, 256, 13, 13, 13, 13, 1),
+    (1, 256, 61, 61, 29, 29, 0),
+    (1, 256, 29, 29, 29, 29, 1),
+    (1, 256, 39, 39, 15, 15, 0),
+    (5, 24, 29, 29, 5, 5, 0),      # C % G == 0 with small C
+    (2, 20, 29, 29, 5, 5, 0),      # C % G != 0 -> generic kernel
+]
+
+
+@pytest.mark.parametrize("shape", FAST_SHAPES)
+@pytest.mark.parametrize("shared", [False, True])
+def test_xcorr_vs_oracle(shape, shared):
+    B, C, Hx, Wx, Hk, Wk, circ = shape
+    rng = np.random.default_rng(hash(shape) % 2**31)
+    x = rng.standard_normal((B, C, Hx, Wx)).astype(np.float32)
+    k = (rng.standard_normal((1 if shared else B, C, Hk, Wk)) * 0.1).astype(np.float32)
+    ref = c_oracle.xcorr_dw(x, k, bool(circ))
+    fn = ops().xcorr_depthwise_circular if circ else ops().xcorr_depthwise
+    out = fn(g2d(x), g2d(k)).cpu().numpy()
+    assert_close(out, ref, what=str(shape))
+
+
+def test_xcorr_multi_equals_single():
+    rng = np.random.default_rng(11)
+    xs = [g2d(rng.standard_normal((2, 256, 29, 29)).astype(np.float32)) for _ in range(6)]
+    ks = [g2d(rng.standard_normal((2, 256, 5, 5)).astype(np.float32)) for _ in range(6)]
+    multi = ops().xcorr_depthwise_multi(xs, ks)
+    for x, k, m in zip(xs, ks, multi):
+        assert torch.equal(ops().xcorr_depthwise(x, k), m)  # same kernel, same order -> bit-identical
+    xs = [g2d(rng.standard_normal((2, 256, 13, 13)).astype(np.float32)) for _ in range(6)]
+    multi = ops().xcorr_depthwise_multi(xs, xs, circular=True)
+    for x, m in zip(xs, multi):
+        assert torch.equal(ops().xcorr_depthwise_circular(x, x), m)
+
+
+def test_xcorr_unaligned_views_fall_back_correctly():
+    rng = np.random.default_rng(12)
+    buf = g2d(rng.standard_normal(2 * 256 * 29 * 29 + 1).astype(np.float32))
+    x = buf[1:].reshape(2, 256, 29, 29)  # 4-byte aligned only -> generic kernel
+    k = g2d(rng.standard_normal((2, 256, 5, 5)).astype(np.float32))
+    ref = c_oracle.xcorr_dw(x.cpu().numpy(), k.cpu().numpy())
+    assert_close(ops().xcorr_depthwise(x, k).cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("shape", [(64, 256, 61, 61, 29, 29, 0), (64, 256, 29, 29, 29, 29, 1), (64, 256, 29, 29, 5, 5, 0),
+                                   (64, 256, 13, 13, 13, 13, 1), (256, 256, 39, 39, 15, 15, 0)])
+def test_xcorr_full_size_properties(shape):
+    """BASELINE.json sizes (batch 64 / 256): one-hot kernels make the correlation an exact shifted crop,
+    and the operator is linear in x."""
+    B, C, Hx, Wx, Hk, Wk, circ = shape
+    fn = ops().xcorr_depthwise_circular if circ else ops().xcorr_depthwise
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    x = torch.randn((B, C, Hx, Wx), device=DEV, generator=gen)
+    u0, v0 = Hk // 3, Wk - 2
+    k = torch.zeros((B, C, Hk, Wk), device=DEV)
+    k[:, :, u0, v0] = 1.0
+    out = fn(x, k)
+    Ho, Wo = ops().xcorr_out_hw(Hx, Wx, Hk, Wk, circ)
+    assert tuple(out.shape) == (B, C, Ho, Wo)
+    if circ:
+        rows = (torch.arange(Ho, device=DEV) + u0 - Hx // 2) % Hx
+        cols = (torch.arange(Wo, device=DEV) + v0 - Wx // 2).clamp(0, Wx - 1)
+        expect = x[:, :, rows][:, :, :, cols]
+    else:
+        expect = x[:, :, u0:u0 + Ho, v0:v0 + Wo]
+    assert torch.equal(out, expect)  # 1.0 * x + 0 * ... is exact
+    # linearity with a dense kernel
+    k = torch.randn((B, C, Hk, Wk), device=DEV, generator=gen) * 0.1
+    x2 = torch.randn((B, C, Hx, Wx), device=DEV, generator=gen)
+    lhs = fn(2.0 * x + x2, k)
+    rhs = 2.0 * fn(x, k) + fn(x2, k)
+    assert torch.allclose(lhs, rhs, rtol=1e-3, atol=1e-4 * float(rhs.abs().max()))
+    # shared template == tiled template
+    assert torch.equal(fn(x, k[:1]), fn(x, k[:1].expand(B, C, Hk, Wk).contiguous()))
+
+
+# ------------------------------------------------------------------ K3
+@pytest.mark.parametrize("name", golden_names("ops_k3_"))
+def test_logpolar_golden(name):
+    g = load_golden(name)
+    img = regen_image(g)
+    S = int(g["inst"]) // 2
+    stn = ops().STN_Polar(int(g["inst"]))
+    out, grid = stn(g2d(img), g2d(g["polar"]), [0, float(g["delta"][1])])
+    assert grid is None and tuple(out.shape) == g["out"].shape
+    assert_close(out.cpu().numpy(), g["out"], what=name)
+    assert_close(out.cpu().numpy(), c_oracle.logpolar(img, g["polar"], float(g["delta"][1]), S), what=name + " vs C")
+
+
+def test_logpolar_full_size_affine_reproduction():
+    """[64,3,512,512] -> [64,3,256,256]: bilinear sampling reproduces an affine image exactly at the sample point."""
+    B, H, W, S = 64, 512, 512, 256
+    yy, xx = torch.meshgrid(torch.arange(H, device=DEV, dtype=torch.float32), torch.arange(W, device=DEV, dtype=torch.float32), indexing="ij")
+    img = torch.stack([0.5 * xx + 0.25 * yy, xx, yy]).unsqueeze(0).expand(B, 3, H, W).contiguous()
+    out = ops().logpolar_sample(img, None, 0.0, S)
+    assert tuple(out.shape) == (B, 3, S, S)
+    j = torch.arange(S, dtype=torch.float64)
+    rho = torch.exp(np.log(S / 2) / S * j) - 1
+    th = torch.arange(S, dtype=torch.float64) * 2 * np.pi / S
+    ix = (((rho[None] * torch.cos(th)[:, None]) / (H // 2) + 1) * W - 1) / 2
+    iy = (((rho[None] * torch.sin(th)[:, None]) / (W // 2) + 1) * H - 1) / 2
+    ix, iy = ix.clamp(0, W - 1), iy.clamp(0, H - 1)
+    got = out[7].double().cpu()
+    assert float((got[1] - ix).abs().max()) < 2e-3
+    assert float((got[2] - iy).abs().max()) < 2e-3
+    assert float((got[0] - (0.5 * ix + 0.25 * iy)).abs().max()) < 2e-3
+    assert torch.equal(out[0], out[63])
+    # grid option reproduces the reference's second return value shape
+    stn = ops().STN_Polar(512, return_grid=True)
+    _, grid = stn(img[:2], torch.zeros(2, 2, device=DEV))
+    assert tuple(grid.shape) == (2, S, S, 2)
+
+
+# ------------------------------------------------------------------ K5
+def test_dlt_golden_and_property():
+    from test_oracle_golden import reproject
+    g = load_golden("ops_k5_dlt")
+    H = ops().DLT_solve(g2d(g["src"]), g2d(g["off"]))
+    assert tuple(H.shape) == (16, 1, 3, 3)
+    got, ref = H[:, 0].cpu().numpy(), g["H"][:, 0]
+    assert np.allclose(got, ref, rtol=1e-3, atol=1e-5)
+    assert np.max(np.abs(reproject(got, g["src"]) - reproject(ref, g["src"]))) <= 1e-3 * 127
+    assert np.array_equal(got, c_oracle.dlt4(g["src"], g["off"]))  # same fp64 elimination order -> bit-identical
+    # full batch: H maps every source corner onto src + off
+    rng = np.random.default_rng(3)
+    B = 4096 + 3
+    src = np.tile(np.asarray([0, 0, 0, 127, 127, 127, 127, 0], np.float32), (B, 1))
+    off = rng.uniform(-8, 8, (B, 8)).astype(np.float32)
+    got = ops().DLT_solve(g2d(src), g2d(off))[:, 0].cpu().numpy()
+    assert np.max(np.abs(reproject(got, src) - (src + off).reshape(-1, 4, 2))) < 2e-3
+    assert np.all(got[:, 2, 2] == 1.0)
+
+
+# ------------------------------------------------------------------ K4
+@pytest.mark.parametrize("name", ["ops_k4_warp", "ops_k4_warp_small"])
+def test_homo_warp_golden(name):
+    from test_oracle_golden import _warp_mismatch_ok
+    g = load_golden(name)
+    M, Minv = (g["M"], g["M_inv"]) if "M" in g else c_oracle.default_M(127, 127)
+    out = ops().homo_warp(g2d(g["img"]), g2d(g["H"]), list(np.asarray(M).reshape(9)), list(np.asarray(Minv).reshape(9))).cpu().numpy()
+    _warp_mismatch_ok(out, g["out"], name)
+    ref = c_oracle.homo_warp(g["img"], g["H"], M, Minv)
+    assert np.mean(out != ref) < 1e-3, "GPU and C oracle follow the same fp32 operation order"
+    # the reference-signature entry point, with explicit (identity) patch indices -> general gather path
+    B, Ch, H, W = g["img"].shape
+    Mt = g2d(np.asarray(M, np.float32)).unsqueeze(0).expand(B, 3, 3)
+    Mit = g2d(np.asarray(Minv, np.float32)).unsqueeze(0).expand(B, 3, 3)
+    pidx = torch.arange(H * W, device=DEV, dtype=torch.float32).unsqueeze(0).expand(B, H * W)
+    bidx = (torch.arange(B, device=DEV) * H * W).unsqueeze(1).expand(B, H * W).reshape(-1)
+    via = ops().transform(H, W, Mit, g2d(g["H"]), Mt, g2d(g["img"]), pidx, bidx)
+    fast = ops().transform(H, W, Mit, g2d(g["H"]), Mt, g2d(g["img"]), None, None)
+    assert torch.equal(via, fast) and np.array_equal(fast.cpu().numpy(), out)
+
+
+def test_dlt_warp_fused_equals_two_step():
+    rng = np.random.default_rng(9)
+    B = 64
+    src = g2d(np.tile(np.asarray([0, 0, 0, 127, 127, 127, 127, 0], np.float32), (B, 1)))
+    off = g2d(rng.uniform(-8, 8, (B, 8)).astype(np.float32))
+    img = g2d(rng.standard_normal((B, 1, 127, 127)).astype(np.float32))
+    H1 = ops().DLT_solve(src, off)[:, 0]
+    w1 = ops().homo_warp(img, H1)
+    H2, w2 = ops().dlt_warp(src, off, img)
+    assert torch.equal(H1, H2) and torch.equal(w1, w2)
+    # zero offsets: identity H is a stretch by W/(W-1), last row / col ~ 0
+    H0, w0 = ops().dlt_warp(src[:1], torch.zeros_like(off[:1]), img[:1])
+    assert float(w0[0, 0, -1, :].abs().max()) < 1e-6 and float(w0[0, 0, :, -1].abs().max()) < 1e-6
+
+
+# ------------------------------------------------------------------ K6
+def test_score_argmax_golden():
+    g = load_golden("ops_k6_score")
+    idx, ps, sc, gath = ops().score_argmax(g2d(g["cls"]), g2d(g["loc"]), g2d(g["window"]), float(g["win_infl"]))
+    assert idx.dtype == torch.int64 and ps.dtype == torch.float64
+    assert np.array_equal(idx.cpu().numpy(), g["idx"])
+    assert np.allclose(ps.cpu().numpy(), g["pscore"], rtol=1e-6, atol=1e-7)
+    assert np.allclose(sc.cpu().numpy(), g["score"], rtol=1e-6, atol=1e-7)
+    centre = g["points"][g["idx"]] - 8.0 * gath.cpu().numpy()
+    assert np.allclose(centre, g["center"], rtol=1e-6, atol=1e-5)
+    g = load_golden("ops_k6_score_lp")
+    idx, ps, sc, gath = ops().score_argmax(g2d(g["cls"]), g2d(g["loc"]), None, 0.0)
+    assert np.array_equal(idx.cpu().numpy(), g["idx"])
+    assert np.allclose(sc.cpu().numpy(), g["score"], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("N,L,windowed", [(25, 2, True), (13, 4, False), (33, 2, True), (40, 3, True)])
+def test_score_argmax_vs_oracle_batch512(N, L, windowed):
+    rng = np.random.default_rng(N)
+    B = 512
+    cls = (rng.standard_normal((B, 2, N, N)) * 2).astype(np.float32)
+    loc = rng.standard_normal((B, L, N, N)).astype(np.float32)
+    cls[5] = 0.25  # exact ties everywhere
+    win = np.outer(np.hanning(N), np.hanning(N)).flatten() if windowed else None
+    w = 0.1632532824922313 if windowed else 0.0
+    ridx, rps, rsc, rg = c_oracle.score_argmax(cls, loc, win, w)
+    idx, ps, sc, gath = ops().score_argmax(g2d(cls), g2d(loc), g2d(win) if windowed else None, w)
+    assert np.array_equal(idx.cpu().numpy(), ridx)  # bit-exact index
+    assert np.array_equal(gath.cpu().numpy(), rg)
+    assert np.allclose(ps.cpu().numpy(), rps, rtol=1e-6, atol=1e-7)
+    assert np.allclose(sc.cpu().numpy(), rsc, rtol=1e-6, atol=1e-7)
+    if not windowed:
+        assert int(idx[5]) == 0  # first maximum wins a full tie
