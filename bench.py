@@ -90,7 +90,10 @@ class ClockSampler:
             self.proc.terminate()
 
     def summary(self, t0, t1):
-        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15 and len(r) >= 7] or [r for _, r in self.rows[-3:] if len(r) >= 7]
+        good = [(t, r) for t, r in self.rows if len(r) >= 7]
+        rows = [r for t, r in good if t0 <= t <= t1 + 0.1]
+        if not rows and good:  # timed region shorter than the sampling period: take the sample nearest to it
+            rows = [min(good, key=lambda tr: abs(tr[0] - 0.5 * (t0 + t1)))[1]]
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]

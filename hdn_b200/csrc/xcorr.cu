@@ -27,9 +27,9 @@ struct XProblems {
     float *out[HDN_MAX_PROBLEMS];
 };
 
-template <int KH_, int KW_, int HX_, int WX_, bool CIRC_, int G_, int NT_, int STAGES_, int KSPLIT_, bool SPILL_>
+template <int KH_, int KW_, int HX_, int WX_, bool CIRC_, int G_, int NT_, int STAGES_, int KSPLIT_, bool SPILL_, int CTAS_ = 1>
 struct XCfg {
-    static constexpr int KH = KH_, KW = KW_, HX = HX_, WX = WX_, G = G_, NT = NT_, STAGES = STAGES_, KSPLIT = KSPLIT_;
+    static constexpr int KH = KH_, KW = KW_, HX = HX_, WX = WX_, G = G_, NT = NT_, STAGES = STAGES_, KSPLIT = KSPLIT_, CTAS = CTAS_;
     static constexpr bool CIRC = CIRC_, SPILL = SPILL_;
     static constexpr int PH = CIRC ? HX / 2 : 0, PW = CIRC ? WX / 2 : 0;
     static constexpr int HO = HX + 2 * PH - KH + 1, WO = WX + 2 * PW - KW + 1;
@@ -39,7 +39,8 @@ struct XCfg {
     static constexpr size_t SMEM = (size_t)(STAGES * STAGE_FLOATS + 2 * OUT_FLOATS) * 4 + STAGES * 8 + 16;
     static_assert(G % 4 == 0, "bulk copies need 16-byte multiples");
     static_assert(!SPILL || (HO == 33 && NT == 32 * G * KSPLIT), "row-spill mapping is for 33-row outputs");
-    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+    static_assert(SMEM * CTAS <= 227 * 1024 - 1024 * CTAS, "shared memory budget");
+    static_assert(256 % G == 0, "G must divide the network's 256 channels or the staged path is never taken");
 };
 
 // Accumulate kernel rows [u0,u1) of output row i into acc[WO].
@@ -143,7 +144,7 @@ __device__ __forceinline__ void compute_group(const float *__restrict__ sx, cons
 }
 
 template <class Cfg>
-__global__ void __launch_bounds__(Cfg::NT, 1)
+__global__ void __launch_bounds__(Cfg::NT, Cfg::CTAS)
     xcorr_staged_kernel(XProblems P, int groups_per_problem, int n_groups, int C, long long k_bstride) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *sin = reinterpret_cast<float *>(smem_raw);
@@ -236,20 +237,30 @@ static int launch_staged(const XProblems &P, int n, int B, int C, long long kbs,
     }
     const int gpp = (int)(((long long)B * C) / Cfg::G);
     const int total = gpp * n;
-    const int grid = total < sm_count() ? total : sm_count();
+    const int slots = sm_count() * Cfg::CTAS;
+    const int grid = total < slots ? total : slots;
     xcorr_staged_kernel<Cfg><<<grid, Cfg::NT, Cfg::SMEM, st>>>(P, gpp, total, C, kbs);
     count_launch();
     return launch_status();
 }
 
 //                       KH  KW  HX  WX  circ   G   NT  ST KS spill
-using CfgNative = XCfg<5, 5, 29, 29, false, 12, 320, 3, 1, false>;     // 127/255 crops (HBM-bound)
+using CfgNative = XCfg<5, 5, 29, 29, false, 8, 224, 2, 1, false, 2>;   // 127/255 crops (HBM-bound), 2 CTAs/SM
 using CfgNativeLp = XCfg<13, 13, 13, 13, true, 32, 416, 3, 1, false>;  // lp branch, 127 crops
 using Cfg256 = XCfg<29, 29, 61, 61, false, 4, 256, 2, 2, true>;        // 256/512 crops (FMA-bound)
 using Cfg256Lp = XCfg<29, 29, 29, 29, true, 8, 256, 2, 1, false>;      // lp branch, INSTANCE_SIZE=512
 using CfgWin15 = XCfg<15, 15, 39, 39, false, 8, 224, 2, 1, false>;     // 15x15 window sweep
 
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static bool staged_applicable(int C, int Hx, int Wx, int Hk, int Wk, int circular, long long kbs) {
+    if (!(kbs == 0 || kbs == (long long)C * Hk * Wk)) return false;
+#define HDN_IS(CFG) \
+    if (Hk == CFG::KH && Wk == CFG::KW && Hx == CFG::HX && Wx == CFG::WX && (circular != 0) == CFG::CIRC && C % CFG::G == 0) return true;
+    HDN_IS(CfgNative) HDN_IS(CfgNativeLp) HDN_IS(Cfg256) HDN_IS(Cfg256Lp) HDN_IS(CfgWin15)
+#undef HDN_IS
+    return false;
+}
 
 static int xcorr_dispatch(const XProblems &P, int n, int B, int C, int Hx, int Wx, int Hk, int Wk, int circular, long long kbs,
                           cudaStream_t st) {
@@ -304,4 +315,8 @@ extern "C" int hdn_xcorr_dw_multi_f32(int n, const float *const *x_host, const f
 extern "C" int hdn_xcorr_dw_f32(const float *x, const float *k, float *out, int B, int C, int Hx, int Wx, int Hk, int Wk, int circular,
                                 int64_t k_batch_stride, hdn_stream_t stream) {
     return hdn_xcorr_dw_multi_f32(1, &x, &k, &out, B, C, Hx, Wx, Hk, Wk, circular, k_batch_stride, stream);
+}
+
+extern "C" int hdn_xcorr_is_staged(int C, int Hx, int Wx, int Hk, int Wk, int circular, int64_t k_batch_stride) {
+    return staged_applicable(C, Hx, Wx, Hk, Wk, circular, (long long)k_batch_stride) ? 1 : 0;
 }

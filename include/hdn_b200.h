@@ -63,6 +63,9 @@ int hdn_xcorr_dw_f32(const float *x, const float *k, float *out, int B, int C, i
 int hdn_xcorr_dw_multi_f32(int n, const float *const *x_host, const float *const *k_host, float *const *out_host, int B, int C, int Hx,
                            int Wx, int Hk, int Wk, int circular, int64_t k_batch_stride, hdn_stream_t stream);
 
+/* 1 if (shape, 16-byte aligned pointers) takes the TMA-staged kernel, 0 if it takes the generic one-thread-per-output kernel. */
+int hdn_xcorr_is_staged(int C, int Hx, int Wx, int Hk, int Wk, int circular, int64_t k_batch_stride);
+
 /* K3.  Replaces hdn/models/logpolar.py:50-134 STN_Polar.forward: analytic log-polar
  * grid (rows = angle, cols = log-radius) + bilinear border sampling, align_corners=False.
  *   img [B,Ch,H,W] -> out [B,Ch,S,S];  S = INSTANCE_SIZE//2;  polar [B,2] or NULL (= zeros);

@@ -72,3 +72,12 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "SO_PATH", "/nonexistent/libhdn_b200.so")
     with pytest.raises(_lib.HdnError, match="no CPU fallback"):
         _lib.lib()
+
+
+def test_network_shapes_take_the_staged_kernel(lib):
+    """The five shapes the network produces (C = 256) must hit the TMA-staged kernels, not the generic fallback."""
+    for Hx, Hk, circ in ((29, 5, 0), (13, 13, 1), (61, 29, 0), (29, 29, 1), (39, 15, 0)):
+        assert lib.hdn_xcorr_is_staged(256, Hx, Hx, Hk, Hk, circ, 256 * Hk * Hk) == 1, (Hx, Hk, circ)
+        assert lib.hdn_xcorr_is_staged(256, Hx, Hx, Hk, Hk, circ, 0) == 1            # shared template
+    assert lib.hdn_xcorr_is_staged(256, 31, 31, 5, 5, 0, 256 * 25) == 0               # not in the table
+    assert lib.hdn_xcorr_is_staged(20, 29, 29, 5, 5, 0, 20 * 25) == 0                 # C not a multiple of the group
