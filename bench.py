@@ -176,6 +176,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     B = a.batch or (256 if a.workload == "win15" else 64)
+    sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
+    if rank == 0:
+        sampler.start()  # before the (slow) input generation so nvidia-smi is already streaming when timing starts
     shared = (world > 1) if a.shared_template < 0 else bool(a.shared_template)
     full = a.workload != "win15"
 
@@ -232,10 +235,6 @@ def main():
             lambda: _lib.check(L.hdn_score_argmax_f32(p(inp["cls_lp"]), p(inp["loc_lp"]), None, 0.0, p(out["idx_lp"]), p(out["pscore_lp"]),
                                                       p(out["score_lp"]), p(out["sim_lp"]), B, 4, w["score_lp"], st()), "K6lp"),
         ]
-
-    sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
-    if rank == 0:
-        sampler.start()
 
     # ---- device-resident timed region --------------------------------------------------------------
     for _ in range(max(a.warmup, 3)):
