@@ -1,0 +1,97 @@
+"""Box-adaptive heads of the similarity branch -- mirror of hdn/models/head/ban.py (DepthwiseXCorr :51-78,
+DepthwiseBAN :81-90, MultiBAN :92-127).  UPChannelBAN is not mirrored (no shipped configuration uses it).
+
+Same module tree / state-dict keys (box{2,3,4}.{cls,loc}.{conv_kernel,conv_search,head}.*, cls_weight, loc_weight,
+loc_scale) and the same arithmetic, restructured for the GPU:
+  * the template side `conv_kernel(z_f)` depends only on the template, which is fixed between `template()` calls;
+    the reference recomputes it every frame (ban.py:74).  `MultiBAN.prepare(z_fs)` computes the 6 kernels once;
+  * the 3 levels x {cls, loc} correlations have one shape, so they go out as ONE `xcorr_depthwise_multi` launch
+    (hdn_xcorr_dw_multi_f32) instead of 6 grouped-conv calls.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from hdn.core.xcorr import xcorr_depthwise, xcorr_depthwise_multi
+
+
+class BAN(nn.Module):
+    def forward(self, z_f, x_f):
+        raise NotImplementedError
+
+
+def _conv_bn_relu(cin, cout, k):
+    return nn.Sequential(nn.Conv2d(cin, cout, kernel_size=k, bias=False), nn.BatchNorm2d(cout), nn.ReLU(inplace=True))
+
+
+class DepthwiseXCorr(nn.Module):
+    correlate = staticmethod(xcorr_depthwise)
+    circular = False
+
+    def __init__(self, in_channels, hidden, out_channels, kernel_size=3):
+        super().__init__()
+        self.conv_kernel = _conv_bn_relu(in_channels, hidden, kernel_size)
+        self.conv_search = _conv_bn_relu(in_channels, hidden, kernel_size)
+        self.head = nn.Sequential(nn.Conv2d(hidden, hidden, kernel_size=1, bias=False), nn.BatchNorm2d(hidden), nn.ReLU(inplace=True),
+                                  nn.Conv2d(hidden, out_channels, kernel_size=1))
+
+    def forward(self, kernel, search):
+        return self.head(self.correlate(self.conv_search(search), self.conv_kernel(kernel)))
+
+
+class DepthwiseBAN(BAN):
+    branch = DepthwiseXCorr
+    loc_channels = 2
+
+    def __init__(self, in_channels=256, out_channels=256, cls_out_channels=2, weighted=False):
+        super().__init__()
+        self.cls = self.branch(in_channels, out_channels, cls_out_channels)
+        self.loc = self.branch(in_channels, out_channels, self.loc_channels)
+
+    def forward(self, z_f, x_f):
+        return self.cls(z_f, x_f), self.loc(z_f, x_f)
+
+
+class MultiBAN(BAN):
+    level_head = DepthwiseBAN
+
+    def __init__(self, in_channels, cls_out_channels, weighted=False):
+        super().__init__()
+        self.weighted = weighted
+        self.levels = len(in_channels)
+        for i, ch in enumerate(in_channels):
+            self.add_module("box%d" % (i + 2), self.level_head(ch, ch, cls_out_channels))
+        if weighted:
+            self.cls_weight = nn.Parameter(torch.ones(self.levels))
+            self.loc_weight = nn.Parameter(torch.ones(self.levels))
+        self.loc_scale = nn.Parameter(torch.ones(self.levels))
+        self._kernels = None
+
+    def _branches(self):
+        for i in range(self.levels):
+            box = getattr(self, "box%d" % (i + 2))
+            yield box.cls
+            yield box.loc
+
+    def prepare(self, z_fs):
+        """Template-side kernels, once per template: [cls2, loc2, cls3, loc3, cls4, loc4]."""
+        self._kernels = [br.conv_kernel(z_fs[n // 2]).contiguous() for n, br in enumerate(self._branches())]
+        return self._kernels
+
+    def forward(self, z_fs, x_fs, kernels=None):
+        if kernels is None:
+            kernels = [br.conv_kernel(z_fs[n // 2]) for n, br in enumerate(self._branches())]
+        branches = list(self._branches())
+        searches = [br.conv_search(x_fs[n // 2]) for n, br in enumerate(branches)]
+        same = len({tuple(s.shape) for s in searches}) == 1 and len({tuple(k.shape) for k in kernels}) == 1
+        if same and len(searches) <= 8:
+            feats = xcorr_depthwise_multi(searches, kernels, circular=branches[0].circular)
+        else:
+            feats = [br.correlate(s, k) for br, s, k in zip(branches, searches, kernels)]
+        outs = [br.head(f) for br, f in zip(branches, feats)]
+        cls = outs[0::2]
+        loc = [l * self.loc_scale[i] for i, l in enumerate(outs[1::2])]  # ban.py:109
+        if self.weighted:  # ban.py:112-125
+            cw, lw = F.softmax(self.cls_weight, 0), F.softmax(self.loc_weight, 0)
+            return sum(c * cw[i] for i, c in enumerate(cls)), sum(l * lw[i] for i, l in enumerate(loc))
+        return sum(cls) / len(cls), sum(loc) / len(loc)

@@ -1,0 +1,153 @@
+"""`ModelBuilder` -- mirror of the INFERENCE half of hdn/models/model_builder_e2e_unconstrained_v2.py (lines 35-217).
+
+Same constructor (reads the global cfg), same sub-module names and therefore the same 836 state-dict tensors
+(backbone.*, neck.*, neck_lp.*, head.*, head_lp.*, hm_net.*), same methods and return values:
+    template(z)              :87-96    z [B,6,127,127] = BGR crop | its log-polar image
+    track_new(x)             :132-141  -> {'cls', 'loc_c'}
+    track_new_lp(x, delta)   :145-158  -> {'x_lp', 'cls_lp', 'loc_lp', 'grid'}
+    track_proj(data, mask)   :161-217  -> (H_mat [B,3,3], homo score, similarity score)
+The training forward / loss wiring (:333-563) is out of scope.
+
+What runs where: dense convolutions -> cuDNN through torch, TF32 off (parity first: a reduced-precision backbone can
+flip the arg-max that must stay bit-exact); K1/K2 correlations, K3 log-polar, K5+K4 DLT+warp, K6 epilogue ->
+libhdn_b200 (sm_100a).  Template-side head convolutions are computed once in `template()` (the reference redoes
+them every frame, ban.py:74).  `track_new_scored` / `track_new_lp_scored` add the fused K6 epilogue so that only
+an index and a few floats leave the device.
+"""
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from hdn.core.config import cfg
+from hdn.models.backbone import get_backbone
+from hdn.models.head import get_ban_head
+from hdn.models.logpolar import STN_Polar
+from hdn.models.neck import get_neck
+from hdn.utils.point import Point, generate_points, generate_points_lp
+from hdn_b200 import ops
+from homo_estimator.Deep_homography.Oneline_DLTv1.models.homo_model_builder import HomoModelBuilder
+
+
+class ModelBuilder(nn.Module):
+    def __init__(self):
+        super().__init__()
+        if os.environ.get("HDN_B200_TF32", "0") != "1":
+            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cuda.matmul.allow_tf32 = False
+        self.backbone = get_backbone(cfg.BACKBONE.TYPE, **cfg.BACKBONE.KWARGS)
+        self.logpolar_instance = STN_Polar(cfg.TRACK.INSTANCE_SIZE)
+        if cfg.ADJUST.ADJUST:
+            self.neck = get_neck(cfg.ADJUST.TYPE, **cfg.ADJUST.KWARGS)
+            self.neck_lp = get_neck(cfg.ADJUST.TYPE, **cfg.ADJUST.KWARGS, cut=False)
+        self.score_size = (cfg.TRACK.INSTANCE_SIZE - cfg.TRACK.EXEMPLAR_SIZE) // cfg.POINT.STRIDE + 1 + cfg.TRACK.BASE_SIZE
+        self.cls_out_channels = cfg.BAN.KWARGS.cls_out_channels
+        self.points = generate_points(cfg.POINT.STRIDE, self.score_size)
+        self.p = Point(cfg.POINT.STRIDE, cfg.TRAIN.OUTPUT_SIZE, cfg.TRAIN.EXEMPLAR_SIZE // 2)
+        self.points_lp = generate_points_lp(cfg.POINT.STRIDE_LP, cfg.POINT.STRIDE_LP, cfg.TRAIN.OUTPUT_SIZE_LP)
+        if cfg.BAN.BAN:
+            self.head = get_ban_head(cfg.BAN.TYPE, **cfg.BAN.KWARGS)
+            # the reference ignores cfg.BAN_LP and always builds MultiCircBAN with BAN.KWARGS (model_builder...py:66)
+            self.head_lp = get_ban_head("MultiCircBAN", **cfg.BAN.KWARGS)
+        self.hm_net = HomoModelBuilder(pretrained=True)
+        self.zf = self.zf_lp = None
+        self._k_sim = self._k_lp = None
+        self._M = self._Minv = None
+
+    # ------------------------------------------------------------------ features
+    def feature_extractor(self, x):
+        return self.backbone(x)
+
+    def _necked(self, x, neck):
+        f = self.feature_extractor(x)
+        return getattr(self, neck)(f) if cfg.ADJUST.ADJUST else f
+
+    @torch.no_grad()
+    def template(self, z):
+        self.zf = self._necked(z[:, 0:3], "neck")
+        self.zf_lp = self._necked(z[:, 3:6], "neck_lp")
+        # template-side correlation kernels: once per template instead of once per frame
+        self._k_sim = self.head.prepare(self.zf)
+        self._k_lp = self.head_lp.prepare(self.zf_lp)
+
+    @torch.no_grad()
+    def update_template(self, z, rot):
+        """model_builder...py:98-108: re-template from a 3-channel crop, log-polar image taken on the device."""
+        polar = torch.zeros(z.shape[0], 2, device=z.device)
+        z_lp, _ = self.logpolar_instance(z, polar, rot)
+        self.zf = self._necked(z, "neck")
+        self.zf_lp = self._necked(z_lp, "neck_lp")
+        self._k_sim = self.head.prepare(self.zf)
+        self._k_lp = self.head_lp.prepare(self.zf_lp)
+
+    # ------------------------------------------------------------------ stage 1: translation
+    @torch.no_grad()
+    def track_new(self, x, delta=[0, 0]):
+        cls, loc_c = self.head(self.zf, self._necked(x, "neck"), self._k_sim)
+        return {"cls": cls, "loc_c": loc_c}
+
+    # ------------------------------------------------------------------ stage 2: scale / rotation
+    @torch.no_grad()
+    def track_new_lp(self, x, delta=[0, 0]):
+        polar = torch.zeros(x.shape[0], 2, device=x.device)  # the target has been moved to the crop centre (:146)
+        x_lp, grid = self.logpolar_instance(x, polar, delta)
+        cls_lp, loc_lp = self.head_lp(self.zf_lp, self._necked(x_lp, "neck_lp"), self._k_lp)
+        return {"x_lp": x_lp, "cls_lp": cls_lp, "loc_lp": loc_lp, "grid": grid}
+
+    # ------------------------------------------------------------------ stage 3: residual homography
+    def _m_pair(self, device):
+        """M = [[63.5,0,63.5],[0,63.5,63.5],[0,0,1]] (hard-coded by the reference, :196-199) and torch.inverse(M) (:205),
+        taken once instead of every frame."""
+        if self._M is None:
+            m = torch.tensor([[63.5, 0.0, 63.5], [0.0, 63.5, 63.5], [0.0, 0.0, 1.0]], device=device)
+            self._M = m.reshape(9).tolist()
+            self._Minv = torch.inverse(m).reshape(9).tolist()
+        return self._M, self._Minv
+
+    @torch.no_grad()
+    def track_proj(self, data, tmp_mask=None):
+        org_imgs, input_tensors, h4p = data["org_imgs"], data["input_tensors"], data["h4p"]
+        offsets, patch_1, patch_2 = self.hm_net.offsets(input_tensors)
+        M, Minv = self._m_pair(org_imgs.device)
+        H_mat, pred_I2 = ops.dlt_warp(h4p, offsets, org_imgs[:, :1], M, Minv)  # K5 + K4, one launch (:195, :210)
+        pred_feat = self.hm_net.ShareFeature(pred_I2)
+        # both scores use the FIRST sample only and a fixed 127*127 divisor (:213-216)
+        similarity_norm = torch.sum(torch.abs(patch_2 - pred_feat)[0][0]) / (127 * 127)
+        similarity_norm_simi = torch.sum(torch.abs(patch_2 - patch_1)[0][0]) / (127 * 127)
+        return H_mat, similarity_norm, similarity_norm_simi
+
+    # ------------------------------------------------------------------ fused epilogues (K6)
+    def _window(self, n, device):
+        key = (n, str(device))
+        cache = self.__dict__.setdefault("_win_cache", {})
+        if key not in cache:
+            h = np.hanning(n)
+            cache[key] = torch.from_numpy(np.outer(h, h).flatten()).to(device)
+        return cache[key]
+
+    @torch.no_grad()
+    def track_new_scored(self, x, win_influence=None):
+        """track_new + on-device softmax / Hanning blend / arg-max / loc gather (hdn_tracker.py:82-89, proj_e2e:172-174).
+        -> (idx, pscore, score, loc[:, idx]) as NumPy, one packed D2H."""
+        out = self.track_new(x)
+        w = cfg.TRACK.WINDOW_INFLUENCE if win_influence is None else win_influence
+        return ops.score_argmax_host(out["cls"], out["loc_c"], self._window(out["cls"].shape[-1], x.device), w)
+
+    @torch.no_grad()
+    def track_new_lp_scored(self, x, delta=[0, 0]):
+        out = self.track_new_lp(x, delta)
+        return ops.score_argmax_host(out["cls_lp"], out["loc_lp"], None, 0.0)
+
+    # ------------------------------------------------------------------ reference helpers (:69-80)
+    def _convert_score(self, score):
+        return score.contiguous().view(score.shape[0], self.cls_out_channels, -1).permute(0, 2, 1)[:, :, 1]
+
+    def softmax(self, cls):
+        return torch.softmax(cls.permute(0, 2, 3, 1).contiguous(), dim=3) if cfg.BAN.BAN else cls
+
+    def log_softmax(self, cls):
+        return torch.log_softmax(cls.permute(0, 2, 3, 1).contiguous(), dim=3) if cfg.BAN.BAN else cls
+
+    def forward(self, data):
+        raise NotImplementedError("ModelBuilder.forward is the reference's TRAINING path (model_builder...py:333); out of scope here")

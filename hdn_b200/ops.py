@@ -234,3 +234,22 @@ def score_argmax(cls, loc, window=None, win_influence=0.0):
                                          _ptr(ps), _ptr(sc), _ptr(g), B, L, N, _stream())
     _lib.check(st, "hdn_score_argmax_f32")
     return idx, ps, sc, g
+
+
+def score_argmax_host(cls, loc, window=None, win_influence=0.0):
+    """K6 + ONE packed device->host copy (8+8+4+4L bytes per item instead of the whole score / loc maps; the
+    reference moves both maps to the host and does this in NumPy).  -> NumPy (idx int64[B], pscore f64[B], score f32[B],
+    gathered f32[B,L])."""
+    cls, loc = _dev(cls, "cls"), _dev(loc, "loc")
+    B, _, N, _ = cls.shape
+    L = loc.shape[1]
+    if window is not None:
+        window = _dev(window, "window", torch.float64)
+    o_ps, o_sc, o_g, total = 8 * B, 16 * B, 20 * B, 20 * B + 4 * B * L
+    buf = torch.empty(total + (-total) % 8, device=cls.device, dtype=torch.uint8)
+    base = buf.data_ptr()
+    st = _lib.lib().hdn_score_argmax_f32(_ptr(cls), _ptr(loc), _ptr(window) if window is not None else None, float(win_influence), _vp(base),
+                                         _vp(base + o_ps), _vp(base + o_sc), _vp(base + o_g), B, L, N, _stream())
+    _lib.check(st, "hdn_score_argmax_f32")
+    host = buf.cpu().numpy()
+    return (host[:o_ps].view("<i8"), host[o_ps:o_sc].view("<f8"), host[o_sc:o_g].view("<f4"), host[o_g:total].view("<f4").reshape(B, L))
