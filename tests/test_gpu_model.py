@@ -67,7 +67,8 @@ def test_model_level_parity(tag):
     h4p = np.asarray([[0, 0, 0, 127, 127, 127, 127, 0]], np.float32)
     data = {"org_imgs": cuda(pair), "input_tensors": cuda(pair), "h4p": cuda(h4p), "patch_indices": None}
     H, s_homo, s_simi = model.track_proj(data, None)
-    off, _, _ = model.hm_net.offsets(cuda(pair))
+    with torch.no_grad():
+        off, _, _ = model.hm_net.offsets(cuda(pair))
     assert np.allclose(off.cpu().numpy(), g["offsets"], rtol=1e-3, atol=1e-3)
     assert np.allclose(H.cpu().numpy(), g["H"], rtol=1e-3, atol=1e-5)
     assert abs(float(s_homo) - float(g["homo_score"])) <= 1e-3 * abs(float(g["homo_score"])) + 1e-5
