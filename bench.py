@@ -54,11 +54,13 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def traffic_from_profiles(workload):
-    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, if any."""
+def traffic_from_profiles(workload, pairs):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture (per pair x pairs), if any."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
-        return json.load(open(p)).get(workload)
+        e = json.load(open(p)).get(workload)
+        if e:
+            return e["bytes_per_pair"] * pairs
     return None
 
 
@@ -301,7 +303,7 @@ def main():
     fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
     achieved = k1_bytes / k1_s / 1e9
     roofline = {"kernel": "xcorr_staged_kernel (K1, 6 problems/launch)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic_from_profiles(a.workload),
+                "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic_from_profiles(a.workload, B),
                 "algorithmic_bytes_per_launch": k1_bytes, "launch_ms": kern_avg["k1"],
                 "fp32_tflops": k1_flops / k1_s / 1e12, "fp32_peak_tflops": fp32_peak, "fp32_frac": k1_flops / k1_s / 1e12 / fp32_peak,
                 "flop_per_byte": k1_flops / k1_bytes,
