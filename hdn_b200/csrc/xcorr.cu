@@ -17,6 +17,7 @@
 //   * Accumulation order is fixed (u outer, v inner, split-K halves combined in order) -> results
 //     are run-to-run deterministic.
 //   * Shapes outside the table fall back to a plain one-thread-per-output kernel (still on device).
+#include <type_traits>
 #include "common.cuh"
 
 namespace hdn {
@@ -197,6 +198,206 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::CTAS)
     if (tid == 0) bulk_wait_all<0>();
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Vectorised variant for the FMA-bound shapes (29x29 kernels).  Same TMA staging, but the landed planes are
+// re-pitched once per group into a work tile whose row pitch XP (and kernel-row pitch KP) is a multiple of 4
+// floats with XP/4 odd: every row starts 16-byte aligned, so a thread reads its input row and the kernel row
+// with LDS.128, and lanes (= rows) of a quarter-warp still fall into distinct 16-byte bank groups.  Per kernel
+// row u that is ceil(WX/4) + ceil(KW/4) shared loads feeding WO*KW FFMA (16 + 8 -> 957 for 61 (*) 29).
+// The raw landing buffer is free as soon as the re-pitch is done, so the next group's TMA overlaps the compute.
+template <int KH_, int KW_, int HX_, int WX_, bool CIRC_, int G_, int NT_, int KSPLIT_, int XP_, int KP_, bool TAIL_>
+struct VCfg {
+    static constexpr int KH = KH_, KW = KW_, HX = HX_, WX = WX_, G = G_, NT = NT_, KSPLIT = KSPLIT_, XP = XP_, KP = KP_, CTAS = 1;
+    static constexpr bool CIRC = CIRC_, TAIL = TAIL_;
+    static constexpr int PH = CIRC ? HX / 2 : 0, PW = CIRC ? WX / 2 : 0;
+    static constexpr int HO = HX + 2 * PH - KH + 1, WO = WX + 2 * PW - KW + 1;
+    static constexpr int XPL = HX * WX, KPL = KH * KW, OPL = HO * WO;
+    static constexpr int NX4 = (WX + 3) / 4, NK4 = (KW + 3) / 4;
+    static constexpr int RAW_FLOATS = G * (XPL + KPL), WX_FLOATS = G * HX * XP, WK_FLOATS = G * KH * KP, OUT_FLOATS = G * OPL;
+    static constexpr size_t SMEM = (size_t)(RAW_FLOATS + WX_FLOATS + WK_FLOATS + 2 * OUT_FLOATS) * 4 + 8 + 16;
+    static_assert(G % 4 == 0 && 256 % G == 0, "group size");
+    static_assert(XP % 4 == 0 && (XP / 4) % 2 == 1 && XP >= NX4 * 4, "x pitch: 16-byte rows, odd number of 16-byte groups");
+    static_assert(KP % 4 == 0 && (KP / 4) % 2 == 1 && KP >= NK4 * 4, "k pitch");
+    static_assert(!TAIL || (HO == 33 && NT == 32 * G * KSPLIT && KH <= 32), "tail-row mapping is for 33-row outputs");
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
+
+// One kernel row: acc[c] += sum_v x[r][c+v-PW] * k[u][v], operands fetched with 128-bit shared loads.
+template <class Cfg>
+__device__ __forceinline__ void row_step_vec(const float *__restrict__ xrow, const float *__restrict__ krow, float (&acc)[Cfg::WO]) {
+    float xv[Cfg::NX4 * 4], kv[Cfg::NK4 * 4];
+#pragma unroll
+    for (int q = 0; q < Cfg::NX4; ++q) {
+        const float4 t = reinterpret_cast<const float4 *>(xrow)[q];
+        xv[4 * q] = t.x; xv[4 * q + 1] = t.y; xv[4 * q + 2] = t.z; xv[4 * q + 3] = t.w;
+    }
+#pragma unroll
+    for (int q = 0; q < Cfg::NK4; ++q) {
+        const float4 t = reinterpret_cast<const float4 *>(krow)[q];
+        kv[4 * q] = t.x; kv[4 * q + 1] = t.y; kv[4 * q + 2] = t.z; kv[4 * q + 3] = t.w;
+    }
+#pragma unroll
+    for (int v = 0; v < Cfg::KW; ++v) {
+#pragma unroll
+        for (int c = 0; c < Cfg::WO; ++c) {
+            int q = c + v - Cfg::PW;
+            q = q < 0 ? 0 : (q > Cfg::WX - 1 ? Cfg::WX - 1 : q);
+            acc[c] = fmaf(xv[q], kv[v], acc[c]);
+        }
+    }
+}
+
+template <class Cfg>
+__device__ __forceinline__ void rows_vec(const float *__restrict__ xp, const float *__restrict__ kp, int i, int u0, int u1, float (&acc)[Cfg::WO]) {
+#pragma unroll 1
+    for (int u = u0; u < u1; ++u) {
+        int r = i + u - Cfg::PH;
+        if (Cfg::CIRC) {
+            if (r < 0) r += Cfg::HX;
+            else if (r >= Cfg::HX) r -= Cfg::HX;
+        }
+        row_step_vec<Cfg>(xp + r * Cfg::XP, kp + u * Cfg::KP, acc);
+    }
+}
+
+template <class Cfg>
+__device__ __forceinline__ void compute_group_vec(const float *__restrict__ wx, const float *__restrict__ wk, float *__restrict__ so, int tid) {
+    constexpr int ROWS = Cfg::G * Cfg::HO;
+    if constexpr (!Cfg::TAIL) {
+#pragma unroll 1
+        for (int ks = 0; ks < Cfg::KSPLIT; ++ks) {
+#pragma unroll 1
+            for (int t = tid; t < ROWS * Cfg::KSPLIT; t += Cfg::NT) {
+                const int myks = t / ROWS;
+                if (myks != ks) continue;
+                const int rrow = t - myks * ROWS;
+                const int p = rrow / Cfg::HO, i = rrow - p * Cfg::HO;
+                float acc[Cfg::WO];
+#pragma unroll
+                for (int c = 0; c < Cfg::WO; ++c) acc[c] = 0.f;
+                rows_vec<Cfg>(wx + p * Cfg::HX * Cfg::XP, wk + p * Cfg::KH * Cfg::KP, i, ks * Cfg::KH / Cfg::KSPLIT, (ks + 1) * Cfg::KH / Cfg::KSPLIT, acc);
+                float *o = so + p * Cfg::OPL + i * Cfg::WO;
+                if (ks == 0) {
+#pragma unroll
+                    for (int c = 0; c < Cfg::WO; ++c) o[c] = acc[c];
+                } else {
+#pragma unroll
+                    for (int c = 0; c < Cfg::WO; ++c) o[c] += acc[c];
+                }
+            }
+            if (ks + 1 < Cfg::KSPLIT) __syncthreads();
+        }
+    } else {
+        // 33-row outputs.  warp = (plane, K-slice); lane = output rows 0..31 over the slice's kernel rows.
+        // Row 32 is done by the slice-0 warp with lane = KERNEL row: every lane runs one row step (its own input
+        // row 32+u against kernel row u), then a butterfly transpose-reduction leaves column j's total in lane j.
+        // Slice 0 has the shorter u-range (KH/KSPLIT rounded down), so the extra step balances the slices.
+        const int warp = tid >> 5, lane = tid & 31;
+        const int p = warp % Cfg::G, ks = warp / Cfg::G;
+        const int u0 = ks * Cfg::KH / Cfg::KSPLIT, u1 = (ks + 1) * Cfg::KH / Cfg::KSPLIT;
+        const float *xp = wx + p * Cfg::HX * Cfg::XP, *kp = wk + p * Cfg::KH * Cfg::KP;
+        float acc[Cfg::WO];
+#pragma unroll
+        for (int c = 0; c < Cfg::WO; ++c) acc[c] = 0.f;
+        rows_vec<Cfg>(xp, kp, lane, u0, u1, acc);
+        float *o = so + p * Cfg::OPL;
+        if (ks == 0) {
+#pragma unroll
+            for (int c = 0; c < Cfg::WO; ++c) o[lane * Cfg::WO + c] = acc[c];
+            float t[Cfg::WO];
+#pragma unroll
+            for (int c = 0; c < Cfg::WO; ++c) t[c] = 0.f;
+            const int u = lane < Cfg::KH ? lane : Cfg::KH - 1;
+            row_step_vec<Cfg>(xp + (32 + u) * Cfg::XP, kp + u * Cfg::KP, t);
+            if (lane >= Cfg::KH) {
+#pragma unroll
+                for (int c = 0; c < Cfg::WO; ++c) t[c] = 0.f;
+            }
+            float last = t[32];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) last += __shfl_xor_sync(0xffffffffu, last, off);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {  // after the step with `off`, a lane holds `off` partial columns
+                const bool upper = (lane & off) != 0;
+#pragma unroll
+                for (int j = 0; j < off; ++j) {
+                    const float send = upper ? t[j] : t[j + off];
+                    const float keep = upper ? t[j + off] : t[j];
+                    t[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+            o[32 * Cfg::WO + lane] = t[0];
+            if (lane == 0) o[32 * Cfg::WO + 32] = last;
+        }
+#pragma unroll 1
+        for (int s = 1; s < Cfg::KSPLIT; ++s) {
+            __syncthreads();
+            if (s == ks) {
+#pragma unroll
+                for (int c = 0; c < Cfg::WO; ++c) o[lane * Cfg::WO + c] += acc[c];
+            }
+        }
+    }
+}
+
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::NT, 1)
+    xcorr_vec_kernel(XProblems P, int groups_per_problem, int n_groups, int C, long long k_bstride) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *raw = reinterpret_cast<float *>(smem_raw);
+    float *wx = raw + Cfg::RAW_FLOATS;
+    float *wk = wx + Cfg::WX_FLOATS;
+    float *sout = wk + Cfg::WK_FLOATS;
+    uint64_t *full = reinterpret_cast<uint64_t *>(sout + 2 * Cfg::OUT_FLOATS);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(full, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto issue = [&](int g) {  // elected thread only
+        const int prob = g / groups_per_problem;
+        const long long plane0 = (long long)(g - prob * groups_per_problem) * Cfg::G;
+        const long long b = plane0 / C, c0 = plane0 - b * C;
+        mbar_expect_tx(full, Cfg::RAW_FLOATS * 4);
+        bulk_g2s(raw, P.x[prob] + plane0 * Cfg::XPL, Cfg::G * Cfg::XPL * 4, full);
+        bulk_g2s(raw + Cfg::G * Cfg::XPL, P.k[prob] + b * k_bstride + c0 * Cfg::KPL, Cfg::G * Cfg::KPL * 4, full);
+    };
+    if (tid == 0 && (int)blockIdx.x < n_groups) issue(blockIdx.x);
+
+    int it = 0;
+    for (int g = blockIdx.x; g < n_groups; g += gridDim.x, ++it) {
+        mbar_wait(full, it & 1);
+        // re-pitch: dense planes -> 16-byte-aligned rows (pad columns are never used as operands)
+#pragma unroll 4
+        for (int e = tid; e < Cfg::G * Cfg::XPL; e += Cfg::NT) {
+            const int row = e / Cfg::WX, c = e - row * Cfg::WX;
+            wx[row * Cfg::XP + c] = raw[e];
+        }
+        for (int e = tid; e < Cfg::G * Cfg::KPL; e += Cfg::NT) {
+            const int row = e / Cfg::KW, c = e - row * Cfg::KW;
+            wk[row * Cfg::KP + c] = raw[Cfg::G * Cfg::XPL + e];
+        }
+        __syncthreads();  // work tile complete; raw buffer free
+        if (tid == 0) {
+            const int gn = g + gridDim.x;
+            if (gn < n_groups) issue(gn);  // lands while this group computes
+        }
+        float *so = sout + (it & 1) * Cfg::OUT_FLOATS;
+        compute_group_vec<Cfg>(wx, wk, so, tid);
+        if (tid == 0) bulk_wait_read<0>();
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            const int prob = g / groups_per_problem;
+            const long long plane0 = (long long)(g - prob * groups_per_problem) * Cfg::G;
+            bulk_s2g(P.out[prob] + plane0 * Cfg::OPL, so, Cfg::OUT_FLOATS * 4);
+            bulk_commit();
+        }
+    }
+    if (tid == 0) bulk_wait_all<0>();
+}
+
 // Any shape, any alignment: one thread per output element, straight from global memory.
 __global__ void xcorr_generic_kernel(XProblems P, int nprob, int B, int C, int Hx, int Wx, int Hk, int Wk, int ph, int pw, int Ho, int Wo,
                                      long long k_bstride, long long plane_begin) {
@@ -227,11 +428,20 @@ __global__ void xcorr_generic_kernel(XProblems P, int nprob, int B, int C, int H
     }
 }
 
+template <class Cfg, class = void>
+struct KernelOf {
+    static constexpr auto fn = xcorr_staged_kernel<Cfg>;
+};
+template <class Cfg>
+struct KernelOf<Cfg, std::void_t<decltype(Cfg::XP)>> {
+    static constexpr auto fn = xcorr_vec_kernel<Cfg>;
+};
+
 template <class Cfg>
 static int launch_staged(const XProblems &P, int n, int B, int C, long long kbs, cudaStream_t st) {
     static bool configured = false;  // benign race: idempotent attribute set
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(xcorr_staged_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(KernelOf<Cfg>::fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
@@ -239,7 +449,7 @@ static int launch_staged(const XProblems &P, int n, int B, int C, long long kbs,
     const int total = gpp * n;
     const int slots = sm_count() * Cfg::CTAS;
     const int grid = total < slots ? total : slots;
-    xcorr_staged_kernel<Cfg><<<grid, Cfg::NT, Cfg::SMEM, st>>>(P, gpp, total, C, kbs);
+    KernelOf<Cfg>::fn<<<grid, Cfg::NT, Cfg::SMEM, st>>>(P, gpp, total, C, kbs);
     count_launch();
     return launch_status();
 }
@@ -247,8 +457,9 @@ static int launch_staged(const XProblems &P, int n, int B, int C, long long kbs,
 //                       KH  KW  HX  WX  circ   G   NT  ST KS spill
 using CfgNative = XCfg<5, 5, 29, 29, false, 8, 224, 2, 1, false, 2>;   // 127/255 crops (HBM-bound), 2 CTAs/SM
 using CfgNativeLp = XCfg<13, 13, 13, 13, true, 32, 416, 3, 1, false>;  // lp branch, 127 crops
-using Cfg256 = XCfg<29, 29, 61, 61, false, 4, 256, 2, 2, true>;        // 256/512 crops (FMA-bound)
-using Cfg256Lp = XCfg<29, 29, 29, 29, true, 8, 256, 2, 1, false>;      // lp branch, INSTANCE_SIZE=512
+//                     KH  KW  HX  WX  circ   G   NT KS  XP  KP  tail
+using Cfg256 = VCfg<29, 29, 61, 61, false, 4, 256, 2, 68, 36, true>;    // 256/512 crops (FMA-bound), LDS.128 operands
+using Cfg256Lp = VCfg<29, 29, 29, 29, true, 8, 256, 1, 36, 36, false>;  // lp branch, INSTANCE_SIZE=512
 using CfgWin15 = XCfg<15, 15, 39, 39, false, 8, 224, 2, 1, false>;     // 15x15 window sweep
 
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
