@@ -54,6 +54,7 @@ class ModelBuilder(nn.Module):
         self.zf = self.zf_lp = None
         self._k_sim = self._k_lp = None
         self._M = self._Minv = None
+        self._use_graphs, self._graphs = False, {}
 
     # ------------------------------------------------------------------ features
     def feature_extractor(self, x):
@@ -63,13 +64,25 @@ class ModelBuilder(nn.Module):
         f = self.feature_extractor(x)
         return getattr(self, neck)(f) if cfg.ADJUST.ADJUST else f
 
+    def _set_template_kernels(self):
+        """Template-side correlation kernels: once per template instead of once per frame (the reference redoes them per
+        frame, ban.py:74).  Kept in persistent buffers so captured CUDA graphs stay valid across re-templating."""
+        for name, head, feats in (("_k_sim", self.head, self.zf), ("_k_lp", self.head_lp, self.zf_lp)):
+            fresh = head.prepare(feats)
+            old = getattr(self, name)
+            if old is not None and all(o.shape == f.shape and o.device == f.device for o, f in zip(old, fresh)):
+                for o, f in zip(old, fresh):
+                    o.copy_(f)
+                head._kernels = old
+            else:
+                setattr(self, name, fresh)
+                self._graphs.clear()
+
     @torch.no_grad()
     def template(self, z):
         self.zf = self._necked(z[:, 0:3], "neck")
         self.zf_lp = self._necked(z[:, 3:6], "neck_lp")
-        # template-side correlation kernels: once per template instead of once per frame
-        self._k_sim = self.head.prepare(self.zf)
-        self._k_lp = self.head_lp.prepare(self.zf_lp)
+        self._set_template_kernels()
 
     @torch.no_grad()
     def update_template(self, z, rot):
@@ -78,8 +91,7 @@ class ModelBuilder(nn.Module):
         z_lp, _ = self.logpolar_instance(z, polar, rot)
         self.zf = self._necked(z, "neck")
         self.zf_lp = self._necked(z_lp, "neck_lp")
-        self._k_sim = self.head.prepare(self.zf)
-        self._k_lp = self.head_lp.prepare(self.zf_lp)
+        self._set_template_kernels()
 
     # ------------------------------------------------------------------ stage 1: translation
     @torch.no_grad()
@@ -126,18 +138,69 @@ class ModelBuilder(nn.Module):
             cache[key] = torch.from_numpy(np.outer(h, h).flatten()).to(device)
         return cache[key]
 
+    # ---- CUDA-graph replay of a whole stage (B = 1 inference is launch-bound: ~170 kernels per stage) -------------
+    def enable_graphs(self, on=True):
+        self._use_graphs = bool(on)
+        self._graphs.clear()
+        return self
+
+    def _staged(self, key, fn, *inputs):
+        """Run fn(*inputs) -> device tensor, replaying a captured graph when enabled (inputs copied into static buffers)."""
+        if not self._use_graphs:
+            return fn(*inputs)
+        key = (key,) + tuple(tuple(t.shape) for t in inputs)
+        entry = self._graphs.get(key)
+        if entry is None:
+            static_in = [t.clone() for t in inputs]
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(2):  # cuDNN algorithm selection, smem attribute opt-in: all before capture
+                    fn(*static_in)
+            cur.wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = fn(*static_in)
+            entry = self._graphs[key] = (graph, static_in, static_out)
+        graph, static_in, static_out = entry
+        for dst, src in zip(static_in, inputs):
+            dst.copy_(src, non_blocking=True)
+        graph.replay()
+        return static_out
+
+    def _stage1_packed(self, x, w):
+        out = self.track_new(x)
+        return ops.score_argmax_packed(out["cls"], out["loc_c"], self._window(out["cls"].shape[-1], x.device), w)
+
+    def _stage2_packed(self, x):
+        out = self.track_new_lp(x, [0, 0])
+        return ops.score_argmax_packed(out["cls_lp"], out["loc_lp"], None, 0.0)
+
+    def _stage3_packed(self, pair, h4p):
+        H, s_homo, s_simi = self.track_proj({"org_imgs": pair, "input_tensors": pair, "h4p": h4p, "patch_indices": None}, None)
+        return torch.cat((H.reshape(-1), s_homo.reshape(1), s_simi.reshape(1)))
+
     @torch.no_grad()
     def track_new_scored(self, x, win_influence=None):
         """track_new + on-device softmax / Hanning blend / arg-max / loc gather (hdn_tracker.py:82-89, proj_e2e:172-174).
         -> (idx, pscore, score, loc[:, idx]) as NumPy, one packed D2H."""
-        out = self.track_new(x)
         w = cfg.TRACK.WINDOW_INFLUENCE if win_influence is None else win_influence
-        return ops.score_argmax_host(out["cls"], out["loc_c"], self._window(out["cls"].shape[-1], x.device), w)
+        buf = self._staged("s1", lambda t: self._stage1_packed(t, w), x)
+        return ops.unpack_scores(buf.cpu().numpy(), x.shape[0], 2)
 
     @torch.no_grad()
     def track_new_lp_scored(self, x, delta=[0, 0]):
-        out = self.track_new_lp(x, delta)
-        return ops.score_argmax_host(out["cls_lp"], out["loc_lp"], None, 0.0)
+        if delta[0] != 0 or delta[1] != 0:
+            out = self.track_new_lp(x, delta)
+            return ops.score_argmax_host(out["cls_lp"], out["loc_lp"], None, 0.0)
+        buf = self._staged("s2", self._stage2_packed, x)
+        return ops.unpack_scores(buf.cpu().numpy(), x.shape[0], 4)
+
+    @torch.no_grad()
+    def track_proj_packed(self, pair, h4p):
+        """track_proj for one pair with a single read-back: NumPy [H (9 per item) ..., homo_score, simi_score]."""
+        return self._staged("s3", self._stage3_packed, pair, h4p).cpu().numpy()
 
     # ------------------------------------------------------------------ reference helpers (:69-80)
     def _convert_score(self, score):

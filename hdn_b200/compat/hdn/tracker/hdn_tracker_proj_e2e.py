@@ -50,6 +50,11 @@ class hdnTrackerHomo(hdnTracker):
                 "h4p": up(info["four_points"]), "patch_indices": None}  # identity indices (get_img_info.py:92): gather skipped
         return self.model.track_proj(data, tmp_mask)
 
+    def _h4p(self):
+        if getattr(self, "_h4p_dev", None) is None:
+            self._h4p_dev = torch.tensor([[0.0, 0.0, 0.0, 127.0, 127.0, 127.0, 127.0, 0.0]]).cuda()  # get_img_info.py:93-98
+        return self._h4p_dev
+
     # ------------------------------------------------------------------ first frame
     def init(self, img, bbox, poly, gt_points, first_point):
         self._start_state(bbox, poly, first_point)
@@ -125,8 +130,12 @@ class hdnTrackerHomo(hdnTracker):
         crop_w = self.z_crop_points_sm[2] - self.z_crop_points_sm[0] + 1
         crop_h = self.z_crop_points_sm[3] - self.z_crop_points_sm[1] + 1
         search_gray, _ = get_search_info(torch.from_numpy(x_homo)[:, 0:3, :, :])
-        H_hm, homo_score, simi_score = self.homo_estimate(self.init_homo_tmp, search_gray, None)
-        both = torch.cat((H_hm.reshape(-1)[:9], homo_score.reshape(1))).detach().cpu().numpy()  # one read-back for H and its score
+        if hasattr(self.model, "track_proj_packed") and cfg.CUDA:
+            pair = torch.from_numpy(np.concatenate([self.init_homo_tmp, search_gray], 0).astype(np.float32)).unsqueeze(0).pin_memory()
+            both = self.model.track_proj_packed(pair.cuda(non_blocking=True), self._h4p())  # one upload, one read-back (H + scores)
+        else:
+            H_hm, homo_score, simi_score = self.homo_estimate(self.init_homo_tmp, search_gray, None)
+            both = torch.cat((H_hm.reshape(-1)[:9], homo_score.reshape(1))).detach().cpu().numpy()
         homo_score = both[9]
         H_hm = np.linalg.inv(both[:9].reshape(3, 3))
         H_hm = (1.0 / H_hm.item(8)) * H_hm

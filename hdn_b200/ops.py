@@ -236,10 +236,9 @@ def score_argmax(cls, loc, window=None, win_influence=0.0):
     return idx, ps, sc, g
 
 
-def score_argmax_host(cls, loc, window=None, win_influence=0.0):
-    """K6 + ONE packed device->host copy (8+8+4+4L bytes per item instead of the whole score / loc maps; the
-    reference moves both maps to the host and does this in NumPy).  -> NumPy (idx int64[B], pscore f64[B], score f32[B],
-    gathered f32[B,L])."""
+def score_argmax_packed(cls, loc, window=None, win_influence=0.0):
+    """K6 writing all four results into ONE device byte buffer: [idx i64 x B | pscore f64 x B | score f32 x B | loc[:,idx] f32 x B*L].
+    Graph-capturable (no host sync).  Decode the host copy with `unpack_scores`."""
     cls, loc = _dev(cls, "cls"), _dev(loc, "loc")
     B, _, N, _ = cls.shape
     L = loc.shape[1]
@@ -251,5 +250,17 @@ def score_argmax_host(cls, loc, window=None, win_influence=0.0):
     st = _lib.lib().hdn_score_argmax_f32(_ptr(cls), _ptr(loc), _ptr(window) if window is not None else None, float(win_influence), _vp(base),
                                          _vp(base + o_ps), _vp(base + o_sc), _vp(base + o_g), B, L, N, _stream())
     _lib.check(st, "hdn_score_argmax_f32")
-    host = buf.cpu().numpy()
+    return buf
+
+
+def unpack_scores(host, B, L):
+    """host: NumPy uint8 copy of a `score_argmax_packed` buffer -> (idx i64[B], pscore f64[B], score f32[B], gathered f32[B,L])."""
+    o_ps, o_sc, o_g, total = 8 * B, 16 * B, 20 * B, 20 * B + 4 * B * L
     return (host[:o_ps].view("<i8"), host[o_ps:o_sc].view("<f8"), host[o_sc:o_g].view("<f4"), host[o_g:total].view("<f4").reshape(B, L))
+
+
+def score_argmax_host(cls, loc, window=None, win_influence=0.0):
+    """K6 + ONE packed device->host copy (8+8+4+4L bytes per item instead of the whole score / loc maps; the
+    reference moves both maps to the host and does this in NumPy).  -> NumPy (idx, pscore, score, gathered)."""
+    buf = score_argmax_packed(cls, loc, window, win_influence)
+    return unpack_scores(buf.cpu().numpy(), cls.shape[0], loc.shape[1])

@@ -5,8 +5,8 @@ TEST INFRASTRUCTURE ONLY.   python oracle/gen_golden_model.py [--calibrate] [wha
 Writes tests/golden/model_*.npz, tests/golden/tracker_*.npz and tests/golden/state_dict_keys.json.
 
 The reference's ModelBuilder / hdnTrackerHomo are imported unmodified from /root/reference (oracle/ref_import.py),
-filled with the deterministic weight fixture of tests/weights_fixture.py (no checkpoint ships with the reference),
-and run on seeded inputs from tests/synth.py.  The tests rebuild the same weights and inputs on the GPU box from the
+filled with the deterministic weight fixture of hdn_b200/synthetic.py (no checkpoint ships with the reference),
+and run on seeded inputs from the same file.  The tests rebuild the same weights and inputs on the GPU box from the
 same seeds, so only the (small) outputs are stored.
 
 Reference call sites exercised:
@@ -33,15 +33,20 @@ OUT = os.path.join(REPO, "tests", "golden")
 YAML = os.path.join(ref_import.REF_ROOT, "experiments", "tracker_homo_config", "proj_e2e_GOT_unconstrained_v2.yaml")
 
 
-def load_by_path(name):
-    spec = importlib.util.spec_from_file_location(name, os.path.join(REPO, "tests", name + ".py"))
+def load_by_path(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
 
 
-fixture = load_by_path("weights_fixture")
-synth = load_by_path("synth")
+# loaded BY PATH: in this process `hdn` is the reference, and the repo root is not importable (oracle/ref_import.py)
+synth = load_by_path("hdn_b200_synthetic", os.path.join(REPO, "hdn_b200", "synthetic.py"))
+
+
+class fixture:  # same names the rest of this script uses
+    SCALES = synth.SCALES
+    fill = staticmethod(synth.fill_weights)
 t = torch.from_numpy
 
 

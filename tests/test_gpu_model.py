@@ -109,3 +109,33 @@ def test_tracker_trajectory_parity():
         assert abs(float(o["best_score"]) - g["best_score"][idx - 1]) < 1e-3
         assert np.allclose(tracker.H_total, g["H_total"][idx - 1], rtol=1e-3, atol=1e-3 * np.abs(g["H_total"][idx - 1]).max())
         assert set(o) == {"bbox_aligned", "best_score", "polygon", "points", "bbox"}
+
+
+def test_cuda_graph_stages_equal_eager():
+    """Replaying the three network stages from CUDA graphs must not change a single output value."""
+    import synth
+    from hdn.tracker.tracker_builder import build_tracker
+    from hdn.utils.bbox import get_min_max_bbox, get_w_h_from_poly
+    frames, polys = synth.sequence(21, 5)
+
+    def run(graphs):
+        model, _ = build_model()
+        model.enable_graphs(graphs)
+        tracker = build_tracker(model)
+        gt = polys[0]
+        cx, cy, w, h = get_min_max_bbox(np.array(gt))
+        tracker.init(frames[0], [cx - (w - 1) / 2, cy - (h - 1) / 2, w, h], get_w_h_from_poly(np.array(gt)), gt, np.array([gt[:2]]))
+        return np.asarray([tracker.track_new(i, frames[i], None, None, None)["polygon"] for i in range(1, len(frames))])
+
+    eager, graphed = run(False), run(True)
+    assert np.array_equal(eager, graphed)
+
+
+def test_sanitizer_smoke_shapes():
+    """Small staged-kernel cases kept cheap enough to run under compute-sanitizer (profiles/r01_sanitizer_*.log)."""
+    from hdn_b200 import ops
+    x = torch.randn(1, 256, 61, 61, device="cuda")
+    k = torch.randn(1, 256, 29, 29, device="cuda")
+    out = ops.xcorr_depthwise(x, k)
+    ref = torch.nn.functional.conv2d(x.view(1, 256, 61, 61), k.view(256, 1, 29, 29), groups=256)
+    assert torch.allclose(out, ref.view_as(out), rtol=1e-3, atol=1e-4 * float(ref.abs().max()))
