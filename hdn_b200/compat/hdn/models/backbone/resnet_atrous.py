@@ -8,11 +8,14 @@ downsample.{0,1}), same geometry:
     `2 - stride` when undilated -- i.e. layer2's stride-2 3x3 has padding 0 (:68-80);
   * projection shortcuts are 1x1 only for layer1; every other stage uses a 3x3 (padding 0 at stride 2, else the
     halved dilation) (:150-173).
-The dense convolutions run on cuDNN through torch (library GEMMs).
+The dense convolutions run on cuDNN / cuBLAS through torch (library GEMMs); the wide dilated 3x3
+layers go through hdn_b200.convs.dilated_conv3x3 (cuDNN has no fast fp32 kernel for them).
 """
 import math
 
 import torch.nn as nn
+
+from hdn_b200.convs import conv3x3
 
 __all__ = ["ResNet", "resnet18", "resnet34", "resnet50"]
 
@@ -47,10 +50,14 @@ class Bottleneck(nn.Module):
 
     def forward(self, x):
         y = self.relu(self.bn1(self.conv1(x)))
-        y = self.relu(self.bn2(self.conv2(y)))
+        y = self.relu(self.bn2(conv3x3(self.conv2, y)))  # dilated layers: 9 shifted GEMMs instead of cuDNN's direct kernel
         y = self.bn3(self.conv3(y))
-        y += x if self.downsample is None else self.downsample(x)
+        y += x if self.downsample is None else self._shortcut(x)
         return self.relu(y)
+
+    def _shortcut(self, x):
+        proj, bn = self.downsample[0], self.downsample[1]
+        return bn(conv3x3(proj, x))
 
 
 class BasicBlock(nn.Module):

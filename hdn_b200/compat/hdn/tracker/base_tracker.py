@@ -35,21 +35,18 @@ def crop_window(im, pos, model_sz, original_sz, avg_chans, islog=False):
     left, top = int(max(0.0, -x0)), int(max(0.0, -y0))
     right, bottom = int(max(0.0, x1 - cols + 1)), int(max(0.0, y1 - rows + 1))
     x0, x1, y0, y1 = x0 + left, x1 + left, y0 + top, y1 + top
+    ya, yb, xa, xb = int(y0), int(y1 + 1), int(x0), int(x1 + 1)  # window in the coordinates of the padded frame
     if left or top or right or bottom:
-        canvas = np.zeros((rows + top + bottom, cols + left + right, chans), np.uint8)
-        canvas[top:top + rows, left:left + cols, :] = im
-        if top:
-            canvas[0:top, left:left + cols, :] = avg_chans
-        if bottom:
-            canvas[rows + top:, left:left + cols, :] = avg_chans
-        if left:
-            canvas[:, 0:left, :] = avg_chans
-        if right:
-            canvas[:, cols + left:, :] = avg_chans
-        src = canvas
+        # The reference materialises the whole padded frame (base_tracker.py:99-112) and slices it; every padded pixel is the
+        # channel mean (cast to uint8 on assignment) and every other pixel is the frame, so only the window is built here.
+        patch = np.empty((yb - ya, xb - xa, chans), np.uint8)
+        patch[:] = avg_chans
+        ia, ib = max(ya, top), min(yb, top + rows)
+        ja, jb = max(xa, left), min(xb, left + cols)
+        if ib > ia and jb > ja:
+            patch[ia - ya:ib - ya, ja - xa:jb - xa, :] = im[ia - top:ib - top, ja - left:jb - left, :]
     else:
-        src = im
-    patch = src[int(y0):int(y1 + 1), int(x0):int(x1 + 1), :]
+        patch = im[ya:yb, xa:xb, :]
     if not np.array_equal(model_sz, original_sz):
         patch = cv2.resize(patch, (model_sz, model_sz))
     if islog:

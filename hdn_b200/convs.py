@@ -1,0 +1,57 @@
+"""Dense-convolution helpers for the backbones (library GEMM territory: SURVEY 2.3 K7).
+
+cuDNN has no fast fp32 kernel for the stride-8 backbone's DILATED 3x3 convolutions at tracking batch sizes: with TF32
+off it falls back to `conv2d_grouped_direct_kernel`, 2.7 ms for one 512->512 31x31 dilation-4 layer on a B200
+(1.7 TFLOP/s) -- three such layers are 61 % of the whole ResNet-50 forward (profiles/r01_backbone_profile.txt).
+
+`dilated_conv3x3` computes the same convolution as 9 plain fp32 GEMMs (cuBLAS, TF32 off): with the input zero-padded
+by the dilation d and each plane flattened, tap (ky,kx) reads the contiguous slice starting at ky*d*Wp + kx*d, so
+    out_flat[:, q] = sum_tap  W[:, :, ky, kx] @ xpad_flat[:, off_tap + q],   q = r*Wp + c,
+and the valid outputs are the columns c < W of that Wp-strided grid (W/Wp of the work is useful: 31/39 at d = 4).
+0.30 ms for the same layer; results differ from cuDNN's by fp32 summation order only (~3e-6 relative).
+"""
+import torch
+import torch.nn.functional as F
+
+_TAP_CACHE = {}
+
+
+def _tap_major(weight):
+    """[Cout,Cin,3,3] -> [9,Cout,Cin] contiguous, cached per parameter version (load_state_dict / .cuda() invalidate it)."""
+    key = id(weight)
+    ver = (weight.data_ptr(), weight._version, weight.device)
+    hit = _TAP_CACHE.get(key)
+    if hit is None or hit[0] != ver:
+        hit = (ver, weight.detach().permute(2, 3, 0, 1).reshape(9, weight.shape[0], weight.shape[1]).contiguous())
+        _TAP_CACHE[key] = hit
+    return hit[1]
+
+
+def wants_shifted_gemm(conv, x):
+    return (x.is_cuda and conv.kernel_size == (3, 3) and conv.stride == (1, 1) and conv.groups == 1 and conv.bias is None
+            and conv.dilation[0] == conv.dilation[1] > 1 and conv.padding == conv.dilation and conv.in_channels >= 512
+            and x.dtype == torch.float32)
+
+
+def dilated_conv3x3(x, conv):
+    """conv(x) for a stride-1 3x3 convolution with padding == dilation, as 9 shifted GEMMs."""
+    d = conv.dilation[0]
+    wt = _tap_major(conv.weight)
+    B, Cin, H, W = x.shape
+    Wp = W + 2 * d
+    xp = F.pad(x, (d, d, d, d)).reshape(B, Cin, -1)
+    L = (H - 1) * Wp + W
+    out = x.new_empty((B, wt.shape[1], H * Wp))
+    acc = out[:, :, :L]
+    for tap in range(9):
+        off = (tap // 3) * d * Wp + (tap % 3) * d
+        xs = xp[:, :, off:off + L]
+        if tap == 0:
+            torch.matmul(wt[0], xs, out=acc) if B == 1 else torch.bmm(wt[0].expand(B, -1, -1), xs, out=acc)
+        else:
+            acc.baddbmm_(wt[tap].expand(B, -1, -1), xs)
+    return out.view(B, -1, H, Wp)[:, :, :, :W]
+
+
+def conv3x3(conv, x):
+    return dilated_conv3x3(x, conv) if wants_shifted_gemm(conv, x) else conv(x)

@@ -130,3 +130,42 @@ def test_log_polar_template_image(cfg):
 def test_tracker_builder_dispatch(cfg):
     from hdn.tracker.tracker_builder import TRACKS
     assert set(TRACKS) == {"hdnTracker", "hdnTrackerHomoProje2e"}
+
+
+def _crop_full_canvas(im, pos, model_sz, original_sz, avg):
+    """The reference's construction (base_tracker.py:76-118): pad the WHOLE frame, then slice.  Used to stress crop_window."""
+    import cv2
+    r, c, k = im.shape
+    half = (original_sz - 1) / 2
+    x0 = np.floor(pos[0] - half + 0.5); x1 = x0 + original_sz - 1
+    y0 = np.floor(pos[1] - half + 0.5); y1 = y0 + original_sz - 1
+    lp, tp = int(max(0., -x0)), int(max(0., -y0))
+    rp, bp = int(max(0., x1 - c + 1)), int(max(0., y1 - r + 1))
+    x0, x1, y0, y1 = x0 + lp, x1 + lp, y0 + tp, y1 + tp
+    if any([tp, bp, lp, rp]):
+        te = np.zeros((r + tp + bp, c + lp + rp, k), np.uint8)
+        te[tp:tp + r, lp:lp + c, :] = im
+        if tp: te[0:tp, lp:lp + c, :] = avg
+        if bp: te[r + tp:, lp:lp + c, :] = avg
+        if lp: te[:, 0:lp, :] = avg
+        if rp: te[:, c + lp:, :] = avg
+        patch = te[int(y0):int(y1 + 1), int(x0):int(x1 + 1), :]
+    else:
+        patch = im[int(y0):int(y1 + 1), int(x0):int(x1 + 1), :]
+    if not np.array_equal(model_sz, original_sz):
+        patch = cv2.resize(patch, (model_sz, model_sz))
+    return patch.transpose(2, 0, 1)[np.newaxis].astype(np.float32), (x0, y0, x1 + 1, y1 + 1)
+
+
+def test_crop_window_equals_full_canvas_construction(cfg):
+    from hdn.tracker.base_tracker import crop_window
+    import synth
+    img = synth.texture(3, 90, 130)
+    avg = np.mean(img, axis=(0, 1))
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        pos = np.array([rng.uniform(-60, 190), rng.uniform(-60, 150)])
+        osz = float(np.floor(rng.uniform(5, 140))) if rng.random() < 0.5 else float(rng.uniform(5, 140))  # stage 3 passes fractional sizes
+        a, abox = crop_window(img, pos, 31, osz, avg)
+        b, bbox = _crop_full_canvas(img, pos, 31, osz, avg)
+        assert np.array_equal(a, b) and tuple(abox) == tuple(bbox)
