@@ -178,8 +178,15 @@ class ModelBuilder(nn.Module):
         return ops.score_argmax_packed(out["cls_lp"], out["loc_lp"], None, 0.0)
 
     def _stage3_packed(self, pair, h4p):
-        H, s_homo, s_simi = self.track_proj({"org_imgs": pair, "input_tensors": pair, "h4p": h4p, "patch_indices": None}, None)
-        return torch.cat((H.reshape(-1), s_homo.reshape(1), s_simi.reshape(1)))
+        """-> [B, 11]: H (9), homo score, similarity score PER ITEM.  For B = 1 these are exactly track_proj's returns (the
+        reference scores only sample 0 of a batch, model_builder...py:213-216; here every item is scored as if alone)."""
+        offsets, patch_1, patch_2 = self.hm_net.offsets(pair)
+        M, Minv = self._m_pair(pair.device)
+        H_mat, pred_I2 = ops.dlt_warp(h4p, offsets, pair[:, :1], M, Minv)
+        pred_feat = self.hm_net.ShareFeature(pred_I2)
+        s_homo = torch.abs(patch_2 - pred_feat)[:, 0].sum((1, 2)) / (127 * 127)
+        s_simi = torch.abs(patch_2 - patch_1)[:, 0].sum((1, 2)) / (127 * 127)
+        return torch.cat((H_mat.reshape(-1, 9), s_homo[:, None], s_simi[:, None]), 1)
 
     @torch.no_grad()
     def track_new_scored(self, x, win_influence=None):
@@ -199,7 +206,7 @@ class ModelBuilder(nn.Module):
 
     @torch.no_grad()
     def track_proj_packed(self, pair, h4p):
-        """track_proj for one pair with a single read-back: NumPy [H (9 per item) ..., homo_score, simi_score]."""
+        """track_proj with a single read-back: NumPy [B, 11] = H (9), homo_score, simi_score per item."""
         return self._staged("s3", self._stage3_packed, pair, h4p).cpu().numpy()
 
     # ------------------------------------------------------------------ reference helpers (:69-80)

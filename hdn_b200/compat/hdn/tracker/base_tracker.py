@@ -21,6 +21,13 @@ class BaseTracker(object):
         raise NotImplementedError
 
 
+def _fill(region, colour):
+    """region[..., c] = colour[c]; per channel, because NumPy broadcasts a length-3 inner axis ~10x slower than a scalar fill."""
+    if region.size:
+        for ch in range(region.shape[2]):
+            region[:, :, ch] = colour[ch]
+
+
 def crop_window(im, pos, model_sz, original_sz, avg_chans, islog=False):
     """-> (float32 ndarray [1,C,model_sz,model_sz], (xmin, ymin, xmax+1, ymax+1) in padded-frame coordinates)."""
     if isinstance(pos, float):
@@ -40,11 +47,17 @@ def crop_window(im, pos, model_sz, original_sz, avg_chans, islog=False):
         # The reference materialises the whole padded frame (base_tracker.py:99-112) and slices it; every padded pixel is the
         # channel mean (cast to uint8 on assignment) and every other pixel is the frame, so only the window is built here.
         patch = np.empty((yb - ya, xb - xa, chans), np.uint8)
-        patch[:] = avg_chans
+        fill = np.asarray(avg_chans).astype(np.uint8)  # the same float -> uint8 cast the reference's slice assignment performs
         ia, ib = max(ya, top), min(yb, top + rows)
         ja, jb = max(xa, left), min(xb, left + cols)
         if ib > ia and jb > ja:
             patch[ia - ya:ib - ya, ja - xa:jb - xa, :] = im[ia - top:ib - top, ja - left:jb - left, :]
+            _fill(patch[:ia - ya], fill)
+            _fill(patch[ib - ya:], fill)
+            _fill(patch[ia - ya:ib - ya, :ja - xa], fill)
+            _fill(patch[ia - ya:ib - ya, jb - xa:], fill)
+        else:
+            _fill(patch, fill)
     else:
         patch = im[ya:yb, xa:xb, :]
     if not np.array_equal(model_sz, original_sz):

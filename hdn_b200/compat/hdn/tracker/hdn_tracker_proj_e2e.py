@@ -20,12 +20,45 @@ import torch
 
 from hdn.core.config import cfg
 from hdn.tracker.base_tracker import crop_window, to_model_tensor
-from hdn.tracker.hdn_tracker import hdnTracker
+from hdn.tracker.hdn_tracker import decode_center, decode_logpolar, hdnTracker
 from hdn.utils.point import Point
 from hdn.utils.transform import img_rot_around_center, rot_scale_around_center_shift_tran
 from homo_estimator.Deep_homography.Oneline_DLTv1.tools.get_img_info import get_search_info, get_template_info, merge_tmp_search
 
 _EYE = [[1, 0, 0], [0, 1, 0], [0, 0, 1]]
+
+
+def serve(model, kind, batch):
+    """Answer one (possibly batched) stage request.  batch: float32 ndarray [B,...].  -> list of B per-item results."""
+    x = torch.from_numpy(np.ascontiguousarray(batch))
+    if cfg.CUDA:
+        x = x.pin_memory().cuda(non_blocking=True)
+    B = x.shape[0]
+    if kind == "template":
+        model.template(x)
+        return [x[i:i + 1] for i in range(B)]
+    if kind == "stage1":
+        idx, ps, sc, g = model.track_new_scored(x, cfg.TRACK.WINDOW_INFLUENCE)
+    elif kind == "stage2":
+        idx, ps, sc, g = model.track_new_lp_scored(x, [0, 0])
+    elif kind == "stage3":
+        if getattr(model, "_h4p_cache", None) is None or model._h4p_cache.shape[0] != B or model._h4p_cache.device != x.device:
+            model._h4p_cache = torch.tensor([[0.0, 0.0, 0.0, 127.0, 127.0, 127.0, 127.0, 0.0]], device=x.device).repeat(B, 1)  # get_img_info.py:93-98
+        out = model.track_proj_packed(x, model._h4p_cache)
+        return [out[i] for i in range(B)]
+    else:
+        raise ValueError(kind)
+    return [(idx[i], ps[i], sc[i], g[i]) for i in range(B)]
+
+
+def serve_alone(model, steps):
+    """Drive one tracker's step generator with batch-1 network calls; returns the generator's return value."""
+    try:
+        kind, payload = next(steps)
+        while True:
+            kind, payload = steps.send(serve(model, kind, payload)[0])
+    except StopIteration as done:
+        return done.value
 
 
 class hdnTrackerHomo(hdnTracker):
@@ -50,22 +83,21 @@ class hdnTrackerHomo(hdnTracker):
                 "h4p": up(info["four_points"]), "patch_indices": None}  # identity indices (get_img_info.py:92): gather skipped
         return self.model.track_proj(data, tmp_mask)
 
-    def _h4p(self):
-        if getattr(self, "_h4p_dev", None) is None:
-            self._h4p_dev = torch.tensor([[0.0, 0.0, 0.0, 127.0, 127.0, 127.0, 127.0, 0.0]]).cuda()  # get_img_info.py:93-98
-        return self._h4p_dev
-
     # ------------------------------------------------------------------ first frame
     def init(self, img, bbox, poly, gt_points, first_point):
+        """proj_e2e:60-120.  Same arguments as the reference."""
+        serve_alone(self.model, self._init_steps(img, bbox, poly, gt_points, first_point))
+
+    def _init_steps(self, img, bbox, poly, gt_points, first_point):
+        """Generator form of `init`: yields ('template', z_crop) so several trackers can be templated in one batch."""
         self._start_state(bbox, poly, first_point)
         w_z, h_z, s_z = self._context_size(cfg.TRACK.CONTEXT_AMOUNT)
         _, _, s_z_sm = self._context_size(0)  # no-context window: the homography estimator's crop
         self.channel_average = np.mean(img, axis=(0, 1))
-        self.z_crop, self.z_crop_points = self.get_subwindow_for_homo(img, self.center_pos, cfg.TRACK.EXEMPLAR_SIZE, s_z, self.channel_average,
-                                                                      islog=1)
+        z_crop, self.z_crop_points = crop_window(img, self.center_pos, cfg.TRACK.EXEMPLAR_SIZE, s_z, self.channel_average, islog=1)
         z_sm, self.z_crop_points_sm = crop_window(img, self.center_pos, cfg.TRACK.EXEMPLAR_SIZE, s_z_sm, self.channel_average, islog=1)
         self.z_crop_sm = torch.from_numpy(z_sm)  # only read on the host (get_template_info): no upload needed
-        self.model.template(self.z_crop)
+        self.z_crop = yield ("template", z_crop)
         self.init_img = img
         self.init_crop_size = np.array([w_z, h_z])
         self.init_size = self.size
@@ -95,6 +127,13 @@ class hdnTrackerHomo(hdnTracker):
 
     # ------------------------------------------------------------------ every other frame
     def track_new(self, fr_idx, img, gt_box=None, gt_poly=None, gt_points=None):
+        """proj_e2e:141-285.  Same arguments and result dict as the reference."""
+        return serve_alone(self.model, self._track_steps(fr_idx, img))
+
+    def _track_steps(self, fr_idx, img):
+        """Generator form of `track_new`: yields ('stage1'|'stage2'|'stage3', host array) requests and receives the stage's
+        read-back, so a driver can run many sequences in lock-step with ONE batched network call per stage
+        (hdn_b200.batched.LockstepTrackers); `track_new` drives it alone."""
         # 0. bring the frame back into the template's pose
         if np.linalg.det(self.H_total) == 0:
             self.H_total = np.array(_EYE).astype(np.float32)
@@ -107,7 +146,9 @@ class hdnTrackerHomo(hdnTracker):
         s_x = np.floor(s_z * ratio)
 
         # 1. translation
-        best_idx, pbest, best_score, pred_c = self._stage1(self.get_subwindow(img, center_pos, cfg.TRACK.INSTANCE_SIZE, s_x, self.channel_average))
+        x_crop, _ = crop_window(img, center_pos, cfg.TRACK.INSTANCE_SIZE, s_x, self.channel_average)
+        idx, ps, sc, g = yield ("stage1", x_crop)
+        best_idx, pbest, best_score, pred_c = int(idx), ps, sc, decode_center(self.points, int(idx), g)
         stop_update = pbest < 0.05
         center = [0, 0] if stop_update else pred_c / scale_z
         cx, cy = center[0] + center_pos[0], center[1] + center_pos[1]
@@ -115,7 +156,9 @@ class hdnTrackerHomo(hdnTracker):
         self.center_pos = np.array([cx, cy])
 
         # 2. scale / rotation in log-polar coordinates
-        _, lp_score, sim_lp = self._stage2(self.get_subwindow(img, self.center_pos, cfg.TRACK.INSTANCE_SIZE, s_x, self.channel_average), fr_idx)
+        x_moved, _ = crop_window(img, self.center_pos, cfg.TRACK.INSTANCE_SIZE, s_x, self.channel_average)
+        idx, _, lp_score, g = yield ("stage2", x_moved)
+        sim_lp = decode_logpolar(self.points_lp, int(idx), g)
         if stop_update or lp_score < 0.25:
             sim_lp = [1, 1, 0, 0]
         scale_delta = sim_lp[0] * cur_sz / self.init_s_z
@@ -130,12 +173,7 @@ class hdnTrackerHomo(hdnTracker):
         crop_w = self.z_crop_points_sm[2] - self.z_crop_points_sm[0] + 1
         crop_h = self.z_crop_points_sm[3] - self.z_crop_points_sm[1] + 1
         search_gray, _ = get_search_info(torch.from_numpy(x_homo)[:, 0:3, :, :])
-        if hasattr(self.model, "track_proj_packed") and cfg.CUDA:
-            pair = torch.from_numpy(np.concatenate([self.init_homo_tmp, search_gray], 0).astype(np.float32)).unsqueeze(0).pin_memory()
-            both = self.model.track_proj_packed(pair.cuda(non_blocking=True), self._h4p())  # one upload, one read-back (H + scores)
-        else:
-            H_hm, homo_score, simi_score = self.homo_estimate(self.init_homo_tmp, search_gray, None)
-            both = torch.cat((H_hm.reshape(-1)[:9], homo_score.reshape(1))).detach().cpu().numpy()
+        both = yield ("stage3", np.concatenate([self.init_homo_tmp, search_gray], 0).astype(np.float32)[np.newaxis])  # H (9) + scores
         homo_score = both[9]
         H_hm = np.linalg.inv(both[:9].reshape(3, 3))
         H_hm = (1.0 / H_hm.item(8)) * H_hm

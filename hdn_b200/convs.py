@@ -54,4 +54,7 @@ def dilated_conv3x3(x, conv):
 
 
 def conv3x3(conv, x):
-    return dilated_conv3x3(x, conv) if wants_shifted_gemm(conv, x) else conv(x)
+    """Inference path only: with autograd recording, defer to the module (training is out of scope)."""
+    if wants_shifted_gemm(conv, x) and not (torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad)):
+        return dilated_conv3x3(x, conv)
+    return conv(x)

@@ -32,6 +32,7 @@ def parse():
                                                      "proj_e2e_GOT_unconstrained_v2.yaml"))
     ap.add_argument("--graphs", type=int, default=1, help="replay the three network stages from CUDA graphs")
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--lockstep", type=int, default=0, help="advance this many sequences per GPU in lock-step (0 = one at a time)")
     return ap.parse_args()
 
 
@@ -69,6 +70,30 @@ def track_sequence(tracker, frames, polys):
     return np.asarray(out), time.perf_counter() - t0
 
 
+def first_frame_args(gt):
+    """What tools/test.py:118-130 derives from the first ground-truth polygon."""
+    from hdn.utils.bbox import get_min_max_bbox, get_w_h_from_poly
+    cx, cy, w, h = get_min_max_bbox(np.array(gt))
+    return [cx - (w - 1) / 2, cy - (h - 1) / 2, w, h], get_w_h_from_poly(np.array(gt)), gt, np.array([gt[:2]])
+
+
+def track_lockstep(model, seqs):
+    """seqs: list of (frames, polys) of equal length -> (polygons [S, n-1, 4, 2], seconds in track_new)."""
+    import torch
+    from hdn_b200.batched import LockstepTrackers
+    group = LockstepTrackers(model, len(seqs))
+    firsts = [first_frame_args(p[0]) for _, p in seqs]
+    group.init([f[0] for f, _ in seqs], *[list(col) for col in zip(*firsts)])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = []
+    for idx in range(1, len(seqs[0][0])):
+        res = group.track_new(idx, [f[idx] for f, _ in seqs])
+        out.append([np.asarray(r["polygon"], np.float64) for r in res])
+    torch.cuda.synchronize()
+    return np.asarray(out).transpose(1, 0, 2, 3), time.perf_counter() - t0
+
+
 def main():
     a = parse()
     import torch
@@ -82,14 +107,25 @@ def main():
     # warm-up on a short private sequence (cuDNN autotune, graph capture)
     wf, wp = synthetic.sequence(99, a.warmup + 1, size=(H, W), obj=(H // 3, W // 3))
     track_sequence(tracker, wf, wp)
+    if a.lockstep:
+        track_lockstep(model, [(wf, wp)] * min(a.lockstep, len(mine)))
     shard.barrier()
     t_all0 = time.perf_counter()
     busy, n_frames, results = 0.0, 0, {}
-    for s in mine:
-        polys, dt = track_sequence(tracker, *seqs[s])
-        results[s] = polys
-        busy += dt
-        n_frames += len(polys)
+    if a.lockstep:
+        for lo in range(0, len(mine), a.lockstep):
+            chunk = mine[lo:lo + a.lockstep]
+            polys, dt = track_lockstep(model, [seqs[s] for s in chunk])
+            for s, p in zip(chunk, polys):
+                results[s] = p
+            busy += dt
+            n_frames += polys.shape[0] * polys.shape[1]
+    else:
+        for s in mine:
+            polys, dt = track_sequence(tracker, *seqs[s])
+            results[s] = polys
+            busy += dt
+            n_frames += len(polys)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t_all0
     wall_max = shard.max_over_ranks(wall, torch.device("cuda", local_rank))
@@ -104,7 +140,7 @@ def main():
     if rank == 0:
         line = {"metric": "tracker frames/sec (hdnTrackerHomo.track_new, native 127/255 crops)", "value": total_frames / wall_max, "unit": "frames/s",
                 "n_gpus": world, "sequences": a.sequences, "frames_per_sequence": a.frames, "frame_size": [H, W],
-                "per_rank_fps": n_frames / busy if busy else None, "ms_per_frame": 1e3 * busy / max(n_frames, 1), "cuda_graphs": bool(a.graphs),
+                "per_rank_fps": n_frames / busy if busy else None, "ms_per_frame": 1e3 * busy / max(n_frames, 1), "cuda_graphs": bool(a.graphs), "lockstep_per_gpu": a.lockstep,
                 "weights": a.snapshot or "seeded fixture (hdn_b200.synthetic.fill_weights)", "data": "synthetic homography walk",
                 "polygon_checksum": float(slot.abs().sum().item())}
         print(json.dumps(line), flush=True)

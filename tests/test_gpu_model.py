@@ -139,3 +139,17 @@ def test_sanitizer_smoke_shapes():
     out = ops.xcorr_depthwise(x, k)
     ref = torch.nn.functional.conv2d(x.view(1, 256, 61, 61), k.view(256, 1, 29, 29), groups=256)
     assert torch.allclose(out, ref.view_as(out), rtol=1e-3, atol=1e-4 * float(ref.abs().max()))
+
+
+def test_lockstep_batch_equals_single_sequence_tracking():
+    """4 sequences advanced in lock-step (one batched network call per stage) == each tracked alone, within fp32 noise."""
+    import synth
+    from hdn.tracker.tracker_builder import build_tracker
+    from hdn_b200 import runner
+    model, _ = build_model()
+    seqs = [synth.sequence(30 + s, 5) for s in range(4)]
+    polys, _ = runner.track_lockstep(model, seqs)
+    diag = float(np.hypot(*seqs[0][0][0].shape[:2]))
+    for s, (frames, gt) in enumerate(seqs):
+        alone, _ = runner.track_sequence(build_tracker(model), frames, gt)
+        assert np.abs(polys[s] - alone).max() <= 1e-3 * diag, s
