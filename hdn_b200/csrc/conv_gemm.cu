@@ -1,0 +1,251 @@
+// conv_gemm.cu -- stride-1 1x1 / (dilated) 3x3 convolution as an implicit GEMM on the 5th-gen tensor cores
+// (tcgen05.mma, accumulator in TMEM), fp32-accurate through 3xTF32 operand splitting, with the eval-mode BatchNorm,
+// the residual add and the ReLU of a ResNet block fused into the epilogue.
+//
+// Replaces, for the backbone's stride-1 layers (hdn/models/backbone/resnet_atrous.py:62-110, neck.py:11-29), the
+// cuDNN fp32 convolutions of the reference.  With TF32 off cuDNN runs these at 2-7 TFLOP/s for tracking batch sizes
+// (and falls back to a direct kernel for the dilated layers); plain TF32 would be fast but its 10-bit mantissa can
+// flip the arg-max that must stay bit-exact.  3xTF32 keeps fp32 accuracy on the tensor cores:
+//     x = hi + lo,  hi = x with the low 13 mantissa bits cleared (exactly a TF32 number),  lo = x - hi  (exact in fp32)
+//     a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi          (dropped term a_lo*b_lo <= 2^-20 |a b|)
+// accumulated in fp32 in TMEM.
+//
+// GEMM view per image:  D[co, p] = sum_{tap, ci} Wt[co, tap, ci] * X[ci, p + shift(tap)]      (zero outside the image)
+//     A = Wt   [Cout x K]   K = taps*Cin contiguous  -> UMMA K-major
+//     B = X    [K x HW]     pixels contiguous        -> UMMA MN-major
+// One CTA owns a 128 (co) x BN (pixels) tile.  All 256 threads stage a 32-deep K block: global -> registers -> hi / lo
+// -> shared memory in the canonical no-swizzle UMMA layouts (8x16-byte core matrices); one thread then issues
+// 4 k-steps x 3 tcgen05.mma (kind::tf32, M=128, N=BN, K=8) and commits them to an mbarrier that frees the stage.
+// Two stages: the tensor core works on block k while the threads stage block k+1.
+// Epilogue: tcgen05.ld (32 lanes x 32b x 16 columns) -> y = acc*scale[co] + shift[co] (+ residual) (ReLU) -> global NCHW.
+#include "common.cuh"
+
+namespace hdn {
+
+constexpr int CG_BM = 128, CG_BK = 32, CG_THREADS = 256;
+
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    // cute::UMMA::SmemDescriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout=0 (no swizzle) [61,64)
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
+    hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    lo = x - hi;
+}
+
+struct ConvGemmArgs {
+    const float *x, *wt, *scale, *shift, *residual;
+    float *out;
+    int Cin, Cout, H, W, taps, dil, relu;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_tf32x3_kernel(ConvGemmArgs a) {
+    constexpr int A_TILE = CG_BM * CG_BK * 4;  // bytes of one operand tile (hi or lo)
+    constexpr int B_TILE = CG_BK * BN * 4;
+    constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
+    constexpr uint32_t A_SBO = 128, A_LBO = (CG_BM / 8) * 128;  // K-major: 8-row groups 128 B apart, 4-wide K chunks A_LBO apart
+    constexpr uint32_t B_SBO = 128, B_LBO = (BN / 4) * 128;     // MN-major: 4-pixel atoms 128 B apart, 8-deep K groups B_LBO apart
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(CG_BM >> 4) << 24);
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t bar_free[2], bar_done;
+    __shared__ uint32_t tmem_base_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int HW = a.H * a.W;
+    const int pix0 = blockIdx.x * BN, co0 = blockIdx.y * CG_BM, img = blockIdx.z;
+    const int Ktot = a.taps * a.Cin;
+    const float *xb = a.x + (size_t)img * a.Cin * HW;
+
+    if (tid == 0) {
+        mbar_init(&bar_free[0], 1);
+        mbar_init(&bar_free[1], 1);
+        mbar_init(&bar_done, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"((uint32_t)BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base_slot;
+
+    // ---- per-thread staging coordinates (fixed for the whole K loop) ------------------------------------------------
+    // A: float4 slots f = tid + 256*j, j < 4:  r0 = f&7, kc = (f>>3)&7, rg = f>>6   (row = rg*8 + r0, k = kc*4..+3)
+    // B: float4 slots f = tid + 256*j, j < BN/32: k0 = f&7, n4 = (f>>3)&(BN/4-1), kg = f>>(3+log2(BN/4))  (k = kg*8+k0, n = n4*4..+3)
+    constexpr int NBJ = BN / 32;
+    int b_r[NBJ][4], b_c[NBJ][4];  // pixel row / column of the 4 pixels of each slot (row = -1: beyond the image)
+#pragma unroll
+    for (int j = 0; j < NBJ; ++j) {
+        const int f = tid + CG_THREADS * j;
+        const int n4 = (f >> 3) & (BN / 4 - 1);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int p = pix0 + n4 * 4 + e;
+            b_r[j][e] = p < HW ? p / a.W : -1;
+            b_c[j][e] = p < HW ? p - (p / a.W) * a.W : 0;
+        }
+    }
+
+    const int nkb = Ktot / CG_BK;
+    for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb & 1;
+        unsigned char *st = smem + s * STAGE;
+        float *a_hi = reinterpret_cast<float *>(st), *a_lo = reinterpret_cast<float *>(st + A_TILE);
+        float *b_hi = reinterpret_cast<float *>(st + 2 * A_TILE), *b_lo = reinterpret_cast<float *>(st + 2 * A_TILE + B_TILE);
+        const int k0 = kb * CG_BK;
+        const int tap = k0 / a.Cin, ci0 = k0 - tap * a.Cin;
+        const int dy = a.taps == 1 ? 0 : (tap / 3 - 1) * a.dil, dx = a.taps == 1 ? 0 : (tap % 3 - 1) * a.dil;
+
+        // ---- global -> registers (issued before waiting for the stage, so the loads overlap the running MMAs) ------
+        float4 av[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int f = tid + CG_THREADS * j;
+            const int r0 = f & 7, kc = (f >> 3) & 7, rg = f >> 6;
+            av[j] = __ldg(reinterpret_cast<const float4 *>(a.wt + (size_t)(co0 + rg * 8 + r0) * Ktot + k0 + kc * 4));
+        }
+        float bv[NBJ][4];
+#pragma unroll
+        for (int j = 0; j < NBJ; ++j) {
+            const int f = tid + CG_THREADS * j;
+            const int kk = (f & 7) + 8 * (f >> (3 + (BN == 128 ? 5 : 4)));
+            const float *src = xb + (size_t)(ci0 + kk) * HW;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int r = b_r[j][e] + dy, c = b_c[j][e] + dx;
+                const bool ok = b_r[j][e] >= 0 && r >= 0 && r < a.H && c >= 0 && c < a.W;
+                bv[j][e] = ok ? __ldg(src + r * a.W + c) : 0.f;
+            }
+        }
+        // ---- the MMAs that read this stage two blocks ago must have retired ------------------------------------------
+        if (kb >= 2) mbar_wait(&bar_free[s], ((kb >> 1) - 1) & 1);
+        // ---- registers -> hi / lo -> shared (canonical UMMA layouts) ---------------------------------------------------
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int f = tid + CG_THREADS * j;
+            const int r0 = f & 7, kc = (f >> 3) & 7, rg = f >> 6;
+            float4 h, l;
+            split_tf32(av[j].x, h.x, l.x); split_tf32(av[j].y, h.y, l.y); split_tf32(av[j].z, h.z, l.z); split_tf32(av[j].w, h.w, l.w);
+            const int off = (kc * A_LBO + rg * A_SBO + r0 * 16) >> 2;
+            *reinterpret_cast<float4 *>(a_hi + off) = h;
+            *reinterpret_cast<float4 *>(a_lo + off) = l;
+        }
+#pragma unroll
+        for (int j = 0; j < NBJ; ++j) {
+            const int f = tid + CG_THREADS * j;
+            const int kq = f & 7, n4 = (f >> 3) & (BN / 4 - 1), kg = f >> (3 + (BN == 128 ? 5 : 4));
+            float4 h, l;
+            split_tf32(bv[j][0], h.x, l.x); split_tf32(bv[j][1], h.y, l.y); split_tf32(bv[j][2], h.z, l.z); split_tf32(bv[j][3], h.w, l.w);
+            const int off = (kg * B_LBO + n4 * B_SBO + kq * 16) >> 2;
+            *reinterpret_cast<float4 *>(b_hi + off) = h;
+            *reinterpret_cast<float4 *>(b_lo + off) = l;
+        }
+        fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t sa_hi = smem_u32(a_hi), sa_lo = smem_u32(a_lo), sb_hi = smem_u32(b_hi), sb_lo = smem_u32(b_lo);
+#pragma unroll
+            for (int ks = 0; ks < CG_BK / 8; ++ks) {
+                const uint64_t dah = umma_smem_desc(sa_hi + ks * 2 * A_LBO, A_LBO, A_SBO), dal = umma_smem_desc(sa_lo + ks * 2 * A_LBO, A_LBO, A_SBO);
+                const uint64_t dbh = umma_smem_desc(sb_hi + ks * B_LBO, B_LBO, B_SBO), dbl = umma_smem_desc(sb_lo + ks * B_LBO, B_LBO, B_SBO);
+                umma_tf32(tmem_d, dal, dbh, IDESC, (kb | ks) != 0);  // small terms first
+                umma_tf32(tmem_d, dah, dbl, IDESC, 1);
+                umma_tf32(tmem_d, dah, dbh, IDESC, 1);
+            }
+            umma_commit(&bar_free[s]);                   // arrives when the MMAs above have finished reading the stage
+            if (kb == nkb - 1) umma_commit(&bar_done);  // ... and when the accumulator is final
+        }
+    }
+
+    // ---- epilogue: TMEM -> registers -> BN / residual / ReLU -> global NCHW ---------------------------------------------
+    mbar_wait(&bar_done, 0);
+    tc_fence_after();
+    const int row = (warp & 3) * 32 + lane;  // TMEM lane = output channel within the tile; a warp may only touch its own quadrant
+    const int co = co0 + row;
+    const float sc = a.scale ? __ldg(a.scale + co) : 1.f, sh = a.shift ? __ldg(a.shift + co) : 0.f;
+    const size_t obase = ((size_t)img * a.Cout + co) * HW;
+    constexpr int HALF = BN / 2;
+#pragma unroll 1
+    for (int c0 = (warp >> 2) * HALF; c0 < (warp >> 2) * HALF + HALF; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            const int p = pix0 + c0 + e;
+            if (p < HW) {
+                float y = fmaf(v[e], sc, sh);
+                if (a.residual) y += __ldg(a.residual + obase + p);
+                if (a.relu) y = fmaxf(y, 0.f);
+                a.out[obase + p] = y;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)BN));
+}
+
+template <int BN>
+static int launch_conv_gemm(const ConvGemmArgs &a, int B, cudaStream_t st) {
+    constexpr size_t SMEM = 2 * (2 * CG_BM * CG_BK * 4 + 2 * CG_BK * BN * 4) + 1024;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    dim3 grid((a.H * a.W + BN - 1) / BN, a.Cout / CG_BM, B);
+    conv_gemm_tf32x3_kernel<BN><<<grid, CG_THREADS, SMEM, st>>>(a);
+    count_launch();
+    return launch_status();
+}
+
+}  // namespace hdn
+
+using namespace hdn;
+
+extern "C" int hdn_conv_gemm_supported(int Cin, int Cout, int ksize, int dilation) {
+    return (Cin >= 32 && Cin % 32 == 0 && Cout % CG_BM == 0 && (ksize == 1 || ksize == 3) && dilation >= 1) ? 1 : 0;
+}
+
+extern "C" int hdn_conv_gemm_f32(const float *x, const float *wt, const float *scale, const float *shift, const float *residual, float *out,
+                                 int B, int Cin, int Cout, int H, int W, int ksize, int dilation, int relu, hdn_stream_t stream) {
+    if (!x || !wt || !out) return HDN_ERR_NULL;
+    if (B < 1 || H < 1 || W < 1 || B > 65535) return HDN_ERR_SHAPE;
+    if (!hdn_conv_gemm_supported(Cin, Cout, ksize, dilation)) return HDN_ERR_UNSUPPORTED;
+    if (reinterpret_cast<uintptr_t>(wt) & 15u) return HDN_ERR_ALIGN;
+    ConvGemmArgs a{x, wt, scale, shift, residual, out, Cin, Cout, H, W, ksize * ksize, dilation, relu};
+    const long long tiles128 = (long long)((H * W + 127) / 128) * (Cout / CG_BM) * B;
+    // small problems (tracking batch sizes): narrower pixel tiles put more CTAs on the 148 SMs
+    return tiles128 >= 2 * sm_count() ? launch_conv_gemm<128>(a, B, (cudaStream_t)stream) : launch_conv_gemm<64>(a, B, (cudaStream_t)stream);
+}
