@@ -8,11 +8,15 @@
 // flip the arg-max that must stay bit-exact.  3xTF32 keeps fp32 accuracy on the tensor cores:
 //     x = hi + lo,  hi = x with the low 13 mantissa bits cleared (exactly a TF32 number),  lo = x - hi  (exact in fp32)
 //     a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi          (dropped term a_lo*b_lo <= 2^-20 |a b|)
-// accumulated in fp32 in TMEM.
+// accumulated in fp32 in TMEM.  The tensor core adds into its accumulator with truncation, whose bias grows with the
+// length of the sum (2.7e-5 of max|out| at K = 4608, probed), so the accumulation is CHUNKED: every 256 of K the MMAs
+// switch to the other of two TMEM accumulators and the threads fold the finished one into fp32 registers with
+// round-to-nearest adds (Ootomo & Yokota's remedy) while the tensor core keeps running.
 //
 // GEMM view per image:  D[co, p] = sum_{tap, ci} Wt[co, tap, ci] * X[ci, p + shift(tap)]      (zero outside the image)
 //     A = Wt   [Cout x K]   K = taps*Cin contiguous  -> UMMA K-major
-//     B = X    [K x HW]     pixels contiguous        -> UMMA MN-major
+//     B = X    [K x HW]     pixels contiguous in HBM -> transposed to UMMA K-major ([pixel][k]) while staging (MN-major
+//                                                        TF32 without the 32B-base swizzle reads as zeros; probed)
 // One CTA owns a 128 (co) x BN (pixels) tile.  All 256 threads stage a 32-deep K block: global -> registers -> hi / lo
 // -> shared memory in the canonical no-swizzle UMMA layouts (8x16-byte core matrices); one thread then issues
 // 4 k-steps x 3 tcgen05.mma (kind::tf32, M=128, N=BN, K=8) and commits them to an mbarrier that frees the stage.
@@ -23,6 +27,7 @@
 namespace hdn {
 
 constexpr int CG_BM = 128, CG_BK = 32, CG_THREADS = 256;
+constexpr int CG_KCB = 8;  // K blocks per TMEM accumulation chunk (8 x 32 = 256 of K)
 
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     // cute::UMMA::SmemDescriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout=0 (no swizzle) [61,64)
@@ -30,11 +35,17 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_
 }
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    const uint32_t zero = 0;  // disable-output-lane mask: all lanes enabled
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(zero)
         : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -71,10 +82,11 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_tf32x3_kernel(ConvGem
     constexpr int B_TILE = CG_BK * BN * 4;
     constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
     constexpr uint32_t A_SBO = 128, A_LBO = (CG_BM / 8) * 128;  // K-major: 8-row groups 128 B apart, 4-wide K chunks A_LBO apart
-    constexpr uint32_t B_SBO = 128, B_LBO = (BN / 4) * 128;     // MN-major: 4-pixel atoms 128 B apart, 8-deep K groups B_LBO apart
-    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(CG_BM >> 4) << 24);
+    constexpr uint32_t B_SBO = 128, B_LBO = (BN / 8) * 128;     // K-major as well (pixel rows): the tile is transposed while staging
+    // kind::tf32, fp32 accumulate, A and B K-major, N = BN, M = 128 (cute::UMMA::InstrDescriptor bit layout)
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(CG_BM >> 4) << 24);
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ uint64_t bar_free[2], bar_done;
+    __shared__ uint64_t bar_free[2], bar_acc[2];
     __shared__ uint32_t tmem_base_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -86,11 +98,12 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_tf32x3_kernel(ConvGem
     if (tid == 0) {
         mbar_init(&bar_free[0], 1);
         mbar_init(&bar_free[1], 1);
-        mbar_init(&bar_done, 1);
+        mbar_init(&bar_acc[0], 1);
+        mbar_init(&bar_acc[1], 1);
         mbar_fence_init();
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"((uint32_t)BN));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"((uint32_t)(2 * BN)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
@@ -99,23 +112,37 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_tf32x3_kernel(ConvGem
     const uint32_t tmem_d = tmem_base_slot;
 
     // ---- per-thread staging coordinates (fixed for the whole K loop) ------------------------------------------------
-    // A: float4 slots f = tid + 256*j, j < 4:  r0 = f&7, kc = (f>>3)&7, rg = f>>6   (row = rg*8 + r0, k = kc*4..+3)
-    // B: float4 slots f = tid + 256*j, j < BN/32: k0 = f&7, n4 = (f>>3)&(BN/4-1), kg = f>>(3+log2(BN/4))  (k = kg*8+k0, n = n4*4..+3)
+    // A: float4 slots f = tid + 256*j, j < 4:      r0 = f&7, kc = (f>>3)&7, rg = f>>6        (row = rg*8 + r0, k = kc*4..+3)
+    // B: slots f = tid + 256*j, j < BN/32:          n = f % BN (= tid % BN for every j), kc = f / BN   (k = kc*4..+3)
+    //    consecutive lanes -> consecutive pixels: coalesced scalar loads, and one conflict-free 16-byte store per slot.
     constexpr int NBJ = BN / 32;
-    int b_r[NBJ][4], b_c[NBJ][4];  // pixel row / column of the 4 pixels of each slot (row = -1: beyond the image)
+    const int bn = tid % BN;
+    const int bp = pix0 + bn;
+    const int b_r = bp < HW ? bp / a.W : -(1 << 20), b_c = bp < HW ? bp - (bp / a.W) * a.W : 0;  // beyond the image: never valid
+
+    // fp32 register accumulator of this thread's share of the tile: TMEM lane (= channel) row, columns [col_lo, col_lo + BN/2)
+    constexpr int HALF = BN / 2;
+    const int row = (warp & 3) * 32 + lane;  // a warp may only touch its own TMEM lane quadrant
+    const int col_lo = (warp >> 2) * HALF;
+    float racc[HALF];
 #pragma unroll
-    for (int j = 0; j < NBJ; ++j) {
-        const int f = tid + CG_THREADS * j;
-        const int n4 = (f >> 3) & (BN / 4 - 1);
+    for (int e = 0; e < HALF; ++e) racc[e] = 0.f;
+    auto drain = [&](int chunk) {  // fold finished TMEM accumulator `chunk & 1` into racc (round-to-nearest adds)
+        mbar_wait(&bar_acc[chunk & 1], (chunk >> 1) & 1);
+        tc_fence_after();
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int p = pix0 + n4 * 4 + e;
-            b_r[j][e] = p < HW ? p / a.W : -1;
-            b_c[j][e] = p < HW ? p - (p / a.W) * a.W : 0;
+        for (int c0 = 0; c0 < HALF; c0 += 16) {
+            float v[16];
+            tmem_ld16(tmem_d + (uint32_t)((chunk & 1) * BN) + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(col_lo + c0), v);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) racc[c0 + e] += v[e];
         }
-    }
+        tc_fence_before();
+    };
 
     const int nkb = Ktot / CG_BK;
+    const int nchunks = (nkb + CG_KCB - 1) / CG_KCB;
+    int drained = 0;
     for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb & 1;
         unsigned char *st = smem + s * STAGE;
@@ -134,20 +161,21 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_tf32x3_kernel(ConvGem
             av[j] = __ldg(reinterpret_cast<const float4 *>(a.wt + (size_t)(co0 + rg * 8 + r0) * Ktot + k0 + kc * 4));
         }
         float bv[NBJ][4];
+        {
+            const int r = b_r + dy, c = b_c + dx;
+            const bool ok = r >= 0 && r < a.H && c >= 0 && c < a.W;
+            const float *src = xb + (size_t)ci0 * HW + (ok ? r * a.W + c : 0);
 #pragma unroll
-        for (int j = 0; j < NBJ; ++j) {
-            const int f = tid + CG_THREADS * j;
-            const int kk = (f & 7) + 8 * (f >> (3 + (BN == 128 ? 5 : 4)));
-            const float *src = xb + (size_t)(ci0 + kk) * HW;
+            for (int j = 0; j < NBJ; ++j) {
+                const int kc = (tid + CG_THREADS * j) / BN;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int r = b_r[j][e] + dy, c = b_c[j][e] + dx;
-                const bool ok = b_r[j][e] >= 0 && r >= 0 && r < a.H && c >= 0 && c < a.W;
-                bv[j][e] = ok ? __ldg(src + r * a.W + c) : 0.f;
+                for (int e = 0; e < 4; ++e) bv[j][e] = ok ? __ldg(src + (size_t)(kc * 4 + e) * HW) : 0.f;
             }
         }
         // ---- the MMAs that read this stage two blocks ago must have retired ------------------------------------------
         if (kb >= 2) mbar_wait(&bar_free[s], ((kb >> 1) - 1) & 1);
+        // ---- a chunk whose last block was issued two iterations ago is complete (or nearly): fold it into registers --------
+        if (drained < nchunks && kb >= (drained + 1) * CG_KCB + 1) drain(drained++);
         // ---- registers -> hi / lo -> shared (canonical UMMA layouts) ---------------------------------------------------
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -161,58 +189,53 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_tf32x3_kernel(ConvGem
         }
 #pragma unroll
         for (int j = 0; j < NBJ; ++j) {
-            const int f = tid + CG_THREADS * j;
-            const int kq = f & 7, n4 = (f >> 3) & (BN / 4 - 1), kg = f >> (3 + (BN == 128 ? 5 : 4));
+            const int kc = (tid + CG_THREADS * j) / BN;
             float4 h, l;
             split_tf32(bv[j][0], h.x, l.x); split_tf32(bv[j][1], h.y, l.y); split_tf32(bv[j][2], h.z, l.z); split_tf32(bv[j][3], h.w, l.w);
-            const int off = (kg * B_LBO + n4 * B_SBO + kq * 16) >> 2;
+            const int off = (kc * B_LBO + (bn >> 3) * B_SBO + (bn & 7) * 16) >> 2;
             *reinterpret_cast<float4 *>(b_hi + off) = h;
             *reinterpret_cast<float4 *>(b_lo + off) = l;
         }
         fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {
+          if (elect_one()) {
             tc_fence_after();
             const uint32_t sa_hi = smem_u32(a_hi), sa_lo = smem_u32(a_lo), sb_hi = smem_u32(b_hi), sb_lo = smem_u32(b_lo);
 #pragma unroll
             for (int ks = 0; ks < CG_BK / 8; ++ks) {
                 const uint64_t dah = umma_smem_desc(sa_hi + ks * 2 * A_LBO, A_LBO, A_SBO), dal = umma_smem_desc(sa_lo + ks * 2 * A_LBO, A_LBO, A_SBO);
-                const uint64_t dbh = umma_smem_desc(sb_hi + ks * B_LBO, B_LBO, B_SBO), dbl = umma_smem_desc(sb_lo + ks * B_LBO, B_LBO, B_SBO);
-                umma_tf32(tmem_d, dal, dbh, IDESC, (kb | ks) != 0);  // small terms first
-                umma_tf32(tmem_d, dah, dbl, IDESC, 1);
-                umma_tf32(tmem_d, dah, dbh, IDESC, 1);
+                const uint64_t dbh = umma_smem_desc(sb_hi + ks * 2 * B_LBO, B_LBO, B_SBO), dbl = umma_smem_desc(sb_lo + ks * 2 * B_LBO, B_LBO, B_SBO);
+                const uint32_t acc = tmem_d + (uint32_t)(((kb / CG_KCB) & 1) * BN);
+                umma_tf32(acc, dal, dbh, IDESC, ((kb % CG_KCB) | ks) != 0);  // small terms first; a chunk's first MMA overwrites
+                umma_tf32(acc, dah, dbl, IDESC, 1);
+                umma_tf32(acc, dah, dbh, IDESC, 1);
             }
-            umma_commit(&bar_free[s]);                   // arrives when the MMAs above have finished reading the stage
-            if (kb == nkb - 1) umma_commit(&bar_done);  // ... and when the accumulator is final
+            umma_commit(&bar_free[s]);  // arrives when the MMAs above have finished reading the stage
+            if (kb % CG_KCB == CG_KCB - 1 || kb == nkb - 1) umma_commit(&bar_acc[(kb / CG_KCB) & 1]);  // ... and the chunk is complete
+          }
+          __syncwarp();
         }
     }
 
-    // ---- epilogue: TMEM -> registers -> BN / residual / ReLU -> global NCHW ---------------------------------------------
-    mbar_wait(&bar_done, 0);
-    tc_fence_after();
-    const int row = (warp & 3) * 32 + lane;  // TMEM lane = output channel within the tile; a warp may only touch its own quadrant
+    // ---- epilogue: remaining chunks -> registers -> BN / residual / ReLU -> global NCHW --------------------------------------
+    while (drained < nchunks) drain(drained++);
     const int co = co0 + row;
     const float sc = a.scale ? __ldg(a.scale + co) : 1.f, sh = a.shift ? __ldg(a.shift + co) : 0.f;
     const size_t obase = ((size_t)img * a.Cout + co) * HW;
-    constexpr int HALF = BN / 2;
-#pragma unroll 1
-    for (int c0 = (warp >> 2) * HALF; c0 < (warp >> 2) * HALF + HALF; c0 += 16) {
-        float v[16];
-        tmem_ld16(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, v);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-            const int p = pix0 + c0 + e;
-            if (p < HW) {
-                float y = fmaf(v[e], sc, sh);
-                if (a.residual) y += __ldg(a.residual + obase + p);
-                if (a.relu) y = fmaxf(y, 0.f);
-                a.out[obase + p] = y;
-            }
+    for (int e = 0; e < HALF; ++e) {
+        const int p = pix0 + col_lo + e;
+        if (p < HW) {
+            float y = fmaf(racc[e], sc, sh);
+            if (a.residual) y += __ldg(a.residual + obase + p);
+            if (a.relu) y = fmaxf(y, 0.f);
+            a.out[obase + p] = y;
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)BN));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)(2 * BN)));
 }
 
 template <int BN>
