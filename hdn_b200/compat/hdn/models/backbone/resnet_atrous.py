@@ -15,7 +15,7 @@ import math
 
 import torch.nn as nn
 
-from hdn_b200.convs import conv3x3
+from hdn_b200.convs import conv3x3, conv_bn_act
 
 __all__ = ["ResNet", "resnet18", "resnet34", "resnet50"]
 
@@ -49,15 +49,12 @@ class Bottleneck(nn.Module):
         self.stride = stride
 
     def forward(self, x):
-        y = self.relu(self.bn1(self.conv1(x)))
-        y = self.relu(self.bn2(conv3x3(self.conv2, y)))  # dilated layers: 9 shifted GEMMs instead of cuDNN's direct kernel
-        y = self.bn3(self.conv3(y))
-        y += x if self.downsample is None else self._shortcut(x)
-        return self.relu(y)
-
-    def _shortcut(self, x):
-        proj, bn = self.downsample[0], self.downsample[1]
-        return bn(conv3x3(proj, x))
+        # Each conv + BN (+ residual) (+ ReLU) is one fused launch on the tensor cores where the layer is eligible
+        # (stride 1, Cin % 32 == 0, Cout % 128 == 0: hdn_b200.convs.conv_bn_act); otherwise cuDNN / shifted GEMMs.
+        y = conv_bn_act(self.conv1, self.bn1, x, relu=True)
+        y = conv_bn_act(self.conv2, self.bn2, y, relu=True)
+        shortcut = x if self.downsample is None else conv_bn_act(self.downsample[0], self.downsample[1], x)
+        return conv_bn_act(self.conv3, self.bn3, y, residual=shortcut, relu=True)
 
 
 class BasicBlock(nn.Module):

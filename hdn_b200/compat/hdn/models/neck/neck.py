@@ -6,6 +6,8 @@ with cut=False (model_builder...py:50-51).  Key names: downsample{2,3,4}.downsam
 """
 import torch.nn as nn
 
+from hdn_b200.convs import conv_bn_act
+
 
 class AdjustLayer(nn.Module):
     def __init__(self, in_channels, out_channels, cut=True, cut_left=4, cut_num=7):
@@ -14,7 +16,7 @@ class AdjustLayer(nn.Module):
         self.cut, self.cut_left, self.cut_num = cut, cut_left, cut_num
 
     def forward(self, x):
-        y = self.downsample(x)
+        y = conv_bn_act(self.downsample[0], self.downsample[1], x)
         if self.cut and y.size(3) < 20:
             lo, hi = self.cut_left, self.cut_left + self.cut_num
             y = y[:, :, lo:hi, lo:hi]

@@ -10,6 +10,8 @@ by the dilation d and each plane flattened, tap (ky,kx) reads the contiguous sli
 and the valid outputs are the columns c < W of that Wp-strided grid (W/Wp of the work is useful: 31/39 at d = 4).
 0.30 ms for the same layer; results differ from cuDNN's by fp32 summation order only (~3e-6 relative).
 """
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -51,6 +53,49 @@ def dilated_conv3x3(x, conv):
         else:
             acc.baddbmm_(wt[tap].expand(B, -1, -1), xs)
     return out.view(B, -1, H, Wp)[:, :, :, :W]
+
+
+_FOLD_CACHE = {}
+
+
+def _folded(conv, bn):
+    """(tap-major weight, scale, shift) of conv -> eval-mode BatchNorm, cached per parameter version."""
+    key = (id(conv), id(bn))
+    ver = (conv.weight.data_ptr(), conv.weight._version, bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
+           bn.running_mean.data_ptr())
+    hit = _FOLD_CACHE.get(key)
+    if hit is None or hit[0] != ver:
+        from hdn_b200 import ops
+        scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).detach().float().contiguous()
+        shift = (bn.bias - bn.running_mean * scale).detach().float().contiguous()
+        hit = (ver, ops.tap_major_weight(conv.weight), scale, shift)
+        _FOLD_CACHE[key] = hit
+    return hit[1:]
+
+
+def tensor_core_eligible(conv, x):
+    """The tcgen05 3xTF32 kernel covers stride-1 1x1 / 3x3 'same' convolutions with Cin % 32 == 0 and Cout % 128 == 0."""
+    k = conv.kernel_size[0]
+    return (x.is_cuda and x.dtype == torch.float32 and conv.kernel_size[0] == conv.kernel_size[1] and k in (1, 3) and conv.stride == (1, 1)
+            and conv.groups == 1 and conv.bias is None and conv.dilation[0] == conv.dilation[1]
+            and conv.padding == (conv.dilation[0] * (k // 2),) * 2 and conv.in_channels % 32 == 0 and conv.out_channels % 128 == 0
+            and not torch.is_grad_enabled())
+
+
+def conv_bn_act(conv, bn, x, residual=None, relu=False):
+    """relu?(bn(conv(x)) + residual?) for an eval-mode block.  Eligible layers run as ONE tcgen05 launch (implicit GEMM, fp32-accurate
+    3xTF32, BatchNorm / residual / ReLU in the epilogue: hdn_conv_gemm_f32); the rest fall back to cuDNN / the shifted-GEMM path."""
+    if USE_TENSOR_CORES and not bn.training and tensor_core_eligible(conv, x):
+        from hdn_b200 import ops
+        wt, scale, shift = _folded(conv, bn)
+        return ops.conv_gemm(x, wt, scale, shift, residual, ksize=conv.kernel_size[0], dilation=conv.dilation[0], relu=relu)
+    y = bn(conv3x3(conv, x))
+    if residual is not None:
+        y = y + residual
+    return torch.relu_(y) if relu else y
+
+
+USE_TENSOR_CORES = os.environ.get("HDN_B200_TCGEN05", "1") != "0"
 
 
 def conv3x3(conv, x):

@@ -17,10 +17,10 @@
 //     A = Wt   [Cout x K]   K = taps*Cin contiguous  -> UMMA K-major
 //     B = X    [K x HW]     pixels contiguous in HBM -> transposed to UMMA K-major ([pixel][k]) while staging (MN-major
 //                                                        TF32 without the 32B-base swizzle reads as zeros; probed)
-// One CTA owns a 128 (co) x BN (pixels) tile.  All 256 threads stage a 32-deep K block: global -> registers -> hi / lo
-// -> shared memory in the canonical no-swizzle UMMA layouts (8x16-byte core matrices); one thread then issues
-// 4 k-steps x 3 tcgen05.mma (kind::tf32, M=128, N=BN, K=8) and commits them to an mbarrier that frees the stage.
-// Two stages: the tensor core works on block k while the threads stage block k+1.
+// One CTA owns a 128 (co) x BN (pixels) tile.  256 producer threads stage 32-deep K blocks: global -> registers -> hi / lo
+// -> shared memory in the canonical no-swizzle UMMA layouts (8x16-byte core matrices); a dedicated warp's elected lane
+// issues 4 k-steps x 3 tcgen05.mma (kind::tf32, M=128, N=BN, K=8) per block and commits them to the mbarrier that
+// frees the stage.  3-4 stages decouple staging from the tensor core.
 // Epilogue: tcgen05.ld (32 lanes x 32b x 16 columns) -> y = acc*scale[co] + shift[co] (+ residual) (ReLU) -> global NCHW.
 #include "common.cuh"
 
@@ -70,36 +70,62 @@ __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
     lo = x - hi;
 }
 
+// cp.async (LDGSTS): global -> shared without a register round trip; src_bytes = 0 zero-fills (conv padding / tile tail)
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *dst, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 struct ConvGemmArgs {
     const float *x, *wt, *scale, *shift, *residual;
     float *out;
     int Cin, Cout, H, W, taps, dil, relu;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_tf32x3_kernel(ConvGemmArgs a) {
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Warp-specialised: warps 0..7 (256 threads) are PRODUCERS (global -> registers -> hi/lo -> shared, TMEM drains, epilogue),
+// warp 8 is the MMA ISSUER.  Stages hand over through mbarriers (full: 256 producer arrivals; free: tcgen05.commit), so
+// staging of block k+1.. never waits for the issue of block k; two TMEM accumulators alternate per 256-deep K chunk.
+template <int BN, int STAGES, int RAW>
+__global__ void __launch_bounds__(CG_THREADS + 32, 1) conv_gemm_tf32x3_kernel(ConvGemmArgs a) {
     constexpr int A_TILE = CG_BM * CG_BK * 4;  // bytes of one operand tile (hi or lo)
     constexpr int B_TILE = CG_BK * BN * 4;
     constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
+    constexpr int RAW_STAGE = A_TILE + B_TILE;  // landing ring of the cp.async prefetch (fp32 as loaded)
     constexpr uint32_t A_SBO = 128, A_LBO = (CG_BM / 8) * 128;  // K-major: 8-row groups 128 B apart, 4-wide K chunks A_LBO apart
     constexpr uint32_t B_SBO = 128, B_LBO = (BN / 8) * 128;     // K-major as well (pixel rows): the tile is transposed while staging
     // kind::tf32, fp32 accumulate, A and B K-major, N = BN, M = 128 (cute::UMMA::InstrDescriptor bit layout)
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(CG_BM >> 4) << 24);
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ uint64_t bar_free[2], bar_acc[2];
+    __shared__ uint64_t bar_full[STAGES], bar_free[STAGES], bar_acc_full[2], bar_acc_free[2];
     __shared__ uint32_t tmem_base_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int HW = a.H * a.W;
     const int pix0 = blockIdx.x * BN, co0 = blockIdx.y * CG_BM, img = blockIdx.z;
     const int Ktot = a.taps * a.Cin;
-    const float *xb = a.x + (size_t)img * a.Cin * HW;
+    const int nkb = Ktot / CG_BK;
+    const int nchunks = (nkb + CG_KCB - 1) / CG_KCB;
 
     if (tid == 0) {
-        mbar_init(&bar_free[0], 1);
-        mbar_init(&bar_free[1], 1);
-        mbar_init(&bar_acc[0], 1);
-        mbar_init(&bar_acc[1], 1);
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&bar_full[i], CG_THREADS);
+            mbar_init(&bar_free[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_acc_full[i], 1);
+            mbar_init(&bar_acc_free[i], CG_THREADS);
+        }
         mbar_fence_init();
     }
     if (warp == 0) {
@@ -111,126 +137,150 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_tf32x3_kernel(ConvGem
     tc_fence_after();
     const uint32_t tmem_d = tmem_base_slot;
 
-    // ---- per-thread staging coordinates (fixed for the whole K loop) ------------------------------------------------
-    // A: float4 slots f = tid + 256*j, j < 4:      r0 = f&7, kc = (f>>3)&7, rg = f>>6        (row = rg*8 + r0, k = kc*4..+3)
-    // B: slots f = tid + 256*j, j < BN/32:          n = f % BN (= tid % BN for every j), kc = f / BN   (k = kc*4..+3)
-    //    consecutive lanes -> consecutive pixels: coalesced scalar loads, and one conflict-free 16-byte store per slot.
-    constexpr int NBJ = BN / 32;
-    const int bn = tid % BN;
-    const int bp = pix0 + bn;
-    const int b_r = bp < HW ? bp / a.W : -(1 << 20), b_c = bp < HW ? bp - (bp / a.W) * a.W : 0;  // beyond the image: never valid
-
-    // fp32 register accumulator of this thread's share of the tile: TMEM lane (= channel) row, columns [col_lo, col_lo + BN/2)
-    constexpr int HALF = BN / 2;
-    const int row = (warp & 3) * 32 + lane;  // a warp may only touch its own TMEM lane quadrant
-    const int col_lo = (warp >> 2) * HALF;
-    float racc[HALF];
+    if (warp == CG_THREADS / 32) {
+        // ============================== MMA issuer (one elected lane) ==============================
+        if (elect_one()) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES, chunk = kb / CG_KCB;
+                if (kb % CG_KCB == 0 && chunk >= 2) mbar_wait(&bar_acc_free[chunk & 1], ((chunk >> 1) - 1) & 1);  // producers drained this accumulator
+                mbar_wait(&bar_full[s], (kb / STAGES) & 1);
+                tc_fence_after();
+                const uint32_t sa_hi = smem_u32(smem + s * STAGE), sa_lo = sa_hi + A_TILE, sb_hi = sa_hi + 2 * A_TILE, sb_lo = sb_hi + B_TILE;
+                const uint32_t acc = tmem_d + (uint32_t)((chunk & 1) * BN);
 #pragma unroll
-    for (int e = 0; e < HALF; ++e) racc[e] = 0.f;
-    auto drain = [&](int chunk) {  // fold finished TMEM accumulator `chunk & 1` into racc (round-to-nearest adds)
-        mbar_wait(&bar_acc[chunk & 1], (chunk >> 1) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int c0 = 0; c0 < HALF; c0 += 16) {
-            float v[16];
-            tmem_ld16(tmem_d + (uint32_t)((chunk & 1) * BN) + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(col_lo + c0), v);
-#pragma unroll
-            for (int e = 0; e < 16; ++e) racc[c0 + e] += v[e];
+                for (int ks = 0; ks < CG_BK / 8; ++ks) {
+                    const uint64_t dah = umma_smem_desc(sa_hi + ks * 2 * A_LBO, A_LBO, A_SBO), dal = umma_smem_desc(sa_lo + ks * 2 * A_LBO, A_LBO, A_SBO);
+                    const uint64_t dbh = umma_smem_desc(sb_hi + ks * 2 * B_LBO, B_LBO, B_SBO), dbl = umma_smem_desc(sb_lo + ks * 2 * B_LBO, B_LBO, B_SBO);
+#ifndef HDN_EXP_NOMMA
+                    umma_tf32(acc, dal, dbh, IDESC, ((kb % CG_KCB) | ks) != 0);  // small terms first; a chunk's first MMA overwrites
+#ifndef HDN_EXP_ONEMMA
+                    umma_tf32(acc, dah, dbl, IDESC, 1);
+                    umma_tf32(acc, dah, dbh, IDESC, 1);
+#endif
+#endif
+                }
+                umma_commit(&bar_free[s]);  // arrives when the MMAs above have finished reading the stage
+                if (kb % CG_KCB == CG_KCB - 1 || kb == nkb - 1) umma_commit(&bar_acc_full[chunk & 1]);  // ... and the chunk is complete
+            }
         }
-        tc_fence_before();
-    };
+        __syncwarp();
+    } else {
+        // ============================== producers ==============================
+        const float *xb = a.x + (size_t)img * a.Cin * HW;
+        // A: float4 slots f = tid + 256*j, j < 4:      r0 = f&7, kc = (f>>3)&7, rg = f>>6        (row = rg*8 + r0, k = kc*4..+3)
+        // B: slots f = tid + 256*j, j < BN/32:          n = f % BN (= tid % BN for every j), kc = f / BN   (k = kc*4..+3)
+        //    consecutive lanes -> consecutive pixels: coalesced scalar loads, and one conflict-free 16-byte store per slot.
+        constexpr int NBJ = BN / 32;
+        const int bn = tid % BN;
+        const int bp = pix0 + bn;
+        const int b_r = bp < HW ? bp / a.W : -(1 << 20), b_c = bp < HW ? bp - (bp / a.W) * a.W : 0;  // beyond the image: never valid
 
-    const int nkb = Ktot / CG_BK;
-    const int nchunks = (nkb + CG_KCB - 1) / CG_KCB;
-    int drained = 0;
-    for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb & 1;
-        unsigned char *st = smem + s * STAGE;
-        float *a_hi = reinterpret_cast<float *>(st), *a_lo = reinterpret_cast<float *>(st + A_TILE);
-        float *b_hi = reinterpret_cast<float *>(st + 2 * A_TILE), *b_lo = reinterpret_cast<float *>(st + 2 * A_TILE + B_TILE);
-        const int k0 = kb * CG_BK;
-        const int tap = k0 / a.Cin, ci0 = k0 - tap * a.Cin;
-        const int dy = a.taps == 1 ? 0 : (tap / 3 - 1) * a.dil, dx = a.taps == 1 ? 0 : (tap % 3 - 1) * a.dil;
-
-        // ---- global -> registers (issued before waiting for the stage, so the loads overlap the running MMAs) ------
-        float4 av[4];
+        // fp32 register accumulator of this thread's share of the tile: TMEM lane (= channel) row, columns [col_lo, col_lo + BN/2)
+        constexpr int HALF = BN / 2;
+        const int row = (warp & 3) * 32 + lane;  // a warp may only touch its own TMEM lane quadrant
+        const int col_lo = (warp >> 2) * HALF;
+        float racc[HALF];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int f = tid + CG_THREADS * j;
-            const int r0 = f & 7, kc = (f >> 3) & 7, rg = f >> 6;
-            av[j] = __ldg(reinterpret_cast<const float4 *>(a.wt + (size_t)(co0 + rg * 8 + r0) * Ktot + k0 + kc * 4));
-        }
-        float bv[NBJ][4];
-        {
-            const int r = b_r + dy, c = b_c + dx;
-            const bool ok = r >= 0 && r < a.H && c >= 0 && c < a.W;
-            const float *src = xb + (size_t)ci0 * HW + (ok ? r * a.W + c : 0);
+        for (int e = 0; e < HALF; ++e) racc[e] = 0.f;
+        auto drain = [&](int chunk) {  // fold finished TMEM accumulator `chunk & 1` into racc (round-to-nearest adds), then hand it back
+            mbar_wait(&bar_acc_full[chunk & 1], (chunk >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int c0 = 0; c0 < HALF; c0 += 16) {
+                float v[16];
+                tmem_ld16(tmem_d + (uint32_t)((chunk & 1) * BN) + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(col_lo + c0), v);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) racc[c0 + e] += v[e];
+            }
+            tc_fence_before();
+            mbar_arrive(&bar_acc_free[chunk & 1]);
+        };
+
+        // Landing ring: block kb's fp32 operands are fetched RAW-1 blocks ahead with cp.async into the slot the SAME thread later
+        // converts (so cp.async.wait_group alone orders it).  A lands at its UMMA offset; B lands as [k/4][pixel][k%4] so that one
+        // LDS.128 returns the 4 consecutive-k values a 16-byte row of the K-major core matrix needs.
+        unsigned char *raw = smem + STAGES * STAGE;
+        auto fetch = [&](int kb) {
+            if (kb < nkb) {
+                const int k0 = kb * CG_BK;
+                const int tap = k0 / a.Cin, ci0 = k0 - tap * a.Cin;
+                const int dy = a.taps == 1 ? 0 : (tap / 3 - 1) * a.dil, dx = a.taps == 1 ? 0 : (tap % 3 - 1) * a.dil;
+                float *ra = reinterpret_cast<float *>(raw + (kb % RAW) * RAW_STAGE), *rb = ra + A_TILE / 4;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int f = tid + CG_THREADS * j;
+                    const int r0 = f & 7, kc = (f >> 3) & 7, rg = f >> 6;
+                    cp_async16(ra + ((kc * A_LBO + rg * A_SBO + r0 * 16) >> 2), a.wt + (size_t)(co0 + rg * 8 + r0) * Ktot + k0 + kc * 4);
+                }
+                const int r = b_r + dy, c = b_c + dx;
+                const bool ok = r >= 0 && r < a.H && c >= 0 && c < a.W;
+                const float *src = xb + (size_t)ci0 * HW + (ok ? r * a.W + c : 0);
+#pragma unroll
+                for (int j = 0; j < NBJ; ++j) {
+                    const int kc = (tid + CG_THREADS * j) / BN;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) cp_async4(rb + (kc * BN + bn) * 4 + e, src + (size_t)(kc * 4 + e) * HW, ok ? 4u : 0u);
+                }
+            }
+            cp_async_commit();  // one group per block, also when empty, so the wait count below stays uniform
+        };
+#pragma unroll
+        for (int i = 0; i < RAW - 1; ++i) fetch(i);
+
+        int drained = 0;
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % STAGES;
+            fetch(kb + RAW - 1);
+            cp_async_wait<RAW - 1>();  // block kb has landed (this thread's own slots)
+            // ---- a chunk that was completely staged a few blocks ago is (nearly) through the tensor core: fold it now ----
+            if (drained < nchunks && kb >= (drained + 1) * CG_KCB + 2) drain(drained++);
+            // ---- the MMAs that read this stage STAGES blocks ago must have retired ----
+            if (kb >= STAGES) mbar_wait(&bar_free[s], ((kb / STAGES) - 1) & 1);
+            // ---- landing slot -> hi / lo -> shared (canonical no-swizzle K-major UMMA layouts) ----
+            const float *ra = reinterpret_cast<const float *>(raw + (kb % RAW) * RAW_STAGE), *rb = ra + A_TILE / 4;
+            float *a_hi = reinterpret_cast<float *>(smem + s * STAGE), *a_lo = a_hi + A_TILE / 4;
+            float *b_hi = a_hi + 2 * A_TILE / 4, *b_lo = b_hi + B_TILE / 4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int f = tid + CG_THREADS * j;
+                const int r0 = f & 7, kc = (f >> 3) & 7, rg = f >> 6;
+                const int off = (kc * A_LBO + rg * A_SBO + r0 * 16) >> 2;
+                const float4 v = *reinterpret_cast<const float4 *>(ra + off);
+                float4 h, l;
+                split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+                *reinterpret_cast<float4 *>(a_hi + off) = h;
+                *reinterpret_cast<float4 *>(a_lo + off) = l;
+            }
 #pragma unroll
             for (int j = 0; j < NBJ; ++j) {
                 const int kc = (tid + CG_THREADS * j) / BN;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) bv[j][e] = ok ? __ldg(src + (size_t)(kc * 4 + e) * HW) : 0.f;
+                const float4 v = *reinterpret_cast<const float4 *>(rb + (kc * BN + bn) * 4);
+                float4 h, l;
+                split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+                const int off = (kc * B_LBO + (bn >> 3) * B_SBO + (bn & 7) * 16) >> 2;
+                *reinterpret_cast<float4 *>(b_hi + off) = h;
+                *reinterpret_cast<float4 *>(b_lo + off) = l;
             }
+#ifndef HDN_EXP_NOFENCE
+            fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+#endif
+            mbar_arrive(&bar_full[s]);
         }
-        // ---- the MMAs that read this stage two blocks ago must have retired ------------------------------------------
-        if (kb >= 2) mbar_wait(&bar_free[s], ((kb >> 1) - 1) & 1);
-        // ---- a chunk whose last block was issued two iterations ago is complete (or nearly): fold it into registers --------
-        if (drained < nchunks && kb >= (drained + 1) * CG_KCB + 1) drain(drained++);
-        // ---- registers -> hi / lo -> shared (canonical UMMA layouts) ---------------------------------------------------
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int f = tid + CG_THREADS * j;
-            const int r0 = f & 7, kc = (f >> 3) & 7, rg = f >> 6;
-            float4 h, l;
-            split_tf32(av[j].x, h.x, l.x); split_tf32(av[j].y, h.y, l.y); split_tf32(av[j].z, h.z, l.z); split_tf32(av[j].w, h.w, l.w);
-            const int off = (kc * A_LBO + rg * A_SBO + r0 * 16) >> 2;
-            *reinterpret_cast<float4 *>(a_hi + off) = h;
-            *reinterpret_cast<float4 *>(a_lo + off) = l;
-        }
-#pragma unroll
-        for (int j = 0; j < NBJ; ++j) {
-            const int kc = (tid + CG_THREADS * j) / BN;
-            float4 h, l;
-            split_tf32(bv[j][0], h.x, l.x); split_tf32(bv[j][1], h.y, l.y); split_tf32(bv[j][2], h.z, l.z); split_tf32(bv[j][3], h.w, l.w);
-            const int off = (kc * B_LBO + (bn >> 3) * B_SBO + (bn & 7) * 16) >> 2;
-            *reinterpret_cast<float4 *>(b_hi + off) = h;
-            *reinterpret_cast<float4 *>(b_lo + off) = l;
-        }
-        fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
-        __syncthreads();
-        if (warp == 0) {
-          if (elect_one()) {
-            tc_fence_after();
-            const uint32_t sa_hi = smem_u32(a_hi), sa_lo = smem_u32(a_lo), sb_hi = smem_u32(b_hi), sb_lo = smem_u32(b_lo);
-#pragma unroll
-            for (int ks = 0; ks < CG_BK / 8; ++ks) {
-                const uint64_t dah = umma_smem_desc(sa_hi + ks * 2 * A_LBO, A_LBO, A_SBO), dal = umma_smem_desc(sa_lo + ks * 2 * A_LBO, A_LBO, A_SBO);
-                const uint64_t dbh = umma_smem_desc(sb_hi + ks * 2 * B_LBO, B_LBO, B_SBO), dbl = umma_smem_desc(sb_lo + ks * 2 * B_LBO, B_LBO, B_SBO);
-                const uint32_t acc = tmem_d + (uint32_t)(((kb / CG_KCB) & 1) * BN);
-                umma_tf32(acc, dal, dbh, IDESC, ((kb % CG_KCB) | ks) != 0);  // small terms first; a chunk's first MMA overwrites
-                umma_tf32(acc, dah, dbl, IDESC, 1);
-                umma_tf32(acc, dah, dbh, IDESC, 1);
-            }
-            umma_commit(&bar_free[s]);  // arrives when the MMAs above have finished reading the stage
-            if (kb % CG_KCB == CG_KCB - 1 || kb == nkb - 1) umma_commit(&bar_acc[(kb / CG_KCB) & 1]);  // ... and the chunk is complete
-          }
-          __syncwarp();
-        }
-    }
 
-    // ---- epilogue: remaining chunks -> registers -> BN / residual / ReLU -> global NCHW --------------------------------------
-    while (drained < nchunks) drain(drained++);
-    const int co = co0 + row;
-    const float sc = a.scale ? __ldg(a.scale + co) : 1.f, sh = a.shift ? __ldg(a.shift + co) : 0.f;
-    const size_t obase = ((size_t)img * a.Cout + co) * HW;
+        // ---- epilogue: remaining chunks -> registers -> BN / residual / ReLU -> global NCHW ----
+        while (drained < nchunks) drain(drained++);
+        const int co = co0 + row;
+        const float sc = a.scale ? __ldg(a.scale + co) : 1.f, sh = a.shift ? __ldg(a.shift + co) : 0.f;
+        const size_t obase = ((size_t)img * a.Cout + co) * HW;
 #pragma unroll
-    for (int e = 0; e < HALF; ++e) {
-        const int p = pix0 + col_lo + e;
-        if (p < HW) {
-            float y = fmaf(racc[e], sc, sh);
-            if (a.residual) y += __ldg(a.residual + obase + p);
-            if (a.relu) y = fmaxf(y, 0.f);
-            a.out[obase + p] = y;
+        for (int e = 0; e < HALF; ++e) {
+            const int p = pix0 + col_lo + e;
+            if (p < HW) {
+                float y = fmaf(racc[e], sc, sh);
+                if (a.residual) y += __ldg(a.residual + obase + p);
+                if (a.relu) y = fmaxf(y, 0.f);
+                a.out[obase + p] = y;
+            }
         }
     }
     tc_fence_before();
@@ -238,17 +288,18 @@ __global__ void __launch_bounds__(CG_THREADS, 1) conv_gemm_tf32x3_kernel(ConvGem
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)(2 * BN)));
 }
 
-template <int BN>
+template <int BN, int STAGES, int RAW>
 static int launch_conv_gemm(const ConvGemmArgs &a, int B, cudaStream_t st) {
-    constexpr size_t SMEM = 2 * (2 * CG_BM * CG_BK * 4 + 2 * CG_BK * BN * 4) + 1024;
+    constexpr size_t SMEM = (size_t)STAGES * (2 * CG_BM * CG_BK * 4 + 2 * CG_BK * BN * 4) + (size_t)RAW * (CG_BM * CG_BK * 4 + CG_BK * BN * 4) + 1024;
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_tf32x3_kernel<BN, STAGES, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
     dim3 grid((a.H * a.W + BN - 1) / BN, a.Cout / CG_BM, B);
-    conv_gemm_tf32x3_kernel<BN><<<grid, CG_THREADS, SMEM, st>>>(a);
+    conv_gemm_tf32x3_kernel<BN, STAGES, RAW><<<grid, CG_THREADS + 32, SMEM, st>>>(a);
     count_launch();
     return launch_status();
 }
@@ -270,5 +321,5 @@ extern "C" int hdn_conv_gemm_f32(const float *x, const float *wt, const float *s
     ConvGemmArgs a{x, wt, scale, shift, residual, out, Cin, Cout, H, W, ksize * ksize, dilation, relu};
     const long long tiles128 = (long long)((H * W + 127) / 128) * (Cout / CG_BM) * B;
     // small problems (tracking batch sizes): narrower pixel tiles put more CTAs on the 148 SMs
-    return tiles128 >= 2 * sm_count() ? launch_conv_gemm<128>(a, B, (cudaStream_t)stream) : launch_conv_gemm<64>(a, B, (cudaStream_t)stream);
+    return tiles128 >= 2 * sm_count() ? launch_conv_gemm<128, 2, 3>(a, B, (cudaStream_t)stream) : launch_conv_gemm<64, 2, 5>(a, B, (cudaStream_t)stream);
 }
