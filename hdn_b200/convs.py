@@ -59,7 +59,7 @@ _FOLD_CACHE = {}
 
 
 def _folded(conv, bn):
-    """(tap-major weight, scale, shift) of conv -> eval-mode BatchNorm, cached per parameter version."""
+    """(tensor-core packed weight, scale, shift) of conv -> eval-mode BatchNorm, cached per parameter version."""
     key = (id(conv), id(bn))
     ver = (conv.weight.data_ptr(), conv.weight._version, bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
            bn.running_mean.data_ptr())
@@ -68,7 +68,7 @@ def _folded(conv, bn):
         from hdn_b200 import ops
         scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).detach().float().contiguous()
         shift = (bn.bias - bn.running_mean * scale).detach().float().contiguous()
-        hit = (ver, ops.tap_major_weight(conv.weight), scale, shift)
+        hit = (ver, ops.pack_conv_weight(conv.weight), scale, shift)
         _FOLD_CACHE[key] = hit
     return hit[1:]
 

@@ -17,10 +17,14 @@
 //     A = Wt   [Cout x K]   K = taps*Cin contiguous  -> UMMA K-major
 //     B = X    [K x HW]     pixels contiguous in HBM -> transposed to UMMA K-major ([pixel][k]) while staging (MN-major
 //                                                        TF32 without the 32B-base swizzle reads as zeros; probed)
-// One CTA owns a 128 (co) x BN (pixels) tile.  256 producer threads stage 32-deep K blocks: global -> registers -> hi / lo
-// -> shared memory in the canonical no-swizzle UMMA layouts (8x16-byte core matrices); a dedicated warp's elected lane
-// issues 4 k-steps x 3 tcgen05.mma (kind::tf32, M=128, N=BN, K=8) per block and commits them to the mbarrier that
-// frees the stage.  3-4 stages decouple staging from the tensor core.
+// One CTA owns a 128 (co) x BN (pixels) tile and walks K in 32-deep blocks through a ring of stages:
+//   * WEIGHTS are constants, so their hi / lo split and the UMMA tiling are done once (hdn_conv_pack_weight_f32): a block's
+//     A operand is one contiguous 32 KB record that a single thread fetches with a 1-D TMA bulk copy (UBLKCP);
+//   * ACTIVATIONS are fetched 4 blocks ahead with cp.async into a landing ring (4-byte copies: NCHW rows of odd length are
+//     only 4-byte aligned, zero-fill = padding), then 256 producer threads split them (hi / lo) and store them
+//     transposed into the canonical no-swizzle K-major UMMA layout (8 x 16-byte core matrices);
+//   * a dedicated warp's elected lane issues 4 k-steps x 3 tcgen05.mma (kind::tf32, M=128, N=BN, K=8) per block and commits
+//     them to the mbarrier that frees the stage.
 // Epilogue: tcgen05.ld (32 lanes x 32b x 16 columns) -> y = acc*scale[co] + shift[co] (+ residual) (ReLU) -> global NCHW.
 #include "common.cuh"
 
@@ -84,7 +88,7 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 
 struct ConvGemmArgs {
-    const float *x, *wt, *scale, *shift, *residual;
+    const float *x, *wpk, *scale, *shift, *residual;  // wpk: hdn_conv_pack_weight_f32 output
     float *out;
     int Cin, Cout, H, W, taps, dil, relu;
 };
@@ -97,11 +101,11 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 // warp 8 is the MMA ISSUER.  Stages hand over through mbarriers (full: 256 producer arrivals; free: tcgen05.commit), so
 // staging of block k+1.. never waits for the issue of block k; two TMEM accumulators alternate per 256-deep K chunk.
 template <int BN, int STAGES, int RAW>
-__global__ void __launch_bounds__(CG_THREADS + 32, 1) conv_gemm_tf32x3_kernel(ConvGemmArgs a) {
+__global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(ConvGemmArgs a) {
     constexpr int A_TILE = CG_BM * CG_BK * 4;  // bytes of one operand tile (hi or lo)
     constexpr int B_TILE = CG_BK * BN * 4;
     constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
-    constexpr int RAW_STAGE = A_TILE + B_TILE;  // landing ring of the cp.async prefetch (fp32 as loaded)
+    constexpr int RAW_STAGE = B_TILE;  // landing ring of the activation prefetch (fp32 as loaded)
     constexpr uint32_t A_SBO = 128, A_LBO = (CG_BM / 8) * 128;  // K-major: 8-row groups 128 B apart, 4-wide K chunks A_LBO apart
     constexpr uint32_t B_SBO = 128, B_LBO = (BN / 8) * 128;     // K-major as well (pixel rows): the tile is transposed while staging
     // kind::tf32, fp32 accumulate, A and B K-major, N = BN, M = 128 (cute::UMMA::InstrDescriptor bit layout)
@@ -119,7 +123,7 @@ __global__ void __launch_bounds__(CG_THREADS + 32, 1) conv_gemm_tf32x3_kernel(Co
 
     if (tid == 0) {
         for (int i = 0; i < STAGES; ++i) {
-            mbar_init(&bar_full[i], CG_THREADS);
+            mbar_init(&bar_full[i], CG_THREADS + 1);  // 256 producer arrivals + the TMA issuer's arrive.expect_tx
             mbar_init(&bar_free[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
@@ -164,8 +168,20 @@ __global__ void __launch_bounds__(CG_THREADS + 32, 1) conv_gemm_tf32x3_kernel(Co
             }
         }
         __syncwarp();
+    } else if (warp == CG_THREADS / 32 + 1) {
+        // ============================== weight loader: one 32 KB TMA bulk copy per K block ==============================
+        if (elect_one()) {
+            const float *wsrc = a.wpk + (size_t)blockIdx.y * nkb * (2 * A_TILE / 4);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % STAGES;
+                if (kb >= STAGES) mbar_wait(&bar_free[s], ((kb / STAGES) - 1) & 1);
+                mbar_expect_tx(&bar_full[s], 2 * A_TILE);
+                bulk_g2s(smem + s * STAGE, wsrc + (size_t)kb * (2 * A_TILE / 4), 2 * A_TILE, &bar_full[s]);
+            }
+        }
+        __syncwarp();
     } else {
-        // ============================== producers ==============================
+        // ============================== producers (activations) ==============================
         const float *xb = a.x + (size_t)img * a.Cin * HW;
         // A: float4 slots f = tid + 256*j, j < 4:      r0 = f&7, kc = (f>>3)&7, rg = f>>6        (row = rg*8 + r0, k = kc*4..+3)
         // B: slots f = tid + 256*j, j < BN/32:          n = f % BN (= tid % BN for every j), kc = f / BN   (k = kc*4..+3)
@@ -196,22 +212,16 @@ __global__ void __launch_bounds__(CG_THREADS + 32, 1) conv_gemm_tf32x3_kernel(Co
             mbar_arrive(&bar_acc_free[chunk & 1]);
         };
 
-        // Landing ring: block kb's fp32 operands are fetched RAW-1 blocks ahead with cp.async into the slot the SAME thread later
-        // converts (so cp.async.wait_group alone orders it).  A lands at its UMMA offset; B lands as [k/4][pixel][k%4] so that one
-        // LDS.128 returns the 4 consecutive-k values a 16-byte row of the K-major core matrix needs.
+        // Landing ring: block kb's activations are fetched RAW-1 blocks ahead with cp.async into the slot the SAME thread later
+        // converts (so cp.async.wait_group alone orders it), laid out [k/4][pixel][k%4] so that one LDS.128 returns the 4
+        // consecutive-k values a 16-byte row of the K-major core matrix needs.
         unsigned char *raw = smem + STAGES * STAGE;
         auto fetch = [&](int kb) {
             if (kb < nkb) {
                 const int k0 = kb * CG_BK;
                 const int tap = k0 / a.Cin, ci0 = k0 - tap * a.Cin;
                 const int dy = a.taps == 1 ? 0 : (tap / 3 - 1) * a.dil, dx = a.taps == 1 ? 0 : (tap % 3 - 1) * a.dil;
-                float *ra = reinterpret_cast<float *>(raw + (kb % RAW) * RAW_STAGE), *rb = ra + A_TILE / 4;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int f = tid + CG_THREADS * j;
-                    const int r0 = f & 7, kc = (f >> 3) & 7, rg = f >> 6;
-                    cp_async16(ra + ((kc * A_LBO + rg * A_SBO + r0 * 16) >> 2), a.wt + (size_t)(co0 + rg * 8 + r0) * Ktot + k0 + kc * 4);
-                }
+                float *rb = reinterpret_cast<float *>(raw + (kb % RAW) * RAW_STAGE);
                 const int r = b_r + dy, c = b_c + dx;
                 const bool ok = r >= 0 && r < a.H && c >= 0 && c < a.W;
                 const float *src = xb + (size_t)ci0 * HW + (ok ? r * a.W + c : 0);
@@ -237,20 +247,8 @@ __global__ void __launch_bounds__(CG_THREADS + 32, 1) conv_gemm_tf32x3_kernel(Co
             // ---- the MMAs that read this stage STAGES blocks ago must have retired ----
             if (kb >= STAGES) mbar_wait(&bar_free[s], ((kb / STAGES) - 1) & 1);
             // ---- landing slot -> hi / lo -> shared (canonical no-swizzle K-major UMMA layouts) ----
-            const float *ra = reinterpret_cast<const float *>(raw + (kb % RAW) * RAW_STAGE), *rb = ra + A_TILE / 4;
-            float *a_hi = reinterpret_cast<float *>(smem + s * STAGE), *a_lo = a_hi + A_TILE / 4;
-            float *b_hi = a_hi + 2 * A_TILE / 4, *b_lo = b_hi + B_TILE / 4;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int f = tid + CG_THREADS * j;
-                const int r0 = f & 7, kc = (f >> 3) & 7, rg = f >> 6;
-                const int off = (kc * A_LBO + rg * A_SBO + r0 * 16) >> 2;
-                const float4 v = *reinterpret_cast<const float4 *>(ra + off);
-                float4 h, l;
-                split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-                *reinterpret_cast<float4 *>(a_hi + off) = h;
-                *reinterpret_cast<float4 *>(a_lo + off) = l;
-            }
+            const float *rb = reinterpret_cast<const float *>(raw + (kb % RAW) * RAW_STAGE);
+            float *b_hi = reinterpret_cast<float *>(smem + s * STAGE + 2 * A_TILE), *b_lo = b_hi + B_TILE / 4;
 #pragma unroll
             for (int j = 0; j < NBJ; ++j) {
                 const int kc = (tid + CG_THREADS * j) / BN;
@@ -290,7 +288,7 @@ __global__ void __launch_bounds__(CG_THREADS + 32, 1) conv_gemm_tf32x3_kernel(Co
 
 template <int BN, int STAGES, int RAW>
 static int launch_conv_gemm(const ConvGemmArgs &a, int B, cudaStream_t st) {
-    constexpr size_t SMEM = (size_t)STAGES * (2 * CG_BM * CG_BK * 4 + 2 * CG_BK * BN * 4) + (size_t)RAW * (CG_BM * CG_BK * 4 + CG_BK * BN * 4) + 1024;
+    constexpr size_t SMEM = (size_t)STAGES * (2 * CG_BM * CG_BK * 4 + 2 * CG_BK * BN * 4) + (size_t)RAW * (CG_BK * BN * 4) + 1024;
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
     static bool configured = false;
     if (!configured) {
@@ -299,27 +297,53 @@ static int launch_conv_gemm(const ConvGemmArgs &a, int B, cudaStream_t st) {
         configured = true;
     }
     dim3 grid((a.H * a.W + BN - 1) / BN, a.Cout / CG_BM, B);
-    conv_gemm_tf32x3_kernel<BN, STAGES, RAW><<<grid, CG_THREADS + 32, SMEM, st>>>(a);
+    conv_gemm_tf32x3_kernel<BN, STAGES, RAW><<<grid, CG_THREADS + 64, SMEM, st>>>(a);
     count_launch();
     return launch_status();
+}
+
+// Weights -> per (128-channel tile, 32-deep K block) records of [hi | lo] x [k/4 (8)][row/8 (16)][row%8 (8)][k%4 (4)] floats:
+// exactly the bytes a stage's A region holds, so the kernel moves a block's A operand with one bulk copy.
+__global__ void conv_pack_weight_kernel(const float *__restrict__ wt, float *__restrict__ out, int Cout, int Ktot) {
+    const long long total = (long long)Cout * Ktot;
+    const int nkb = Ktot / CG_BK;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int co = (int)(i / Ktot), k = (int)(i - (long long)co * Ktot);
+        const int mt = co / CG_BM, row = co % CG_BM, kb = k / CG_BK, kk = k % CG_BK;
+        const long long rec = ((long long)mt * nkb + kb) * (2 * CG_BM * CG_BK);
+        const int off = (kk >> 2) * (CG_BM * 4) + (row >> 3) * 32 + (row & 7) * 4 + (kk & 3);
+        float hi, lo;
+        split_tf32(wt[i], hi, lo);
+        out[rec + off] = hi;
+        out[rec + CG_BM * CG_BK + off] = lo;
+    }
 }
 
 }  // namespace hdn
 
 using namespace hdn;
 
+extern "C" int hdn_conv_pack_weight_f32(const float *wt, float *packed, int Cout, int Ktot, hdn_stream_t stream) {
+    if (!wt || !packed) return HDN_ERR_NULL;
+    if (Cout < CG_BM || Cout % CG_BM || Ktot < CG_BK || Ktot % CG_BK) return HDN_ERR_SHAPE;
+    if (reinterpret_cast<uintptr_t>(packed) & 15u) return HDN_ERR_ALIGN;
+    conv_pack_weight_kernel<<<sm_count() * 4, 256, 0, (cudaStream_t)stream>>>(wt, packed, Cout, Ktot);
+    count_launch();
+    return launch_status();
+}
+
 extern "C" int hdn_conv_gemm_supported(int Cin, int Cout, int ksize, int dilation) {
     return (Cin >= 32 && Cin % 32 == 0 && Cout % CG_BM == 0 && (ksize == 1 || ksize == 3) && dilation >= 1) ? 1 : 0;
 }
 
-extern "C" int hdn_conv_gemm_f32(const float *x, const float *wt, const float *scale, const float *shift, const float *residual, float *out,
+extern "C" int hdn_conv_gemm_f32(const float *x, const float *wpk, const float *scale, const float *shift, const float *residual, float *out,
                                  int B, int Cin, int Cout, int H, int W, int ksize, int dilation, int relu, hdn_stream_t stream) {
-    if (!x || !wt || !out) return HDN_ERR_NULL;
+    if (!x || !wpk || !out) return HDN_ERR_NULL;
     if (B < 1 || H < 1 || W < 1 || B > 65535) return HDN_ERR_SHAPE;
     if (!hdn_conv_gemm_supported(Cin, Cout, ksize, dilation)) return HDN_ERR_UNSUPPORTED;
-    if (reinterpret_cast<uintptr_t>(wt) & 15u) return HDN_ERR_ALIGN;
-    ConvGemmArgs a{x, wt, scale, shift, residual, out, Cin, Cout, H, W, ksize * ksize, dilation, relu};
+    if (reinterpret_cast<uintptr_t>(wpk) & 15u) return HDN_ERR_ALIGN;
+    ConvGemmArgs a{x, wpk, scale, shift, residual, out, Cin, Cout, H, W, ksize * ksize, dilation, relu};
     const long long tiles128 = (long long)((H * W + 127) / 128) * (Cout / CG_BM) * B;
     // small problems (tracking batch sizes): narrower pixel tiles put more CTAs on the 148 SMs
-    return tiles128 >= 2 * sm_count() ? launch_conv_gemm<128, 2, 3>(a, B, (cudaStream_t)stream) : launch_conv_gemm<64, 2, 5>(a, B, (cudaStream_t)stream);
+    return tiles128 >= 2 * sm_count() ? launch_conv_gemm<128, 2, 4>(a, B, (cudaStream_t)stream) : launch_conv_gemm<64, 3, 5>(a, B, (cudaStream_t)stream);
 }

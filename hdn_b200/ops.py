@@ -266,20 +266,20 @@ def score_argmax_host(cls, loc, window=None, win_influence=0.0):
     return unpack_scores(buf.cpu().numpy(), cls.shape[0], loc.shape[1])
 
 
-def conv_gemm(x, wt, scale=None, shift=None, residual=None, ksize=1, dilation=1, relu=False, out=None):
+def conv_gemm(x, wpk, scale=None, shift=None, residual=None, ksize=1, dilation=1, relu=False, out=None):
     """Stride-1 1x1 / 3x3 (padding = dilation) convolution + folded BatchNorm (+ residual) (+ ReLU) on tcgen05 (3xTF32).
-    x [B,Cin,H,W]; wt [Cout, ksize*ksize*Cin] tap-major (see `tap_major_weight`); scale/shift [Cout]."""
-    x, wt = _dev(x, "x"), _dev(wt, "wt")
+    x [B,Cin,H,W]; wpk = pack_conv_weight(weight) (done once per layer); scale/shift [Cout]."""
+    x, wpk = _dev(x, "x"), _dev(wpk, "wpk")
     B, Cin, H, W = x.shape
-    Cout = wt.shape[0]
-    if wt.numel() != Cout * ksize * ksize * Cin:
-        raise RuntimeError("conv_gemm: weight %s does not match Cin=%d, ksize=%d" % (tuple(wt.shape), Cin, ksize))
+    Cout = wpk.numel() // (2 * ksize * ksize * Cin)
+    if wpk.numel() != 2 * Cout * ksize * ksize * Cin:
+        raise RuntimeError("conv_gemm: packed weight of %d floats does not match Cin=%d, ksize=%d" % (wpk.numel(), Cin, ksize))
     if out is None:
         out = torch.empty((B, Cout, H, W), device=x.device, dtype=torch.float32)
     opt = lambda t, n: _ptr(_dev(t, n)) if t is not None else None  # noqa: E731
     if residual is not None and tuple(residual.shape) != tuple(out.shape):
         raise RuntimeError("conv_gemm: residual shape mismatch")
-    st = _lib.lib().hdn_conv_gemm_f32(_ptr(x), _ptr(wt), opt(scale, "scale"), opt(shift, "shift"), opt(residual, "residual"), _ptr(out), B, Cin,
+    st = _lib.lib().hdn_conv_gemm_f32(_ptr(x), _ptr(wpk), opt(scale, "scale"), opt(shift, "shift"), opt(residual, "residual"), _ptr(out), B, Cin,
                                       Cout, H, W, ksize, dilation, int(bool(relu)), _stream())
     _lib.check(st, "hdn_conv_gemm_f32")
     return out
@@ -289,6 +289,10 @@ def conv_gemm_supported(Cin, Cout, ksize, dilation=1):
     return bool(_lib.lib().hdn_conv_gemm_supported(Cin, Cout, ksize, dilation))
 
 
-def tap_major_weight(weight):
-    """[Cout,Cin,k,k] conv weight -> [Cout, k*k*Cin] (K index = tap*Cin + ci), the A operand of the implicit GEMM."""
-    return weight.detach().permute(0, 2, 3, 1).reshape(weight.shape[0], -1).contiguous()
+def pack_conv_weight(weight):
+    """[Cout,Cin,k,k] conv weight -> the tensor-core record format of hdn_conv_pack_weight_f32 (2*Cout*k*k*Cin floats):
+    tap-major K (K index = tap*Cin + ci), TF32 hi / lo halves, tiled per 128-channel x 32-deep K block."""
+    wt = _dev(weight.detach().permute(0, 2, 3, 1).reshape(weight.shape[0], -1), "weight")
+    packed = torch.empty(2 * wt.numel(), device=wt.device, dtype=torch.float32)
+    _lib.check(_lib.lib().hdn_conv_pack_weight_f32(_ptr(wt), _ptr(packed), wt.shape[0], wt.shape[1], _stream()), "hdn_conv_pack_weight_f32")
+    return packed

@@ -12,7 +12,7 @@ from hdn_b200 import _lib, ops
 for v in ["BASE", "NOFENCE", "NOMMA", "ONEMMA"]:
     _lib._lib = None; _lib.SO_PATH = "/tmp/lib_%s.so" % v
     x = torch.randn(1, 512, 31, 31, device="cuda"); w = torch.randn(512, 512, 3, 3, device="cuda") * 0.02
-    wt = ops.tap_major_weight(w)
+    wt = ops.pack_conv_weight(w)
     for _ in range(3): ops.conv_gemm(x, wt, ksize=3, dilation=4)
     torch.cuda.synchronize(); t = time.perf_counter()
     for _ in range(20): ops.conv_gemm(x, wt, ksize=3, dilation=4)

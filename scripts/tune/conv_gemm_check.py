@@ -30,7 +30,7 @@ for (B, Cin, Cout, H, W, k, d) in cases:
     res = torch.randn(B, Cout, H, W, device="cuda", generator=g)
     ref = F.relu(F.conv2d(x, w, padding=d * (k // 2), dilation=d) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1) + res)
     ref64 = F.relu(F.conv2d(x.double(), w.double(), padding=d * (k // 2), dilation=d) * scale.double().view(1, -1, 1, 1) + shift.double().view(1, -1, 1, 1) + res.double())
-    wt = ops.tap_major_weight(w)
+    wt = ops.pack_conv_weight(w)
     got = ops.conv_gemm(x, wt, scale, shift, res, ksize=k, dilation=d, relu=True)
     torch.cuda.synchronize()
     den = float(ref64.abs().max())
