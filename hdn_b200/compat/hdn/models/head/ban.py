@@ -13,6 +13,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from hdn.core.xcorr import xcorr_depthwise, xcorr_depthwise_multi
+from hdn_b200.convs import conv_bn_act
 
 
 class BAN(nn.Module):
@@ -35,8 +36,18 @@ class DepthwiseXCorr(nn.Module):
         self.head = nn.Sequential(nn.Conv2d(hidden, hidden, kernel_size=1, bias=False), nn.BatchNorm2d(hidden), nn.ReLU(inplace=True),
                                   nn.Conv2d(hidden, out_channels, kernel_size=1))
 
+    # conv + BN + ReLU of each Sequential as one fused tensor-core launch where eligible (hdn_b200.convs.conv_bn_act)
+    def kernel_features(self, z):
+        return conv_bn_act(self.conv_kernel[0], self.conv_kernel[1], z, relu=True)
+
+    def search_features(self, x):
+        return conv_bn_act(self.conv_search[0], self.conv_search[1], x, relu=True)
+
+    def predict(self, feature):
+        return self.head[3](conv_bn_act(self.head[0], self.head[1], feature, relu=True))
+
     def forward(self, kernel, search):
-        return self.head(self.correlate(self.conv_search(search), self.conv_kernel(kernel)))
+        return self.predict(self.correlate(self.search_features(search), self.kernel_features(kernel)))
 
 
 class DepthwiseBAN(BAN):
@@ -75,20 +86,20 @@ class MultiBAN(BAN):
 
     def prepare(self, z_fs):
         """Template-side kernels, once per template: [cls2, loc2, cls3, loc3, cls4, loc4]."""
-        self._kernels = [br.conv_kernel(z_fs[n // 2]).contiguous() for n, br in enumerate(self._branches())]
+        self._kernels = [br.kernel_features(z_fs[n // 2]).contiguous() for n, br in enumerate(self._branches())]
         return self._kernels
 
     def forward(self, z_fs, x_fs, kernels=None):
         if kernels is None:
-            kernels = [br.conv_kernel(z_fs[n // 2]) for n, br in enumerate(self._branches())]
+            kernels = [br.kernel_features(z_fs[n // 2]) for n, br in enumerate(self._branches())]
         branches = list(self._branches())
-        searches = [br.conv_search(x_fs[n // 2]) for n, br in enumerate(branches)]
+        searches = [br.search_features(x_fs[n // 2]) for n, br in enumerate(branches)]
         same = len({tuple(s.shape) for s in searches}) == 1 and len({tuple(k.shape) for k in kernels}) == 1
         if same and len(searches) <= 8:
             feats = xcorr_depthwise_multi(searches, kernels, circular=branches[0].circular)
         else:
             feats = [br.correlate(s, k) for br, s, k in zip(branches, searches, kernels)]
-        outs = [br.head(f) for br, f in zip(branches, feats)]
+        outs = [br.predict(f) for br, f in zip(branches, feats)]
         cls = outs[0::2]
         loc = [l * self.loc_scale[i] for i, l in enumerate(outs[1::2])]  # ban.py:109
         if self.weighted:  # ban.py:112-125

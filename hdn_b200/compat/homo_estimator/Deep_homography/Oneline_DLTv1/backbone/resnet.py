@@ -6,6 +6,8 @@ owns those); `forward` returns the feature levels listed in `used_layers`.  Same
 """
 import torch.nn as nn
 
+from hdn_b200.convs import conv_bn_act
+
 
 class BasicBlock(nn.Module):
     expansion = 1
@@ -21,9 +23,9 @@ class BasicBlock(nn.Module):
         self.stride = stride
 
     def forward(self, x):
-        y = self.bn2(self.conv2(self.relu(self.bn1(self.conv1(x)))))
-        y += x if self.downsample is None else self.downsample(x)
-        return self.relu(y)
+        y = conv_bn_act(self.conv1, self.bn1, x, relu=True)
+        shortcut = x if self.downsample is None else self.downsample(x)
+        return conv_bn_act(self.conv2, self.bn2, y, residual=shortcut, relu=True)
 
 
 class Bottleneck(nn.Module):

@@ -74,11 +74,11 @@ def _folded(conv, bn):
 
 
 def tensor_core_eligible(conv, x):
-    """The tcgen05 3xTF32 kernel covers stride-1 1x1 / 3x3 'same' convolutions with Cin % 32 == 0 and Cout % 128 == 0."""
+    """The tcgen05 3xTF32 kernel covers stride-1 1x1 and 3x3 ('same' or 'valid') convolutions with Cin % 32 == 0, Cout % 128 == 0."""
     k = conv.kernel_size[0]
     return (x.is_cuda and x.dtype == torch.float32 and conv.kernel_size[0] == conv.kernel_size[1] and k in (1, 3) and conv.stride == (1, 1)
             and conv.groups == 1 and conv.bias is None and conv.dilation[0] == conv.dilation[1]
-            and conv.padding == (conv.dilation[0] * (k // 2),) * 2 and conv.in_channels % 32 == 0 and conv.out_channels % 128 == 0
+            and conv.padding in ((conv.dilation[0] * (k // 2),) * 2, (0, 0)) and conv.in_channels % 32 == 0 and conv.out_channels % 128 == 0
             and not torch.is_grad_enabled())
 
 
@@ -88,7 +88,8 @@ def conv_bn_act(conv, bn, x, residual=None, relu=False):
     if USE_TENSOR_CORES and not bn.training and tensor_core_eligible(conv, x):
         from hdn_b200 import ops
         wt, scale, shift = _folded(conv, bn)
-        return ops.conv_gemm(x, wt, scale, shift, residual, ksize=conv.kernel_size[0], dilation=conv.dilation[0], relu=relu)
+        return ops.conv_gemm(x, wt, scale, shift, residual, ksize=conv.kernel_size[0], dilation=conv.dilation[0], relu=relu,
+                             valid=conv.kernel_size[0] == 3 and conv.padding == (0, 0))
     y = bn(conv3x3(conv, x))
     if residual is not None:
         y = y + residual

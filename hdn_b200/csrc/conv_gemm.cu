@@ -91,6 +91,7 @@ struct ConvGemmArgs {
     const float *x, *wpk, *scale, *shift, *residual;  // wpk: hdn_conv_pack_weight_f32 output
     float *out;
     int Cin, Cout, H, W, taps, dil, relu;
+    int Ho, Wo, off;  // output extent and the input offset of output pixel (0,0): 'same' -> (H, W, 0); 'valid' 3x3 -> (H-2d, W-2d, d)
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(Co
     __shared__ uint32_t tmem_base_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int HW = a.H * a.W;
+    const int HW = a.H * a.W, HWo = a.Ho * a.Wo;
     const int pix0 = blockIdx.x * BN, co0 = blockIdx.y * CG_BM, img = blockIdx.z;
     const int Ktot = a.taps * a.Cin;
     const int nkb = Ktot / CG_BK;
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(Co
         constexpr int NBJ = BN / 32;
         const int bn = tid % BN;
         const int bp = pix0 + bn;
-        const int b_r = bp < HW ? bp / a.W : -(1 << 20), b_c = bp < HW ? bp - (bp / a.W) * a.W : 0;  // beyond the image: never valid
+        const int b_r = bp < HWo ? bp / a.Wo + a.off : -(1 << 20), b_c = bp < HWo ? bp - (bp / a.Wo) * a.Wo + a.off : 0;  // beyond the tile: never valid
 
         // fp32 register accumulator of this thread's share of the tile: TMEM lane (= channel) row, columns [col_lo, col_lo + BN/2)
         constexpr int HALF = BN / 2;
@@ -269,11 +270,11 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(Co
         while (drained < nchunks) drain(drained++);
         const int co = co0 + row;
         const float sc = a.scale ? __ldg(a.scale + co) : 1.f, sh = a.shift ? __ldg(a.shift + co) : 0.f;
-        const size_t obase = ((size_t)img * a.Cout + co) * HW;
+        const size_t obase = ((size_t)img * a.Cout + co) * HWo;
 #pragma unroll
         for (int e = 0; e < HALF; ++e) {
             const int p = pix0 + col_lo + e;
-            if (p < HW) {
+            if (p < HWo) {
                 float y = fmaf(racc[e], sc, sh);
                 if (a.residual) y += __ldg(a.residual + obase + p);
                 if (a.relu) y = fmaxf(y, 0.f);
@@ -296,7 +297,7 @@ static int launch_conv_gemm(const ConvGemmArgs &a, int B, cudaStream_t st) {
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
-    dim3 grid((a.H * a.W + BN - 1) / BN, a.Cout / CG_BM, B);
+    dim3 grid((a.Ho * a.Wo + BN - 1) / BN, a.Cout / CG_BM, B);
     conv_gemm_tf32x3_kernel<BN, STAGES, RAW><<<grid, CG_THREADS + 64, SMEM, st>>>(a);
     count_launch();
     return launch_status();
@@ -337,13 +338,15 @@ extern "C" int hdn_conv_gemm_supported(int Cin, int Cout, int ksize, int dilatio
 }
 
 extern "C" int hdn_conv_gemm_f32(const float *x, const float *wpk, const float *scale, const float *shift, const float *residual, float *out,
-                                 int B, int Cin, int Cout, int H, int W, int ksize, int dilation, int relu, hdn_stream_t stream) {
+                                 int B, int Cin, int Cout, int H, int W, int ksize, int dilation, int valid, int relu, hdn_stream_t stream) {
     if (!x || !wpk || !out) return HDN_ERR_NULL;
     if (B < 1 || H < 1 || W < 1 || B > 65535) return HDN_ERR_SHAPE;
     if (!hdn_conv_gemm_supported(Cin, Cout, ksize, dilation)) return HDN_ERR_UNSUPPORTED;
     if (reinterpret_cast<uintptr_t>(wpk) & 15u) return HDN_ERR_ALIGN;
-    ConvGemmArgs a{x, wpk, scale, shift, residual, out, Cin, Cout, H, W, ksize * ksize, dilation, relu};
-    const long long tiles128 = (long long)((H * W + 127) / 128) * (Cout / CG_BM) * B;
+    const int shrink = (valid && ksize == 3) ? 2 * dilation : 0;
+    if (H - shrink < 1 || W - shrink < 1) return HDN_ERR_SHAPE;
+    ConvGemmArgs a{x, wpk, scale, shift, residual, out, Cin, Cout, H, W, ksize * ksize, dilation, relu, H - shrink, W - shrink, shrink / 2};
+    const long long tiles128 = (long long)((a.Ho * a.Wo + 127) / 128) * (Cout / CG_BM) * B;
     // small problems (tracking batch sizes): narrower pixel tiles put more CTAs on the 148 SMs
     return tiles128 >= 2 * sm_count() ? launch_conv_gemm<128, 2, 4>(a, B, (cudaStream_t)stream) : launch_conv_gemm<64, 3, 5>(a, B, (cudaStream_t)stream);
 }

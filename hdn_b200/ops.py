@@ -266,7 +266,7 @@ def score_argmax_host(cls, loc, window=None, win_influence=0.0):
     return unpack_scores(buf.cpu().numpy(), cls.shape[0], loc.shape[1])
 
 
-def conv_gemm(x, wpk, scale=None, shift=None, residual=None, ksize=1, dilation=1, relu=False, out=None):
+def conv_gemm(x, wpk, scale=None, shift=None, residual=None, ksize=1, dilation=1, relu=False, out=None, valid=False):
     """Stride-1 1x1 / 3x3 (padding = dilation) convolution + folded BatchNorm (+ residual) (+ ReLU) on tcgen05 (3xTF32).
     x [B,Cin,H,W]; wpk = pack_conv_weight(weight) (done once per layer); scale/shift [Cout]."""
     x, wpk = _dev(x, "x"), _dev(wpk, "wpk")
@@ -274,13 +274,14 @@ def conv_gemm(x, wpk, scale=None, shift=None, residual=None, ksize=1, dilation=1
     Cout = wpk.numel() // (2 * ksize * ksize * Cin)
     if wpk.numel() != 2 * Cout * ksize * ksize * Cin:
         raise RuntimeError("conv_gemm: packed weight of %d floats does not match Cin=%d, ksize=%d" % (wpk.numel(), Cin, ksize))
+    shrink = 2 * dilation if (valid and ksize == 3) else 0
     if out is None:
-        out = torch.empty((B, Cout, H, W), device=x.device, dtype=torch.float32)
+        out = torch.empty((B, Cout, H - shrink, W - shrink), device=x.device, dtype=torch.float32)
     opt = lambda t, n: _ptr(_dev(t, n)) if t is not None else None  # noqa: E731
     if residual is not None and tuple(residual.shape) != tuple(out.shape):
         raise RuntimeError("conv_gemm: residual shape mismatch")
     st = _lib.lib().hdn_conv_gemm_f32(_ptr(x), _ptr(wpk), opt(scale, "scale"), opt(shift, "shift"), opt(residual, "residual"), _ptr(out), B, Cin,
-                                      Cout, H, W, ksize, dilation, int(bool(relu)), _stream())
+                                      Cout, H, W, ksize, dilation, int(bool(valid)), int(bool(relu)), _stream())
     _lib.check(st, "hdn_conv_gemm_f32")
     return out
 

@@ -99,19 +99,20 @@ int hdn_dlt_warp_f32(const float *src4, const float *off4, const float *img, con
 int hdn_score_argmax_f32(const float *cls, const float *loc, const double *window, double win_influence, int64_t *idx, double *pscore,
                          float *score, float *gathered, int B, int L, int N, hdn_stream_t stream);
 
-/* Backbone convolution: stride-1 1x1 or 3x3 (padding = dilation) convolution + eval-mode
+/* Backbone / neck / head convolution: stride-1 1x1 or 3x3 convolution (valid = 0: padding =
+ * dilation, same-size output; valid = 1: no padding, output H-2d x W-2d) + eval-mode
  * BatchNorm + optional residual add + optional ReLU, as a 3xTF32 (fp32-accurate) implicit GEMM on tcgen05 / TMEM.
  * Replaces nn.Conv2d -> nn.BatchNorm2d (-> += residual) (-> ReLU) of hdn/models/backbone/resnet_atrous.py:62-110
  * and hdn/models/neck/neck.py:11-29.
  *   x [B,Cin,H,W];  wpk = the weight packed ONCE by hdn_conv_pack_weight_f32;  scale/shift [Cout] or NULL
- *   (y = conv*scale + shift, the folded BatchNorm);  residual [B,Cout,H,W] or NULL;  out [B,Cout,H,W].
+ *   (y = conv*scale + shift, the folded BatchNorm);  residual [B,Cout,Ho,Wo] or NULL;  out [B,Cout,Ho,Wo].
  * Requires hdn_conv_gemm_supported(): Cin % 32 == 0, Cout % 128 == 0, ksize in {1,3}.
  * hdn_conv_pack_weight_f32: wt [Cout, Ktot = ksize*ksize*Cin] tap-major (weight.permute(0,2,3,1)) -> packed [2*Cout*Ktot]
  *   floats (TF32 hi / lo halves, tiled per 128-channel x 32-deep block in the tensor core's shared-memory layout). */
 int hdn_conv_gemm_supported(int Cin, int Cout, int ksize, int dilation);
 int hdn_conv_pack_weight_f32(const float *wt, float *packed, int Cout, int Ktot, hdn_stream_t stream);
 int hdn_conv_gemm_f32(const float *x, const float *wpk, const float *scale, const float *shift, const float *residual, float *out, int B,
-                      int Cin, int Cout, int H, int W, int ksize, int dilation, int relu, hdn_stream_t stream);
+                      int Cin, int Cout, int H, int W, int ksize, int dilation, int valid, int relu, hdn_stream_t stream);
 
 #ifdef __cplusplus
 }
