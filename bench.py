@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--xcorr-algo", default="auto", choices=["auto", "direct"], help="auto = FFT correlation where the direct sum is FMA-bound")
     return ap.parse_args()
 
 
@@ -191,6 +192,9 @@ def main():
         shard.broadcast_template_pack(dev_in["ks"] + dev_in.get("kl", []), src=0)
     eng.bind(dev_in)
     L = _lib.lib()
+    from hdn_b200 import ops
+    ops.set_xcorr_algo(a.xcorr_algo)
+    k1_fft = bool(L.hdn_xcorr_uses_fft(engine.C, eng.w["sim_x"], eng.w["sim_x"], eng.w["sim_k"], eng.w["sim_k"], 0, engine.C * eng.w["sim_k"] ** 2))
 
     def step(events=None):
         """One pass; with `events`, bracket every kernel launch with CUDA events on the launching stream."""
@@ -302,7 +306,8 @@ def main():
     k1_s = kern_avg["k1"] * 1e-3
     fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
     achieved = k1_bytes / k1_s / 1e9
-    roofline = {"kernel": "xcorr_staged_kernel (K1, 6 problems/launch)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"kernel": "%s (K1, 6 problems/launch)" % ("xcorr_fft_kernel: 64x64 FFT correlation" if k1_fft else "xcorr_staged_kernel: direct sum"),
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic_from_profiles(a.workload, B),
                 "algorithmic_bytes_per_launch": k1_bytes, "launch_ms": kern_avg["k1"],
                 "fp32_tflops": k1_flops / k1_s / 1e12, "fp32_peak_tflops": fp32_peak, "fp32_frac": k1_flops / k1_s / 1e12 / fp32_peak,

@@ -16,6 +16,16 @@ inline int launch_status() {
 
 int sm_count();  // api.cu (cached per process)
 
+// Up to HDN_MAX_PROBLEMS same-shape correlation problems of one launch (device pointers, passed by value).
+struct XProblems {
+    const float *x[HDN_MAX_PROBLEMS];
+    const float *k[HDN_MAX_PROBLEMS];
+    float *out[HDN_MAX_PROBLEMS];
+};
+// xcorr_fft.cu: FFT correlation for the FMA-bound shapes.  Returns HDN_ERR_UNSUPPORTED when the shape has no FFT kernel.
+int xcorr_fft_dispatch(const XProblems &P, int n, int B, int C, int Hx, int Wx, int Hk, int Wk, int circular, long long kbs, cudaStream_t st);
+bool xcorr_fft_applicable(int C, int Hx, int Wx, int Hk, int Wk, int circular);
+
 // ---- mbarrier + bulk async copy (TMA, 1-D) -------------------------------------------------
 // SASS: cp.async.bulk -> UBLKCP, expect_tx -> SYNCS.ARRIVE.TRANS64 (B200_PROFILING.md).
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }

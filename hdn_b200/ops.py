@@ -55,6 +55,15 @@ def _xcorr(x, kernel, circular, out=None):
     return out
 
 
+XCORR_ALGOS = {"auto": 0, "direct": 1}
+
+
+def set_xcorr_algo(name):
+    """'auto' (default): the 29x29 / 15x15-template shapes run the 64x64 FFT correlation kernel (xcorr_fft.cu);
+    'direct': every shape runs the direct register-tiled sum (xcorr.cu).  Process-wide."""
+    _lib.check(_lib.lib().hdn_xcorr_set_algo(XCORR_ALGOS[name]), "hdn_xcorr_set_algo")
+
+
 def xcorr_depthwise(x, kernel, out=None):
     """hdn/core/xcorr.py:37-46.  x [B,C,Hx,Wx], kernel [B,C,h,w] (or [1,C,h,w] = template shared by the batch)."""
     return _xcorr(x, kernel, False, out)

@@ -80,9 +80,10 @@ def test_template_kernels_are_cached_and_equal_recomputed():
     model, _ = build_model()
     model.template(cuda(synth.crop_tensor(1000, (1, 6, 127, 127))))
     x = cuda(synth.crop_tensor(1001, (1, 3, 255, 255)))
-    xf = model.neck(model.backbone(x))
-    a = model.head(model.zf, xf, model._k_sim)
-    b = model.head(model.zf, xf, None)  # the reference's per-frame recomputation
+    with torch.no_grad():  # inference: template() cached its kernels on the same (tensor-core) conv path
+        xf = model.neck(model.backbone(x))
+        a = model.head(model.zf, xf, model._k_sim)
+        b = model.head(model.zf, xf, None)  # the reference's per-frame recomputation
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
 
 

@@ -25,8 +25,28 @@ def ops():
 
 
 # ------------------------------------------------------------------ K1 / K2
+@pytest.fixture(params=["auto", "direct"])
+def algo(request):
+    """Both correlation algorithms: 'auto' = FFT kernel for the 29x29 / 15x15-template shapes, 'direct' = direct sum everywhere."""
+    ops().set_xcorr_algo(request.param)
+    yield request.param
+    ops().set_xcorr_algo("auto")
+
+
+def uses_fft(C, Hx, Wx, Hk, Wk, circ):
+    from hdn_b200 import _lib
+    return bool(_lib.lib().hdn_xcorr_uses_fft(C, Hx, Wx, Hk, Wk, int(circ), C * Hk * Wk))
+
+
+def test_fft_kernel_is_the_default_for_the_fma_bound_shapes():
+    for Hx, Hk, circ in ((61, 29, 0), (29, 29, 1), (39, 15, 0)):
+        assert uses_fft(256, Hx, Hx, Hk, Hk, circ)
+    for Hx, Hk, circ in ((29, 5, 0), (13, 13, 1)):
+        assert not uses_fft(256, Hx, Hx, Hk, Hk, circ)  # HBM-bound / tiny: direct sum
+
+
 @pytest.mark.parametrize("name", golden_names("ops_k1_") + golden_names("ops_k2_"))
-def test_xcorr_golden(name):
+def test_xcorr_golden(name, algo):
     g = load_golden(name)
     fn = ops().xcorr_depthwise_circular if int(g["circular"]) else ops().xcorr_depthwise
     out = fn(g2d(g["x"]), g2d(g["k"])).cpu().numpy()
@@ -46,15 +66,19 @@ FAST_SHAPES = [  # (B, C, Hx, Wx, Hk, Wk, circular)  -- the shapes with staged T
 
 @pytest.mark.parametrize("shape", FAST_SHAPES)
 @pytest.mark.parametrize("shared", [False, True])
-def test_xcorr_vs_oracle(shape, shared):
+def test_xcorr_vs_oracle(shape, shared, algo):
     B, C, Hx, Wx, Hk, Wk, circ = shape
     rng = np.random.default_rng(hash(shape) % 2**31)
     x = rng.standard_normal((B, C, Hx, Wx)).astype(np.float32)
+    if algo == "auto":
+        x += 0.5  # post-ReLU-like features with a DC component: the hard case for a transform-domain product
     k = (rng.standard_normal((1 if shared else B, C, Hk, Wk)) * 0.1).astype(np.float32)
     ref = c_oracle.xcorr_dw(x, k, bool(circ))
     fn = ops().xcorr_depthwise_circular if circ else ops().xcorr_depthwise
     out = fn(g2d(x), g2d(k)).cpu().numpy()
     assert_close(out, ref, what=str(shape))
+    if algo == "auto" and uses_fft(C, Hx, Wx, Hk, Wk, circ):  # the FFT route is fp32-accurate, not merely within 1e-3
+        assert np.abs(out - ref).max() <= 5e-6 * np.abs(ref).max()
 
 
 def test_xcorr_multi_equals_single():
@@ -81,10 +105,11 @@ def test_xcorr_unaligned_views_fall_back_correctly():
 
 @pytest.mark.parametrize("shape", [(64, 256, 61, 61, 29, 29, 0), (64, 256, 29, 29, 29, 29, 1), (64, 256, 29, 29, 5, 5, 0),
                                    (64, 256, 13, 13, 13, 13, 1), (256, 256, 39, 39, 15, 15, 0)])
-def test_xcorr_full_size_properties(shape):
+def test_xcorr_full_size_properties(shape, algo):
     """BASELINE.json sizes (batch 64 / 256): one-hot kernels make the correlation an exact shifted crop,
     and the operator is linear in x."""
     B, C, Hx, Wx, Hk, Wk, circ = shape
+    fft = algo == "auto" and uses_fft(C, Hx, Wx, Hk, Wk, circ)
     fn = ops().xcorr_depthwise_circular if circ else ops().xcorr_depthwise
     gen = torch.Generator(device=DEV).manual_seed(5)
     x = torch.randn((B, C, Hx, Wx), device=DEV, generator=gen)
@@ -100,7 +125,10 @@ def test_xcorr_full_size_properties(shape):
         expect = x[:, :, rows][:, :, :, cols]
     else:
         expect = x[:, :, u0:u0 + Ho, v0:v0 + Wo]
-    assert torch.equal(out, expect)  # 1.0 * x + 0 * ... is exact
+    if fft:  # through the transform domain the crop is reproduced to fp32 rounding, not bit for bit
+        assert float((out - expect).abs().max()) <= 1e-5 * float(x.abs().max())
+    else:
+        assert torch.equal(out, expect)  # 1.0 * x + 0 * ... is exact
     # linearity with a dense kernel
     k = torch.randn((B, C, Hk, Wk), device=DEV, generator=gen) * 0.1
     x2 = torch.randn((B, C, Hx, Wx), device=DEV, generator=gen)
@@ -109,6 +137,11 @@ def test_xcorr_full_size_properties(shape):
     assert torch.allclose(lhs, rhs, rtol=1e-3, atol=1e-4 * float(rhs.abs().max()))
     # shared template == tiled template
     assert torch.equal(fn(x, k[:1]), fn(x, k[:1].expand(B, C, Hk, Wk).contiguous()))
+    if fft:  # the two algorithms agree far inside the parity tolerance
+        ops().set_xcorr_algo("direct")
+        direct = fn(x, k)
+        ops().set_xcorr_algo("auto")
+        assert float((fn(x, k) - direct).abs().max()) <= 5e-6 * float(direct.abs().max())
 
 
 # ------------------------------------------------------------------ K3
