@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--xcorr-algo", default="auto", choices=["auto", "direct"], help="auto = FFT correlation where the direct sum is FMA-bound")
+    ap.add_argument("--xcorr-algo", default="auto", choices=["auto", "direct", "fft"], help="auto = FFT correlation where it beats the direct sum")
     return ap.parse_args()
 
 

@@ -183,5 +183,81 @@ HDN_HD void fft64_rn(float (&re)[64], float (&im)[64]) {
     }
 }
 
+// ---- 64-point FFT split over two threads (decimation in frequency) ---------------------------------------------------------
+// Half h in {0,1} of X = FFT64(a), S = -1:   X[2m + h] = FFT32( s )[m],   s[n] = a[n] + a[n+32]            (h = 0)
+//                                                                          s[n] = (a[n] - a[n+32]) * W64^n  (h = 1)
+// Both halves need all 64 inputs; each keeps 32 outputs.  half_butterfly leaves s in (re, im)[0..31].
+template <int N = 1>
+struct HalfTw {  // (re[N], im[N]) = (d[N]) * W64^(-N), N = 1..31
+    static HDN_HD void run(float (&re)[64], float (&im)[64]) {
+        twiddle<-1, N>(re[N], im[N]);
+        HalfTw<N + 1>::run(re, im);
+    }
+};
+template <>
+struct HalfTw<32> {
+    static HDN_HD void run(float (&)[64], float (&)[64]) {}
+};
+
+HDN_HD void half_butterfly(int h, float (&re)[64], float (&im)[64]) {
+    if (h == 0) {
+#pragma unroll
+        for (int n = 0; n < 32; ++n) { re[n] += re[n + 32]; im[n] += im[n + 32]; }
+    } else {
+#pragma unroll
+        for (int n = 0; n < 32; ++n) { re[n] -= re[n + 32]; im[n] -= im[n + 32]; }
+        HalfTw<>::run(re, im);
+    }
+}
+
+// 32-point forward FFT on (re, im)[0..31], natural order in, Y[m] left at POS32(m) = 8*(m%4) + m/4.
+// n = 8a + b (a < 4, b < 8), m = c + 4d (c < 4, d < 8):  W32^(mn) = W4^(ac) * W32^(bc) * W8^(bd).
+HDN_HD constexpr int POS32(int m) { return 8 * (m & 3) + (m >> 2); }
+
+HDN_HD void dft4_fwd(float (&r)[4], float (&i)[4]) {  // W4 = -i
+    const float b0r = r[0] + r[2], b0i = i[0] + i[2], b1r = r[0] - r[2], b1i = i[0] - i[2];
+    const float b2r = r[1] + r[3], b2i = i[1] + i[3], b3r = r[1] - r[3], b3i = i[1] - i[3];
+    r[0] = b0r + b2r; i[0] = b0i + b2i;
+    r[2] = b0r - b2r; i[2] = b0i - b2i;
+    r[1] = b1r + b3i; i[1] = b1i - b3r;  // b1 + (-i)*b3
+    r[3] = b1r - b3i; i[3] = b1i + b3r;
+}
+
+template <int B = 0>
+struct Pass32 {  // for each b: DFT4 over a (stride 8), twiddle by W32^(bc) = W64^(2bc), result at [8c + b]
+    static HDN_HD void run(float (&re)[64], float (&im)[64]) {
+        float r[4], i[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) { r[a] = re[8 * a + B]; i[a] = im[8 * a + B]; }
+        dft4_fwd(r, i);
+        twiddle<-1, 2 * B * 1>(r[1], i[1]);
+        twiddle<-1, 2 * B * 2>(r[2], i[2]);
+        twiddle<-1, 2 * B * 3>(r[3], i[3]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { re[8 * c + B] = r[c]; im[8 * c + B] = i[c]; }
+        Pass32<B + 1>::run(re, im);
+    }
+};
+template <>
+struct Pass32<8> {
+    static HDN_HD void run(float (&)[64], float (&)[64]) {}
+};
+
+HDN_HD void fft32_fwd(float (&re)[64], float (&im)[64]) {
+    Pass32<>::run(re, im);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {  // DFT8 over b of the block [8c + b] -> [8c + d] = Y[c + 4d]
+        float r[8], i[8];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) { r[b] = re[8 * c + b]; i[b] = im[8 * c + b]; }
+        dft8<-1>(r, i);
+#pragma unroll
+        for (int d = 0; d < 8; ++d) { re[8 * c + d] = r[d]; im[8 * c + d] = i[d]; }
+    }
+}
+
+// X[f] of the half that owns parity f % 2, after half_butterfly + fft32_fwd:  X[f] = Y[f / 2]
+HDN_HD constexpr int HPOS(int f) { return POS32(f >> 1); }
+
 }  // namespace fft
 }  // namespace hdn

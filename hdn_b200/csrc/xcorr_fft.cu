@@ -3,11 +3,13 @@
 // Replaces hdn/core/xcorr.py:37-46 / :48-61 at 256/512 crops (61x61 (*) 29x29, 29x29 circular (*) 29x29) and the 15x15
 // large-displacement window (39x39 (*) 15x15).  Algorithm and phase functions: xcorr_fft.cuh; 64-point FFT: fft64.cuh.
 //
-// Kernel structure (one persistent CTA per SM, G = 4 planes per group, 256 threads):
+// Kernel structure (one persistent CTA per SM, G = 4 planes per group, 256 threads = 8 warps):
 //   * the x and k planes of a group are two contiguous byte ranges -> two 1-D TMA bulk copies (UBLKCP) onto an mbarrier;
-//     the NEXT group's copies are issued as soon as phase R has consumed the landing buffer, so they fly during C and O;
-//   * phases R -> C -> O separated by __syncthreads(); every thread runs whole 64-point FFTs in registers, shared memory
-//     only carries the transposes (row spectra -> columns -> rows), pitch 33 complex = conflict-free both ways;
+//     the NEXT group's copies are issued as soon as phase R has consumed the landing buffer, so they fly during the column phases;
+//   * five phases R -> CX -> CK -> CI -> O separated by __syncthreads(); a task = one half of a 64-point FFT, register-resident;
+//     all phases share ONE copy of the half-FFT code (the phase only selects the load / store code around it), so the hot loop
+//     stays resident in the instruction cache -- a fully specialised straight-line kernel (one FFT body per phase, 130 KB of
+//     SASS) spent half of its issue slots waiting for instruction fetch;
 //   * the finished G x HO x WO tile leaves through a double-buffered TMA bulk store.
 // HBM traffic is exactly the algorithmic bytes (each plane read once, each output written once).
 #include "common.cuh"
@@ -43,27 +45,38 @@ __global__ void __launch_bounds__(Cfg::NT, 1)
     int it = 0;
     for (int g = blockIdx.x; g < n_groups; g += gridDim.x, ++it) {
         mbar_wait(full, it & 1);
+        const FftBufs bufs{raw, raw + Cfg::G * Cfg::XPL, XR, KR, sout + (it & 1) * Cfg::OUT_FLOATS};
 #pragma unroll 1
-        for (int s = tid; s < Cfg::R_SLOTS; s += Cfg::NT) fftc_phase_R<Cfg>(raw, raw + Cfg::G * Cfg::XPL, XR, KR, s);
-        __syncthreads();  // row spectra complete; landing buffer free
-        if (tid == 0) {
-            const int gn = g + gridDim.x;
-            if (gn < n_groups) issue(gn);
-            bulk_wait_read<1>();  // the store issued two groups ago has left the output buffer phase O is about to fill
-        }
+        for (int ph = 0; ph < FFT_PHASES; ++ph) {
+            const int ntask = fftc_tasks<Cfg>(ph);
 #pragma unroll 1
-        for (int t = tid; t < Cfg::C_TASKS; t += Cfg::NT) fftc_phase_C<Cfg>(XR, KR, t);
-        __syncthreads();
-        float *so = sout + (it & 1) * Cfg::OUT_FLOATS;
-#pragma unroll 1
-        for (int t = tid; t < Cfg::O_TASKS; t += Cfg::NT) fftc_phase_O<Cfg>(XR, so, t);
-        fence_proxy_async_smem();  // my so[] writes -> visible to the TMA store
-        __syncthreads();           // tile complete; XR free for the next group's phase R
-        if (tid == 0) {
-            const int prob = g / groups_per_problem;
-            const long long plane0 = (long long)(g - prob * groups_per_problem) * Cfg::G;
-            bulk_s2g(P.out[prob] + plane0 * Cfg::OPL, so, Cfg::OUT_FLOATS * 4);
-            bulk_commit();
+            for (int t0 = 0; t0 < ntask; t0 += Cfg::NT) {
+                const int t = t0 + tid;
+                const int h = fft_task_half(t), unit = fft_task_unit(t);
+                float re[64], im[64];
+                const bool active = t < ntask && fftc_load<Cfg>(ph, bufs, unit, re, im);
+                if (ph == FFT_PH_CX) __syncthreads();  // columns are transformed in place: both halves have read before either writes
+                if (active) {
+                    fft::half_butterfly(h, re, im);
+                    fft::fft32_fwd(re, im);
+                    if (h == 0) fftc_store<Cfg, 0>(ph, bufs, unit, re, im);
+                    else fftc_store<Cfg, 1>(ph, bufs, unit, re, im);
+                }
+            }
+            if (ph == FFT_PH_O) fence_proxy_async_smem();  // my output-tile writes -> visible to the TMA store
+            __syncthreads();
+            if (tid == 0) {
+                if (ph == FFT_PH_R) {  // landing buffer consumed
+                    const int gn = g + gridDim.x;
+                    if (gn < n_groups) issue(gn);
+                    bulk_wait_read<1>();  // the store issued two groups ago has left the tile buffer phase O of this group fills
+                } else if (ph == FFT_PH_O) {
+                    const int prob = g / groups_per_problem;
+                    const long long plane0 = (long long)(g - prob * groups_per_problem) * Cfg::G;
+                    bulk_s2g(P.out[prob] + plane0 * Cfg::OPL, bufs.out, Cfg::OUT_FLOATS * 4);
+                    bulk_commit();
+                }
+            }
         }
     }
     if (tid == 0) bulk_wait_all<0>();

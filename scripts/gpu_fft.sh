@@ -6,7 +6,7 @@ timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "xcorr or 
 tail -5 gpurun_out/pytest_fft.log
 timeout 300 python bench.py --no-cpu --no-e2e --xcorr-algo direct > gpurun_out/bench_direct.json 2> gpurun_out/bench_fft.err
 timeout 300 python bench.py --no-cpu --no-e2e > gpurun_out/bench_fft.json 2>> gpurun_out/bench_fft.err
-timeout 300 python bench.py --no-cpu --no-e2e --workload win15 > gpurun_out/bench_fft_win15.json 2>> gpurun_out/bench_fft.err
+timeout 300 python bench.py --no-cpu --no-e2e --workload win15 --xcorr-algo fft > gpurun_out/bench_fft_win15.json 2>> gpurun_out/bench_fft.err
 python - <<'PY'
 import json
 for f in ("bench_direct", "bench_fft", "bench_fft_win15"):

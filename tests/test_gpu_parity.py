@@ -25,9 +25,9 @@ def ops():
 
 
 # ------------------------------------------------------------------ K1 / K2
-@pytest.fixture(params=["auto", "direct"])
+@pytest.fixture(params=["fft", "direct"])
 def algo(request):
-    """Both correlation algorithms: 'auto' = FFT kernel for the 29x29 / 15x15-template shapes, 'direct' = direct sum everywhere."""
+    """Both correlation algorithms: 'fft' = FFT kernel wherever one exists (29x29 / 15x15 templates), 'direct' = direct sum everywhere."""
     ops().set_xcorr_algo(request.param)
     yield request.param
     ops().set_xcorr_algo("auto")
@@ -39,10 +39,14 @@ def uses_fft(C, Hx, Wx, Hk, Wk, circ):
 
 
 def test_fft_kernel_is_the_default_for_the_fma_bound_shapes():
-    for Hx, Hk, circ in ((61, 29, 0), (29, 29, 1), (39, 15, 0)):
+    ops().set_xcorr_algo("auto")
+    for Hx, Hk, circ in ((61, 29, 0), (29, 29, 1)):
         assert uses_fft(256, Hx, Hx, Hk, Hk, circ)
-    for Hx, Hk, circ in ((29, 5, 0), (13, 13, 1)):
-        assert not uses_fft(256, Hx, Hx, Hk, Hk, circ)  # HBM-bound / tiny: direct sum
+    for Hx, Hk, circ in ((29, 5, 0), (13, 13, 1), (39, 15, 0)):
+        assert not uses_fft(256, Hx, Hx, Hk, Hk, circ)  # HBM-bound / tiny / measured slower: direct sum
+    ops().set_xcorr_algo("fft")
+    assert uses_fft(256, 39, 39, 15, 15, 0)
+    ops().set_xcorr_algo("auto")
 
 
 @pytest.mark.parametrize("name", golden_names("ops_k1_") + golden_names("ops_k2_"))
@@ -70,14 +74,14 @@ def test_xcorr_vs_oracle(shape, shared, algo):
     B, C, Hx, Wx, Hk, Wk, circ = shape
     rng = np.random.default_rng(hash(shape) % 2**31)
     x = rng.standard_normal((B, C, Hx, Wx)).astype(np.float32)
-    if algo == "auto":
+    if algo == "fft":
         x += 0.5  # post-ReLU-like features with a DC component: the hard case for a transform-domain product
     k = (rng.standard_normal((1 if shared else B, C, Hk, Wk)) * 0.1).astype(np.float32)
     ref = c_oracle.xcorr_dw(x, k, bool(circ))
     fn = ops().xcorr_depthwise_circular if circ else ops().xcorr_depthwise
     out = fn(g2d(x), g2d(k)).cpu().numpy()
     assert_close(out, ref, what=str(shape))
-    if algo == "auto" and uses_fft(C, Hx, Wx, Hk, Wk, circ):  # the FFT route is fp32-accurate, not merely within 1e-3
+    if algo == "fft" and uses_fft(C, Hx, Wx, Hk, Wk, circ):  # the FFT route is fp32-accurate, not merely within 1e-3
         assert np.abs(out - ref).max() <= 5e-6 * np.abs(ref).max()
 
 
@@ -109,7 +113,7 @@ def test_xcorr_full_size_properties(shape, algo):
     """BASELINE.json sizes (batch 64 / 256): one-hot kernels make the correlation an exact shifted crop,
     and the operator is linear in x."""
     B, C, Hx, Wx, Hk, Wk, circ = shape
-    fft = algo == "auto" and uses_fft(C, Hx, Wx, Hk, Wk, circ)
+    fft = algo == "fft" and uses_fft(C, Hx, Wx, Hk, Wk, circ)
     fn = ops().xcorr_depthwise_circular if circ else ops().xcorr_depthwise
     gen = torch.Generator(device=DEV).manual_seed(5)
     x = torch.randn((B, C, Hx, Wx), device=DEV, generator=gen)
@@ -140,7 +144,7 @@ def test_xcorr_full_size_properties(shape, algo):
     if fft:  # the two algorithms agree far inside the parity tolerance
         ops().set_xcorr_algo("direct")
         direct = fn(x, k)
-        ops().set_xcorr_algo("auto")
+        ops().set_xcorr_algo("fft")
         assert float((fn(x, k) - direct).abs().max()) <= 5e-6 * float(direct.abs().max())
 
 
