@@ -8,7 +8,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libhdn_b200.so")
+SO_PATH = os.environ.get("HDN_B200_LIB") or os.path.join(HERE, "libhdn_b200.so")  # override: A/B builds of the same ABI (dev)
 
 # name -> (restype, argtypes); mirrors include/hdn_b200.h one to one.
 _vp, _ci, _i64, _f, _d = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double

@@ -3,27 +3,31 @@
 // Replaces hdn/core/xcorr.py:37-46 / :48-61 at 256/512 crops (61x61 (*) 29x29, 29x29 circular (*) 29x29) and the 15x15
 // large-displacement window (39x39 (*) 15x15).  Algorithm and phase functions: xcorr_fft.cuh; 64-point FFT: fft64.cuh.
 //
-// Kernel structure (one persistent CTA per SM, G = 4 planes per group, 256 threads = 8 warps):
-//   * the x and k planes of a group are two contiguous byte ranges -> two 1-D TMA bulk copies (UBLKCP) onto an mbarrier;
-//     the NEXT group's copies are issued as soon as phase R has consumed the landing buffer, so they fly during the column phases;
+// Kernel structure (persistent CTAs, TWO per SM; G = 2 planes per group, 128 threads = 4 warps per CTA):
+//   * the x and k planes of a group are two contiguous byte ranges -> two 1-D TMA bulk copies (UBLKCP) onto an mbarrier.  Two
+//     planes of odd size start 0 or 8 bytes past a 16-byte boundary, so the copy fetches the enclosing 16-byte-aligned window (it
+//     stays inside the tensor: C % 4 == 0 makes the tensor's own ends aligned) and the phases index from the offset.  The NEXT
+//     group's copies are issued as soon as phase R has consumed the landing buffer, so they fly during the column phases;
 //   * five phases R -> CX -> CK -> CI -> O separated by __syncthreads(); a task = one half of a 64-point FFT, register-resident;
 //     all phases share ONE copy of the half-FFT code (the phase only selects the load / store code around it), so the hot loop
 //     stays resident in the instruction cache -- a fully specialised straight-line kernel (one FFT body per phase, 130 KB of
 //     SASS) spent half of its issue slots waiting for instruction fetch;
-//   * the finished G x HO x WO tile leaves through a double-buffered TMA bulk store.
-// HBM traffic is exactly the algorithmic bytes (each plane read once, each output written once).
+//   * inside a phase every warp first loads (shared-memory bound), then computes (issue bound), then stores; the two CTAs of an SM
+//     run unsynchronised, so one CTA's loads overlap the other's arithmetic;
+//   * the finished tile is copied out with coalesced stores (2-plane tiles are not 16-byte multiples; G = 4 uses a TMA bulk store).
+// HBM traffic is the algorithmic bytes (each plane read once, each output written once).
 #include "common.cuh"
 #include "xcorr_fft.cuh"
 
 namespace hdn {
 
 template <class Cfg>
-__global__ void __launch_bounds__(Cfg::NT, 1)
+__global__ void __launch_bounds__(Cfg::NT, Cfg::CTAS)
     xcorr_fft_kernel(XProblems P, int groups_per_problem, int n_groups, int C, long long k_bstride) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *raw = reinterpret_cast<float *>(smem_raw);
     float *sout = raw + Cfg::RAW_FLOATS;
-    float2 *XR = reinterpret_cast<float2 *>(sout + 2 * Cfg::OUT_FLOATS);
+    float2 *XR = reinterpret_cast<float2 *>(sout + Cfg::OUT_BUFS * Cfg::OUT_FLOATS);
     float2 *KR = XR + Cfg::G * Cfg::XR_PLANE;
     uint64_t *full = reinterpret_cast<uint64_t *>(KR + Cfg::G * Cfg::KR_PLANE);
     const int tid = threadIdx.x;
@@ -32,20 +36,33 @@ __global__ void __launch_bounds__(Cfg::NT, 1)
         mbar_fence_init();
     }
     __syncthreads();
-    auto issue = [&](int g) {  // elected thread only
-        const int prob = g / groups_per_problem;
+    // group g -> problem, first plane, element offsets of its x / k planes
+    auto locate = [&](int g, int &prob, long long &xoff, long long &koff, long long &ooff) {
+        prob = g / groups_per_problem;
         const long long plane0 = (long long)(g - prob * groups_per_problem) * Cfg::G;
         const long long b = plane0 / C, c0 = plane0 - b * C;
+        xoff = plane0 * Cfg::XPL;
+        koff = b * k_bstride + c0 * Cfg::KPL;
+        ooff = plane0 * Cfg::OPL;
+    };
+    auto issue = [&](int g) {  // elected thread only
+        int prob;
+        long long xoff, koff, ooff;
+        locate(g, prob, xoff, koff, ooff);
         mbar_expect_tx(full, Cfg::RAW_FLOATS * 4);
-        bulk_g2s(raw, P.x[prob] + plane0 * Cfg::XPL, Cfg::G * Cfg::XPL * 4, full);
-        bulk_g2s(raw + Cfg::G * Cfg::XPL, P.k[prob] + b * k_bstride + c0 * Cfg::KPL, Cfg::G * Cfg::KPL * 4, full);
+        bulk_g2s(raw, P.x[prob] + (xoff & ~3ll), Cfg::XWIN * 4, full);
+        bulk_g2s(raw + Cfg::XWIN, P.k[prob] + (koff & ~3ll), Cfg::KWIN * 4, full);
     };
     if (tid == 0 && (int)blockIdx.x < n_groups) issue(blockIdx.x);
 
     int it = 0;
     for (int g = blockIdx.x; g < n_groups; g += gridDim.x, ++it) {
+        int prob;
+        long long xoff, koff, ooff;
+        locate(g, prob, xoff, koff, ooff);
+        float *so = sout + (Cfg::OUT_BUFS == 2 ? (it & 1) * Cfg::OUT_FLOATS : 0);
+        const FftBufs bufs{raw + (int)(xoff & 3), raw + Cfg::XWIN + (int)(koff & 3), XR, KR, so};
         mbar_wait(full, it & 1);
-        const FftBufs bufs{raw, raw + Cfg::G * Cfg::XPL, XR, KR, sout + (it & 1) * Cfg::OUT_FLOATS};
 #pragma unroll 1
         for (int ph = 0; ph < FFT_PHASES; ++ph) {
             const int ntask = fftc_tasks<Cfg>(ph);
@@ -63,23 +80,26 @@ __global__ void __launch_bounds__(Cfg::NT, 1)
                     else fftc_store<Cfg, 1>(ph, bufs, unit, re, im);
                 }
             }
-            if (ph == FFT_PH_O) fence_proxy_async_smem();  // my output-tile writes -> visible to the TMA store
+            if (Cfg::OUT_BUFS == 2 && ph == FFT_PH_O) fence_proxy_async_smem();  // my output-tile writes -> visible to the TMA store
             __syncthreads();
-            if (tid == 0) {
-                if (ph == FFT_PH_R) {  // landing buffer consumed
-                    const int gn = g + gridDim.x;
-                    if (gn < n_groups) issue(gn);
-                    bulk_wait_read<1>();  // the store issued two groups ago has left the tile buffer phase O of this group fills
-                } else if (ph == FFT_PH_O) {
-                    const int prob = g / groups_per_problem;
-                    const long long plane0 = (long long)(g - prob * groups_per_problem) * Cfg::G;
-                    bulk_s2g(P.out[prob] + plane0 * Cfg::OPL, bufs.out, Cfg::OUT_FLOATS * 4);
-                    bulk_commit();
-                }
+            if (ph == FFT_PH_R && tid == 0) {  // landing buffer consumed
+                const int gn = g + gridDim.x;
+                if (gn < n_groups) issue(gn);
+                if (Cfg::OUT_BUFS == 2) bulk_wait_read<1>();  // the store issued two groups ago has left the tile phase O of this group fills
             }
         }
+        if (Cfg::OUT_BUFS == 2) {
+            if (tid == 0) {
+                bulk_s2g(P.out[prob] + ooff, so, Cfg::OUT_FLOATS * 4);
+                bulk_commit();
+            }
+        } else {
+            float *dst = P.out[prob] + ooff;
+#pragma unroll 2
+            for (int e = tid; e < Cfg::OUT_FLOATS; e += Cfg::NT) dst[e] = so[e];  // the next write of so[] is 5 barriers away
+        }
     }
-    if (tid == 0) bulk_wait_all<0>();
+    if (Cfg::OUT_BUFS == 2 && tid == 0) bulk_wait_all<0>();
 }
 
 template <class Cfg>
@@ -92,22 +112,26 @@ static int launch_fft(const XProblems &P, int n, int B, int C, long long kbs, cu
     }
     const int gpp = (int)(((long long)B * C) / Cfg::G);
     const int total = gpp * n;
-    const int grid = total < sm_count() ? total : sm_count();
+    const int slots = sm_count() * Cfg::CTAS;
+    const int grid = total < slots ? total : slots;
     xcorr_fft_kernel<Cfg><<<grid, Cfg::NT, Cfg::SMEM, st>>>(P, gpp, total, C, kbs);
     count_launch();
     return launch_status();
 }
 
 //                     KH  KW  HX  WX  circ  G   NT
-using F256 = FCfg<29, 29, 61, 61, false, 4, 256>;    // 256/512 crops, similarity branch
-using F256Lp = FCfg<29, 29, 29, 29, true, 4, 256>;   // 256/512 crops, log-polar branch (INSTANCE_SIZE = 512)
-using FWin15 = FCfg<15, 15, 39, 39, false, 4, 256>;  // 15x15 large-displacement window
+#ifndef HDN_FFT_G
+#define HDN_FFT_G 2
+#endif
+using F256 = FCfg<29, 29, 61, 61, false, HDN_FFT_G, 64 * HDN_FFT_G>;    // 256/512 crops, similarity branch
+using F256Lp = FCfg<29, 29, 29, 29, true, HDN_FFT_G, 64 * HDN_FFT_G>;   // 256/512 crops, log-polar branch (INSTANCE_SIZE = 512)
+using FWin15 = FCfg<15, 15, 39, 39, false, HDN_FFT_G, 64 * HDN_FFT_G>;  // 15x15 large-displacement window
 
 #define HDN_FFT_SHAPES(X) X(F256) X(F256Lp) X(FWin15)
 
 bool xcorr_fft_applicable(int C, int Hx, int Wx, int Hk, int Wk, int circular) {
 #define HDN_IS(CFG) \
-    if (Hk == CFG::KH && Wk == CFG::KW && Hx == CFG::HX && Wx == CFG::WX && (circular != 0) == CFG::CIRC && C % CFG::G == 0) return true;
+    if (Hk == CFG::KH && Wk == CFG::KW && Hx == CFG::HX && Wx == CFG::WX && (circular != 0) == CFG::CIRC && C % 4 == 0) return true;
     HDN_FFT_SHAPES(HDN_IS)
 #undef HDN_IS
     return false;
@@ -115,7 +139,7 @@ bool xcorr_fft_applicable(int C, int Hx, int Wx, int Hk, int Wk, int circular) {
 
 int xcorr_fft_dispatch(const XProblems &P, int n, int B, int C, int Hx, int Wx, int Hk, int Wk, int circular, long long kbs, cudaStream_t st) {
 #define HDN_TRY(CFG) \
-    if (Hk == CFG::KH && Wk == CFG::KW && Hx == CFG::HX && Wx == CFG::WX && (circular != 0) == CFG::CIRC && C % CFG::G == 0) \
+    if (Hk == CFG::KH && Wk == CFG::KW && Hx == CFG::HX && Wx == CFG::WX && (circular != 0) == CFG::CIRC && C % 4 == 0) \
         return launch_fft<CFG>(P, n, B, C, kbs, st);
     HDN_FFT_SHAPES(HDN_TRY)
 #undef HDN_TRY

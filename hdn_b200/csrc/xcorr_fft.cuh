@@ -47,17 +47,23 @@ struct FCfg {
     static constexpr int PITCH = 33;
     static constexpr int KR_ROWS = KH > HO ? KH : HO;
     static constexpr int XR_PLANE = 64 * PITCH, KR_PLANE = KR_ROWS * PITCH;  // complex elements
-    static constexpr int RAW_FLOATS = G * (XPL + KPL), OUT_FLOATS = G * OPL;
+    // A group's x / k planes are fetched as 16-byte-aligned windows (TMA bulk copies need 16-byte addresses and sizes): a group of 2
+    // planes of odd size starts 0 or 2 floats past a 16-byte boundary, so the window is the group rounded out to multiples of 4 floats.
+    // (offset 0: the window ends 2 floats into the next group -- never the last one, whose offset is 2 because B*C % 4 == 0.)
+    static constexpr int XWIN = (G * XPL + (G % 4 && XPL % 2 ? 2 : 0) + 3) / 4 * 4, KWIN = (G * KPL + (G % 4 && KPL % 2 ? 2 : 0) + 3) / 4 * 4;
+    static constexpr int RAW_FLOATS = XWIN + KWIN, OUT_FLOATS = G * OPL;
+    static constexpr int OUT_BUFS = G % 4 ? 1 : 2;  // 4-plane tiles leave by (asynchronous) TMA bulk store: double-buffered
     static constexpr int R_UNITS_PLANE = KH + (HP - KH + 1) / 2;  // (x_r, k_r) rows, then pairs of the remaining x rows
     static constexpr int R_UNITS = G * R_UNITS_PLANE, C_UNITS = G * 32, O_UNITS = (G / 2) * HO;
     static constexpr int pad32(int n) { return (n + 31) / 32 * 32; }
     // tasks = (unit, half); warps alternate halves so a warp runs one half only:  task t -> h = (t/32) % 2, unit = (t/64)*32 + t%32
     static constexpr int R_TASKS = 2 * pad32(R_UNITS), C_TASKS = 2 * pad32(C_UNITS), O_TASKS = 2 * pad32(O_UNITS);
     static constexpr unsigned long long SMEM =
-        (unsigned long long)(RAW_FLOATS + 2 * OUT_FLOATS) * 4 + (unsigned long long)G * (XR_PLANE + KR_PLANE) * 8 + 16;
+        (unsigned long long)(RAW_FLOATS + OUT_BUFS * OUT_FLOATS) * 4 + (unsigned long long)G * (XR_PLANE + KR_PLANE) * 8 + 16;
+    static constexpr int CTAS = SMEM <= 113 * 1024 ? 2 : 1;
     static_assert(HP <= 64 && WP <= 64, "padded input must fit the 64-point transform");
     static_assert(KH <= HP && KW <= WP && HO <= 64 && WO <= 64, "shape");
-    static_assert(G % 4 == 0, "bulk copies need 16-byte multiples; planes are paired in phase O");
+    static_assert(G % 2 == 0, "planes are paired in phase O");
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
