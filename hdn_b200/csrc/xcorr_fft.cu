@@ -123,7 +123,10 @@ static int launch_fft(const XProblems &P, int n, int B, int C, long long kbs, cu
 #ifndef HDN_FFT_G
 #define HDN_FFT_G 2
 #endif
-using F256 = FCfg<29, 29, 61, 61, false, HDN_FFT_G, 64 * HDN_FFT_G>;    // 256/512 crops, similarity branch
+#ifndef HDN_FFT_NT1
+#define HDN_FFT_NT1 (96 * HDN_FFT_G)
+#endif
+using F256 = FCfg<29, 29, 61, 61, false, HDN_FFT_G, HDN_FFT_NT1>;       // 256/512 crops, similarity branch (phase R = one round of 6 warps)
 using F256Lp = FCfg<29, 29, 29, 29, true, HDN_FFT_G, 64 * HDN_FFT_G>;   // 256/512 crops, log-polar branch (INSTANCE_SIZE = 512)
 using FWin15 = FCfg<15, 15, 39, 39, false, HDN_FFT_G, 64 * HDN_FFT_G>;  // 15x15 large-displacement window
 

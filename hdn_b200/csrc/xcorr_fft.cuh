@@ -60,7 +60,7 @@ struct FCfg {
     static constexpr int R_TASKS = 2 * pad32(R_UNITS), C_TASKS = 2 * pad32(C_UNITS), O_TASKS = 2 * pad32(O_UNITS);
     static constexpr unsigned long long SMEM =
         (unsigned long long)(RAW_FLOATS + OUT_BUFS * OUT_FLOATS) * 4 + (unsigned long long)G * (XR_PLANE + KR_PLANE) * 8 + 16;
-    static constexpr int CTAS = SMEM <= 113 * 1024 ? 2 : 1;
+    static constexpr int CTAS = SMEM <= 75 * 1024 ? 3 : (SMEM <= 113 * 1024 ? 2 : 1);  // resident CTAs per SM (228 KB of shared memory)
     static_assert(HP <= 64 && WP <= 64, "padded input must fit the 64-point transform");
     static_assert(KH <= HP && KW <= WP && HO <= 64 && WO <= 64, "shape");
     static_assert(G % 2 == 0, "planes are paired in phase O");
