@@ -76,8 +76,7 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::CTAS)
                 if (active) {
                     fft::half_butterfly(h, re, im);
                     fft::fft32_fwd(re, im);
-                    if (h == 0) fftc_store<Cfg, 0>(ph, bufs, unit, re, im);
-                    else fftc_store<Cfg, 1>(ph, bufs, unit, re, im);
+                    fftc_store<Cfg>(ph, bufs, unit, h, re, im);
                 }
             }
             if (Cfg::OUT_BUFS == 2 && ph == FFT_PH_O) fence_proxy_async_smem();  // my output-tile writes -> visible to the TMA store

@@ -174,73 +174,87 @@ HDN_HD bool fftc_load(int ph, const FftBufs &b, int unit, float (&re)[64], float
     return true;
 }
 
-// ---- stores: the half's 32 outputs X[f], f % 2 == h, are at (re, im)[HPOS(f)] ---------------------------------------------------
+// ---- stores: the half's 32 outputs X[2m + h] are at (re, im)[POS32(m)] ------------------------------------------------------
+// Phase R needs the half as a compile-time constant (the partner X[64 - f] of X[f] sits at a register index that depends on it).
 template <class Cfg, int H>
-HDN_HD void fftc_store(int ph, const FftBufs &b, int unit, const float (&re)[64], const float (&im)[64]) {
+HDN_HD void fftc_store_R(const FftBufs &b, int unit, const float (&re)[64], const float (&im)[64]) {
+    using namespace fft;
+    const int p = unit / Cfg::R_UNITS_PLANE, j = unit - p * Cfg::R_UNITS_PLANE;
+    const bool ktype = j < Cfg::KH;
+    const int r1 = ktype ? j : Cfg::KH + 2 * (j - Cfg::KH);
+    float2 *d1 = b.XR + p * Cfg::XR_PLANE + r1 * Cfg::PITCH;
+    float2 *d2 = ktype ? b.KR + p * Cfg::KR_PLANE + j * Cfg::PITCH : d1 + Cfg::PITCH;
+    const bool has2 = ktype || r1 + 1 < Cfg::HP;
+    if (H == 0) {
+        d1[0] = float2{2.f * re[HPOS(0)], 2.f * re[HPOS(32)]};
+        if (has2) d2[0] = float2{2.f * im[HPOS(0)], 2.f * im[HPOS(32)]};
+    }
+#pragma unroll
+    for (int f = 2 - H; f < 32; f += 2) {  // 2A(f) = Z(f) + conj Z(-f),  2B(f) = (Z(f) - conj Z(-f)) / i
+        const float ar = re[HPOS(f)], ai = im[HPOS(f)], br = re[HPOS(64 - f)], bi = im[HPOS(64 - f)];
+        d1[f] = float2{ar + br, ai - bi};
+        if (has2) d2[f] = float2{ai + bi, br - ar};
+    }
+}
+
+template <class Cfg>
+HDN_HD void fftc_store(int ph, const FftBufs &b, int unit, int h, const float (&re)[64], const float (&im)[64]) {
     using namespace fft;
     if (ph == FFT_PH_R) {
-        const int p = unit / Cfg::R_UNITS_PLANE, j = unit - p * Cfg::R_UNITS_PLANE;
-        const bool ktype = j < Cfg::KH;
-        const int r1 = ktype ? j : Cfg::KH + 2 * (j - Cfg::KH);
-        float2 *d1 = b.XR + p * Cfg::XR_PLANE + r1 * Cfg::PITCH;
-        float2 *d2 = ktype ? b.KR + p * Cfg::KR_PLANE + j * Cfg::PITCH : d1 + Cfg::PITCH;
-        const bool has2 = ktype || r1 + 1 < Cfg::HP;
-        if (H == 0) {
-            d1[0] = float2{2.f * re[HPOS(0)], 2.f * re[HPOS(32)]};
-            if (has2) d2[0] = float2{2.f * im[HPOS(0)], 2.f * im[HPOS(32)]};
-        }
-#pragma unroll
-        for (int f = 2 - H; f < 32; f += 2) {  // 2A(f) = Z(f) + conj Z(-f),  2B(f) = (Z(f) - conj Z(-f)) / i
-            const float ar = re[HPOS(f)], ai = im[HPOS(f)], br = re[HPOS(64 - f)], bi = im[HPOS(64 - f)];
-            d1[f] = float2{ar + br, ai - bi};
-            if (has2) d2[f] = float2{ai + bi, br - ar};
-        }
+        if (h == 0) fftc_store_R<Cfg, 0>(b, unit, re, im);
+        else fftc_store_R<Cfg, 1>(b, unit, re, im);
         return;
     }
     if (ph == FFT_PH_O) {
         const int m = unit / Cfg::HO, i = unit - m * Cfg::HO;
         constexpr float SCALE = 1.0f / 16384.0f;
-        float *op = b.out + (2 * m) * Cfg::OPL + i * Cfg::WO, *oq = op + Cfg::OPL;
+        float *op = b.out + (2 * m) * Cfg::OPL + i * Cfg::WO + h, *oq = op + Cfg::OPL;
 #pragma unroll
-        for (int jj = H; jj < Cfg::WO; jj += 2) {
-            op[jj] = re[HPOS(jj)] * SCALE;
-            oq[jj] = im[HPOS(jj)] * -SCALE;
+        for (int mm = 0; 2 * mm < Cfg::WO; ++mm) {
+            if (2 * mm + 1 < Cfg::WO || h == 0) {
+                op[2 * mm] = re[POS32(mm)] * SCALE;
+                oq[2 * mm] = im[POS32(mm)] * -SCALE;
+            }
         }
         return;
     }
     const int p = unit >> 5, f = unit & 31;
-    float2 *xc = b.XR + p * Cfg::XR_PLANE + f;
+    float2 *xc = b.XR + p * Cfg::XR_PLANE + f + h * Cfg::PITCH;  // row 2m + h of column f
     if (ph == FFT_PH_CX) {
 #pragma unroll
-        for (int fr = H; fr < 64; fr += 2) xc[fr * Cfg::PITCH] = float2{re[HPOS(fr)], im[HPOS(fr)]};
+        for (int mm = 0; mm < 32; ++mm) xc[2 * mm * Cfg::PITCH] = float2{re[POS32(mm)], im[POS32(mm)]};
     } else if (ph == FFT_PH_CI) {
-        float2 *kc = b.KR + p * Cfg::KR_PLANE + f;
+        float2 *kc = b.KR + p * Cfg::KR_PLANE + f + h * Cfg::PITCH;
 #pragma unroll
-        for (int i = H; i < Cfg::HO; i += 2) kc[i * Cfg::PITCH] = float2{re[HPOS(i)], im[HPOS(i)]};
-    } else {  // CK: conj(P) = conj(X^) * K^ over X^
-        if (f != 0) {
+        for (int mm = 0; 2 * mm < Cfg::HO; ++mm)
+            if (2 * mm + 1 < Cfg::HO || h == 0) kc[2 * mm * Cfg::PITCH] = float2{re[POS32(mm)], im[POS32(mm)]};
+    } else if (f != 0) {  // CK: conj(P) = conj(X^) * K^ over X^
 #pragma unroll
-            for (int fr = H; fr < 64; fr += 2) {
-                const float2 x = xc[fr * Cfg::PITCH];
-                const float kr = re[HPOS(fr)], ki = im[HPOS(fr)];
-                xc[fr * Cfg::PITCH] = float2{x.x * kr + x.y * ki, x.x * ki - x.y * kr};
-            }
-        } else {
-            // packed pair of real-row columns (0 and 32): W = V0 + i*V32 with V0, V32 Hermitian in fr.  For each (fr, -fr):
-            //   4*X0 = A + conj B,  4*X32 = (A - conj B)/i   (A = Wx(fr), B = Wx(-fr));  likewise K from C = Wk(fr), D = Wk(-fr)
-            //   Q(fr) = P0 + i*P32,  Q(-fr) = conj P0 + i*conj P32,  P = X * conj K;  conj(Q) is stored; 1/4 restores the scale
+        for (int mm = 0; mm < 32; ++mm) {
+            const float2 x = xc[2 * mm * Cfg::PITCH];
+            const float kr = re[POS32(mm)], ki = im[POS32(mm)];
+            xc[2 * mm * Cfg::PITCH] = float2{x.x * kr + x.y * ki, x.x * ki - x.y * kr};
+        }
+    } else {
+        // CK, column 0 = the packed pair of real-row columns (0 and 32): W = V0 + i*V32 with V0, V32 Hermitian in fr.  For (fr, -fr):
+        //   4*X0 = A + conj B,  4*X32 = (A - conj B)/i   (A = Wx(fr), B = Wx(-fr));  likewise K from C = Wk(fr), D = Wk(-fr)
+        //   Q(fr) = P0 + i*P32,  Q(-fr) = conj P0 + i*conj P32,  P = X * conj K;  conj(Q) is stored; 1/4 restores the scale.
+        // One lane per plane runs this, so it is a ROLLED loop over shared memory (K^ parked in the spare pad column 32 of XR) to
+        // keep it out of the instruction-cache footprint; fr and -fr have the parity of h, i.e. both were written by this thread.
+        float2 *kp = xc + 32;
 #pragma unroll
-            for (int fr = H; fr <= 32; fr += 2) {
-                const int mf = (64 - fr) & 63;
-                const float2 A = xc[fr * Cfg::PITCH], B = xc[mf * Cfg::PITCH];
-                const float cr = re[HPOS(fr)], ci = im[HPOS(fr)], dr = re[HPOS(mf)], di = im[HPOS(mf)];
-                const float ur = A.x + B.x, ui = A.y - B.y, vr = A.y + B.y, vi = B.x - A.x;
-                const float sr = cr + dr, si = ci - di, tr = ci + di, ti = dr - cr;
-                const float p0r = 0.25f * (ur * sr + ui * si), p0i = 0.25f * (ui * sr - ur * si);
-                const float p1r = 0.25f * (vr * tr + vi * ti), p1i = 0.25f * (vi * tr - vr * ti);
-                xc[fr * Cfg::PITCH] = float2{p0r - p1i, -p0i - p1r};
-                if (mf != fr) xc[mf * Cfg::PITCH] = float2{p0r + p1i, p0i - p1r};
-            }
+        for (int mm = 0; mm < 32; ++mm) kp[2 * mm * Cfg::PITCH] = float2{re[POS32(mm)], im[POS32(mm)]};
+        float2 *c0 = b.XR + p * Cfg::XR_PLANE;
+#pragma unroll 1
+        for (int fr = h; fr <= 32; fr += 2) {
+            const int mf = (64 - fr) & 63;
+            const float2 A = c0[fr * Cfg::PITCH], B = c0[mf * Cfg::PITCH], Cc = c0[fr * Cfg::PITCH + 32], D = c0[mf * Cfg::PITCH + 32];
+            const float ur = A.x + B.x, ui = A.y - B.y, vr = A.y + B.y, vi = B.x - A.x;
+            const float sr = Cc.x + D.x, si = Cc.y - D.y, tr = Cc.y + D.y, ti = D.x - Cc.x;
+            const float p0r = 0.25f * (ur * sr + ui * si), p0i = 0.25f * (ui * sr - ur * si);
+            const float p1r = 0.25f * (vr * tr + vi * ti), p1i = 0.25f * (vi * tr - vr * ti);
+            c0[fr * Cfg::PITCH] = float2{p0r - p1i, -p0i - p1r};
+            if (mf != fr) c0[mf * Cfg::PITCH] = float2{p0r + p1i, p0i - p1r};
         }
     }
 }

@@ -30,8 +30,7 @@ static void run_group(const std::vector<float> &raw, std::vector<float> &out, bo
             const int h = fft_task_half(t), unit = fft_task_unit(t);
             fft::half_butterfly(h, r.re, r.im);
             fft::fft32_fwd(r.re, r.im);
-            if (h == 0) fftc_store<Cfg, 0>(ph, b, unit, r.re, r.im);
-            else fftc_store<Cfg, 1>(ph, b, unit, r.re, r.im);
+            fftc_store<Cfg>(ph, b, unit, h, r.re, r.im);
         };
         if (ph == FFT_PH_CX) {  // the kernel has a barrier between the loads and the stores of this phase
             std::vector<Regs> regs(ntask);
