@@ -4,7 +4,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv > gpurun_out/gpu.txt 2>&1
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 timeout 400 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
 timeout 300 python bench.py --workload 127/255 --batch 512 --no-cpu > gpurun_out/bench_native.json 2>> gpurun_out/bench.err
 timeout 300 python bench.py --workload win15 --no-cpu > gpurun_out/bench_win15.json 2>> gpurun_out/bench.err
@@ -12,6 +12,9 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > gpurun_out/launches_bench.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:xcorr -c 2 -o gpurun_out/prof_xcorr_256 -f \
     python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/prof_xcorr.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:xcorr -c 2 -o gpurun_out/prof_xcorr_256_direct -f \
+    python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --xcorr-algo direct > gpurun_out/prof_xcorr_direct.log 2>&1
+timeout 300 python bench.py --no-cpu --no-e2e --xcorr-algo direct > gpurun_out/bench_direct.json 2>> gpurun_out/bench.err
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_gemm -c 1 -s 2 -o gpurun_out/prof_conv_gemm -f \
     python scripts/tune/conv_one.py > gpurun_out/prof_conv.log 2>&1
 timeout 300 python -m hdn_b200.runner --sequences 2 --frames 40 > gpurun_out/runner.json 2> gpurun_out/runner.err
