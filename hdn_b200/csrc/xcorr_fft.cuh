@@ -13,7 +13,7 @@
 // phase -> { load (phase-specific) ; half-FFT (shared) ; store (phase-specific) } whose hot body stays in the instruction cache.
 //
 // Per plane (shared-memory buffers XR [64][33] complex, KR [max(KH,HO)][33] complex; 33 = odd pitch, conflict-free both ways):
-//   R   rows     unit = two REAL rows packed into one complex row z = a + i*b:  (x_r, k_r) for r < KH, then (x_r, x_r+1).
+//   R   rows     unit = two REAL rows packed into one complex row z = a + i*b:  (x_r, k_r) for r < KH, then (x_r, x_{r+np}).
 //                Z = FFT(z);  2A(f) = Z(f) + conj Z(-f),  2B(f) = (Z(f) - conj Z(-f)) / i.   Only f = 0..32 is kept
 //                (Hermitian); A(0), A(32) are real and share slot 0 -> 32 complex per row.  -> XR rows (x), KR rows (k).
 //   CX  columns  unit = frequency column f < 32 of XR:  X^ = FFT_r(2X[:, f])  (in place, 64 rows).
@@ -53,7 +53,8 @@ struct FCfg {
     static constexpr int XWIN = (G * XPL + (G % 4 && XPL % 2 ? 2 : 0) + 3) / 4 * 4, KWIN = (G * KPL + (G % 4 && KPL % 2 ? 2 : 0) + 3) / 4 * 4;
     static constexpr int RAW_FLOATS = XWIN + KWIN, OUT_FLOATS = G * OPL;
     static constexpr int OUT_BUFS = G % 4 ? 1 : 2;  // 4-plane tiles leave by (asynchronous) TMA bulk store: double-buffered
-    static constexpr int R_UNITS_PLANE = KH + (HP - KH + 1) / 2;  // (x_r, k_r) rows, then pairs of the remaining x rows
+    static constexpr int R_PAIRS = (HP - KH + 1) / 2;         // the x rows without a kernel row are packed in pairs (r, r + R_PAIRS):
+    static constexpr int R_UNITS_PLANE = KH + R_PAIRS;        // consecutive units read consecutive rows (odd pitch: no bank conflicts)
     static constexpr int R_UNITS = G * R_UNITS_PLANE, C_UNITS = G * 32, O_UNITS = (G / 2) * HO;
     static constexpr int pad32(int n) { return (n + 31) / 32 * 32; }
     // tasks = (unit, half); warps alternate halves so a warp runs one half only:  task t -> h = (t/32) % 2, unit = (t/64)*32 + t%32
@@ -96,7 +97,7 @@ HDN_HD bool fftc_load(int ph, const FftBufs &b, int unit, float (&re)[64], float
         if (unit >= Cfg::R_UNITS) return false;
         const int p = unit / Cfg::R_UNITS_PLANE, j = unit - p * Cfg::R_UNITS_PLANE;
         const bool ktype = j < Cfg::KH;
-        const int r1 = ktype ? j : Cfg::KH + 2 * (j - Cfg::KH);
+        const int r1 = j;  // j < KH: (x_j, k_j);  else (x_j, x_{j + R_PAIRS})
         const float *xrow = b.rawx + p * Cfg::XPL + fft_src_row<Cfg>(r1) * Cfg::WX;
 #pragma unroll
         for (int n = 0; n < 64; ++n) {
@@ -109,7 +110,7 @@ HDN_HD bool fftc_load(int ph, const FftBufs &b, int unit, float (&re)[64], float
 #pragma unroll
             for (int n = 0; n < 64; ++n) im[n] = n < Cfg::KW ? krow[n] : 0.f;
         } else {
-            const int r2 = r1 + 1;
+            const int r2 = r1 + Cfg::R_PAIRS;
             const bool has2 = r2 < Cfg::HP;
             const float *xrow2 = b.rawx + p * Cfg::XPL + fft_src_row<Cfg>(has2 ? r2 : r1) * Cfg::WX;
 #pragma unroll
@@ -181,10 +182,10 @@ HDN_HD void fftc_store_R(const FftBufs &b, int unit, const float (&re)[64], cons
     using namespace fft;
     const int p = unit / Cfg::R_UNITS_PLANE, j = unit - p * Cfg::R_UNITS_PLANE;
     const bool ktype = j < Cfg::KH;
-    const int r1 = ktype ? j : Cfg::KH + 2 * (j - Cfg::KH);
+    const int r1 = j;
     float2 *d1 = b.XR + p * Cfg::XR_PLANE + r1 * Cfg::PITCH;
-    float2 *d2 = ktype ? b.KR + p * Cfg::KR_PLANE + j * Cfg::PITCH : d1 + Cfg::PITCH;
-    const bool has2 = ktype || r1 + 1 < Cfg::HP;
+    float2 *d2 = ktype ? b.KR + p * Cfg::KR_PLANE + j * Cfg::PITCH : d1 + Cfg::R_PAIRS * Cfg::PITCH;
+    const bool has2 = ktype || r1 + Cfg::R_PAIRS < Cfg::HP;
     if (H == 0) {
         d1[0] = float2{2.f * re[HPOS(0)], 2.f * re[HPOS(32)]};
         if (has2) d2[0] = float2{2.f * im[HPOS(0)], 2.f * im[HPOS(32)]};
