@@ -1,20 +1,19 @@
-// xcorr_fft.cu -- K1/K2 by 64x64 FFT for the shapes where the direct correlation is FMA-bound (29x29 and 15x15 templates).
+// xcorr_fft.cu -- K1/K2 in the transform domain for the shapes where the direct correlation is FMA-bound (29x29 and 15x15 templates).
 //
 // Replaces hdn/core/xcorr.py:37-46 / :48-61 at 256/512 crops (61x61 (*) 29x29, 29x29 circular (*) 29x29) and the 15x15
 // large-displacement window (39x39 (*) 15x15).  Algorithm and phase functions: xcorr_fft.cuh; 64-point FFT: fft64.cuh.
 //
-// Kernel structure (persistent CTAs, TWO per SM; G = 2 planes per group, 128 threads = 4 warps per CTA):
+// Kernel structure (persistent CTAs, two or three per SM; G = 2 planes per group, 4-6 warps per CTA):
 //   * the x and k planes of a group are two contiguous byte ranges -> two 1-D TMA bulk copies (UBLKCP) onto an mbarrier.  Two
 //     planes of odd size start 0 or 8 bytes past a 16-byte boundary, so the copy fetches the enclosing 16-byte-aligned window (it
 //     stays inside the tensor: C % 4 == 0 makes the tensor's own ends aligned) and the phases index from the offset.  The NEXT
-//     group's copies are issued as soon as phase R has consumed the landing buffer, so they fly during the column phases;
-//   * five phases R -> CX -> CK -> CI -> O separated by __syncthreads(); a task = one half of a 64-point FFT, register-resident;
-//     all phases share ONE copy of the half-FFT code (the phase only selects the load / store code around it), so the hot loop
-//     stays resident in the instruction cache -- a fully specialised straight-line kernel (one FFT body per phase, 130 KB of
-//     SASS) spent half of its issue slots waiting for instruction fetch;
-//   * inside a phase every warp first loads (shared-memory bound), then computes (issue bound), then stores; the two CTAs of an SM
-//     run unsynchronised, so one CTA's loads overlap the other's arithmetic;
-//   * the finished tile is copied out with coalesced stores (2-plane tiles are not 16-byte multiples; G = 4 uses a TMA bulk store).
+//     group's copies are issued as soon as phase R has consumed the landing buffer, so they fly during the column stage;
+//   * phase R (row FFTs) -> column stage (direct complex correlation per frequency column, a dense FFMA loop) -> phase O
+//     (inverse row FFTs), separated by __syncthreads().  An FFT task = one half of a 64-point FFT, register-resident; R and O
+//     share ONE copy of the half-FFT code (the phase only selects the load / store code around it) -- a fully specialised
+//     straight-line kernel (one FFT body per phase, 130 KB of SASS) spent half of its issue slots waiting for instruction fetch;
+//   * the CTAs of an SM run unsynchronised, so one CTA's shared-memory-bound load section overlaps another's arithmetic;
+//   * the finished tile (staged over the dead row-spectrum buffer) is copied out with coalesced stores.
 // HBM traffic is the algorithmic bytes (each plane read once, each output written once).
 #include "common.cuh"
 #include "xcorr_fft.cuh"
@@ -26,17 +25,18 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::CTAS)
     xcorr_fft_kernel(XProblems P, int groups_per_problem, int n_groups, int C, long long k_bstride) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *raw = reinterpret_cast<float *>(smem_raw);
-    float *sout = raw + Cfg::RAW_FLOATS;
-    float2 *XR = reinterpret_cast<float2 *>(sout + Cfg::OUT_BUFS * Cfg::OUT_FLOATS);
+    float2 *XR = reinterpret_cast<float2 *>(raw + Cfg::RAW_FLOATS);
     float2 *KR = XR + Cfg::G * Cfg::XR_PLANE;
-    uint64_t *full = reinterpret_cast<uint64_t *>(KR + Cfg::G * Cfg::KR_PLANE);
+    float2 *CT = KR + Cfg::G * Cfg::KR_PLANE;
+    uint64_t *full = reinterpret_cast<uint64_t *>(CT + Cfg::G * Cfg::CT_PLANE);
+    float *so = reinterpret_cast<float *>(XR);  // output tile: XR is dead once the column stage is done
     const int tid = threadIdx.x;
     if (tid == 0) {
         mbar_init(full, 1);
         mbar_fence_init();
     }
     __syncthreads();
-    // group g -> problem, first plane, element offsets of its x / k planes
+    // group g -> problem, element offsets of its x / k / out planes
     auto locate = [&](int g, int &prob, long long &xoff, long long &koff, long long &ooff) {
         prob = g / groups_per_problem;
         const long long plane0 = (long long)(g - prob * groups_per_problem) * Cfg::G;
@@ -60,8 +60,7 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::CTAS)
         int prob;
         long long xoff, koff, ooff;
         locate(g, prob, xoff, koff, ooff);
-        float *so = sout + (Cfg::OUT_BUFS == 2 ? (it & 1) * Cfg::OUT_FLOATS : 0);
-        const FftBufs bufs{raw + (int)(xoff & 3), raw + Cfg::XWIN + (int)(koff & 3), XR, KR, so};
+        const FftBufs bufs{raw + (int)(xoff & 3), raw + Cfg::XWIN + (int)(koff & 3), XR, KR, CT, so};
         mbar_wait(full, it & 1);
 #pragma unroll 1
         for (int ph = 0; ph < FFT_PHASES; ++ph) {
@@ -71,34 +70,28 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::CTAS)
                 const int t = t0 + tid;
                 const int h = fft_task_half(t), unit = fft_task_unit(t);
                 float re[64], im[64];
-                const bool active = t < ntask && fftc_load<Cfg>(ph, bufs, unit, re, im);
-                if (ph == FFT_PH_CX) __syncthreads();  // columns are transformed in place: both halves have read before either writes
-                if (active) {
+                if (t < ntask && fftc_load<Cfg>(ph, bufs, unit, re, im)) {
                     fft::half_butterfly(h, re, im);
                     fft::fft32_fwd(re, im);
                     fftc_store<Cfg>(ph, bufs, unit, h, re, im);
                 }
             }
-            if (Cfg::OUT_BUFS == 2 && ph == FFT_PH_O) fence_proxy_async_smem();  // my output-tile writes -> visible to the TMA store
             __syncthreads();
-            if (ph == FFT_PH_R && tid == 0) {  // landing buffer consumed
-                const int gn = g + gridDim.x;
-                if (gn < n_groups) issue(gn);
-                if (Cfg::OUT_BUFS == 2) bulk_wait_read<1>();  // the store issued two groups ago has left the tile phase O of this group fills
+            if (ph == FFT_PH_R) {
+                if (tid == 0) {  // landing buffer consumed
+                    const int gn = g + gridDim.x;
+                    if (gn < n_groups) issue(gn);
+                }
+#pragma unroll 1
+                for (int t = tid; t < Cfg::COL_TASKS; t += Cfg::NT) fftc_col<Cfg>(bufs, t);
+                __syncthreads();
             }
         }
-        if (Cfg::OUT_BUFS == 2) {
-            if (tid == 0) {
-                bulk_s2g(P.out[prob] + ooff, so, Cfg::OUT_FLOATS * 4);
-                bulk_commit();
-            }
-        } else {
-            float *dst = P.out[prob] + ooff;
+        float *dst = P.out[prob] + ooff;
 #pragma unroll 2
-            for (int e = tid; e < Cfg::OUT_FLOATS; e += Cfg::NT) dst[e] = so[e];  // the next write of so[] is 5 barriers away
-        }
+        for (int e = tid; e < Cfg::OUT_FLOATS; e += Cfg::NT) dst[e] = so[e];
+        __syncthreads();  // the tile aliases XR, which the next group's phase R writes
     }
-    if (Cfg::OUT_BUFS == 2 && tid == 0) bulk_wait_all<0>();
 }
 
 template <class Cfg>

@@ -1,28 +1,27 @@
-// xcorr_fft.cuh -- per-thread phase code of the FFT depth-wise correlation (K1/K2 at the FMA-bound shapes).
+// xcorr_fft.cuh -- per-thread phase code of the transform-domain depth-wise correlation (K1/K2 at the FMA-bound shapes).
 //
 //   out[i,j] = sum_{u,v} xp[i+u, j+v] * k[u,v]     xp = x (K1) or its circular-row / replicate-column padding (K2)
 //
-// is a 64x64 circular correlation whenever the padded input fits 64x64 (no wrap reaches a valid output):
-//   OUT = IFFT2( FFT2(xp) * conj(FFT2(k)) ).
-// Direct evaluation costs KH*KW FMAs per output (841 at 29x29: 81 flop/B, FMA-bound at 6-7x the HBM time); this route
-// costs ~160 64-point FFTs per plane, ~5x fewer instructions.
+// Direct evaluation costs KH*KW FMAs per output (841 at 29x29: 81 flop/B, FMA-bound at 6-7x the HBM time).  Here the sum
+// over v (along a row) is taken in the frequency domain and the sum over u (across rows) directly:
 //
-// Every 64-point FFT is done by TWO threads (halves h = 0/1 own the even/odd outputs, fft64.cuh) entirely in registers;
-// shared memory only carries the transposes.  All five phases run the SAME forward half-FFT code (inverse transforms use
-// IFFT(a) = conj(FFT(conj a)), the conjugations are folded into the neighbouring phases), so the kernel is a loop
-// phase -> { load (phase-specific) ; half-FFT (shared) ; store (phase-specific) } whose hot body stays in the instruction cache.
+//   R    rows     X'(r,f) = FFT64_j xp[r,j],  K'(u,f) = FFT64_v k[u,v]        (the padded row fits 64 points: no wrap-around
+//                 reaches a valid output).  Rows are REAL, so two of them share one complex FFT (z = a + i*b,
+//                 2A(f) = Z(f) + conj Z(-f), 2B(f) = (Z(f) - conj Z(-f))/i): (x_r, k_r) for r < KH, then (x_r, x_{r+np}).
+//                 Only f = 0..32 is kept (Hermitian); the real values at f = 0 and f = 32 share slot 0 -> 32 complex per row.
+//   COL  columns  c~(i,f) = sum_u X'(i+u,f) * conj K'(u,f)       a 1-D complex correlation per frequency column: KH complex
+//                 MACs per output instead of KH*KW real ones.  (Slot 0 holds two real columns: component-wise products.)
+//   O    outputs  out(i,:) = IFFT64_f c~(i,f), two planes per complex FFT:  Q(f) = c~_p(i,f) + i*c~_q(i,f), extended to f > 32
+//                 by Hermitian symmetry;  out_p(i,:) + i*out_q(i,:) = IFFT(Q) = conj(FFT(conj Q)).
 //
-// Per plane (shared-memory buffers XR [64][33] complex, KR [max(KH,HO)][33] complex; 33 = odd pitch, conflict-free both ways):
-//   R   rows     unit = two REAL rows packed into one complex row z = a + i*b:  (x_r, k_r) for r < KH, then (x_r, x_{r+np}).
-//                Z = FFT(z);  2A(f) = Z(f) + conj Z(-f),  2B(f) = (Z(f) - conj Z(-f)) / i.   Only f = 0..32 is kept
-//                (Hermitian); A(0), A(32) are real and share slot 0 -> 32 complex per row.  -> XR rows (x), KR rows (k).
-//   CX  columns  unit = frequency column f < 32 of XR:  X^ = FFT_r(2X[:, f])  (in place, 64 rows).
-//   CK  columns  K^ = FFT_r(2K[:, f]);  conj(P) = conj(X^) * K^ stored over X^.   Column 0 is the packed pair of the
-//                (real-row) columns 0 and 32: lane 0 separates them, multiplies, re-packs.
-//   CI  columns  conj(c~[:, f]) = FFT_fr(conj P)  -> KR rows i < HO   (c~ = IFFT_fr(P): spatial rows, frequency columns)
-//   O   outputs  unit = output row i of a PAIR of planes (p, q):  Q(f) = c~_p(i,f) + i*c~_q(i,f), extended to f > 32 by
-//                Hermitian symmetry;  out_p(i,:) + i*out_q(i,:) = IFFT(Q) = conj(FFT(conj Q)).
-// Scale: two factors of 2 and two unnormalised inverse transforms = 4 * 64 * 64 = 2^14 (exact).
+// Per output this is ~4*KH + 2 * (64-point FFT / 33) instead of KH*KW operations, fp32-accurate (3e-7 of max|out|).  A full
+// 2-D FFT (columns transformed too) has the same operation count but needs five barrier-separated phases of twiddle-heavy
+// code; the direct column stage is a dense FFMA loop like the direct kernel's.
+//
+// Every 64-point FFT is done by TWO threads (halves h = 0/1 own the even/odd outputs, fft64.cuh) entirely in registers, and
+// phases R and O run the SAME forward half-FFT code (the phase only selects the load / store code around it), so the hot
+// loops stay resident in the instruction cache.  Shared memory per plane: XR [rows][33], KR [KH][33], CT [HO][33] complex
+// (33 = odd pitch: conflict-free for row-wise and column-wise access).  Scale: 2 * 2 * 64 = 2^8 (exact).
 //
 // Host-compilable: tests/native/host_fft_check.cpp runs these phases task by task on the CPU against a direct correlation.
 #pragma once
@@ -45,22 +44,24 @@ struct FCfg {
     static constexpr int HO = HP - KH + 1, WO = WP - KW + 1;
     static constexpr int XPL = HX * WX, KPL = KH * KW, OPL = HO * WO;
     static constexpr int PITCH = 33;
-    static constexpr int KR_ROWS = KH > HO ? KH : HO;
-    static constexpr int XR_PLANE = 64 * PITCH, KR_PLANE = KR_ROWS * PITCH;  // complex elements
+    // column stage: a warp = (plane, segment of SEG consecutive output rows), lane = frequency column
+    static constexpr int NSEG = NT / (32 * G) > 0 ? NT / (32 * G) : 1, SEG = (HO + NSEG - 1) / NSEG, TB = 8;
+    static constexpr int XR_ROWS = NSEG * SEG + KH - 1 > HP ? NSEG * SEG + KH - 1 : HP;  // rows past HP are read (never used) by the last segment
+    static constexpr int XR_PLANE = XR_ROWS * PITCH, KR_PLANE = KH * PITCH, CT_PLANE = HO * PITCH;  // complex elements
     // A group's x / k planes are fetched as 16-byte-aligned windows (TMA bulk copies need 16-byte addresses and sizes): a group of 2
     // planes of odd size starts 0 or 2 floats past a 16-byte boundary, so the window is the group rounded out to multiples of 4 floats.
     // (offset 0: the window ends 2 floats into the next group -- never the last one, whose offset is 2 because B*C % 4 == 0.)
     static constexpr int XWIN = (G * XPL + (G % 4 && XPL % 2 ? 2 : 0) + 3) / 4 * 4, KWIN = (G * KPL + (G % 4 && KPL % 2 ? 2 : 0) + 3) / 4 * 4;
     static constexpr int RAW_FLOATS = XWIN + KWIN, OUT_FLOATS = G * OPL;
-    static constexpr int OUT_BUFS = G % 4 ? 1 : 2;  // 4-plane tiles leave by (asynchronous) TMA bulk store: double-buffered
     static constexpr int R_PAIRS = (HP - KH + 1) / 2;         // the x rows without a kernel row are packed in pairs (r, r + R_PAIRS):
     static constexpr int R_UNITS_PLANE = KH + R_PAIRS;        // consecutive units read consecutive rows (odd pitch: no bank conflicts)
-    static constexpr int R_UNITS = G * R_UNITS_PLANE, C_UNITS = G * 32, O_UNITS = (G / 2) * HO;
+    static constexpr int R_UNITS = G * R_UNITS_PLANE, O_UNITS = (G / 2) * HO;
     static constexpr int pad32(int n) { return (n + 31) / 32 * 32; }
-    // tasks = (unit, half); warps alternate halves so a warp runs one half only:  task t -> h = (t/32) % 2, unit = (t/64)*32 + t%32
-    static constexpr int R_TASKS = 2 * pad32(R_UNITS), C_TASKS = 2 * pad32(C_UNITS), O_TASKS = 2 * pad32(O_UNITS);
-    static constexpr unsigned long long SMEM =
-        (unsigned long long)(RAW_FLOATS + OUT_BUFS * OUT_FLOATS) * 4 + (unsigned long long)G * (XR_PLANE + KR_PLANE) * 8 + 16;
+    // FFT tasks = (unit, half); warps alternate halves so a warp runs one half only:  task t -> h = (t/32) % 2, unit = (t/64)*32 + t%32
+    static constexpr int R_TASKS = 2 * pad32(R_UNITS), O_TASKS = 2 * pad32(O_UNITS), COL_TASKS = G * NSEG * 32;
+    // the output tile is staged over XR (dead once the column stage is done)
+    static_assert((unsigned long long)G * XR_PLANE * 8 >= (unsigned long long)OUT_FLOATS * 4, "output tile must fit the XR region it aliases");
+    static constexpr unsigned long long SMEM = (unsigned long long)RAW_FLOATS * 4 + (unsigned long long)G * (XR_PLANE + KR_PLANE + CT_PLANE) * 8 + 16;
     static constexpr int CTAS = SMEM <= 75 * 1024 ? 3 : (SMEM <= 113 * 1024 ? 2 : 1);  // resident CTAs per SM (228 KB of shared memory)
     static_assert(HP <= 64 && WP <= 64, "padded input must fit the 64-point transform");
     static_assert(KH <= HP && KW <= WP && HO <= 64 && WO <= 64, "shape");
@@ -70,11 +71,11 @@ struct FCfg {
 
 struct FftBufs {
     const float *rawx, *rawk;  // landed planes of the group (dense)
-    float2 *XR, *KR;
-    float *out;  // output tile of the group (dense)
+    float2 *XR, *KR, *CT;
+    float *out;  // output tile of the group (dense); aliases XR
 };
 
-enum { FFT_PH_R = 0, FFT_PH_CX = 1, FFT_PH_CK = 2, FFT_PH_CI = 3, FFT_PH_O = 4, FFT_PHASES = 5 };
+enum { FFT_PH_R = 0, FFT_PH_O = 1, FFT_PHASES = 2 };
 
 HDN_HD int fft_task_half(int t) { return (t >> 5) & 1; }
 HDN_HD int fft_task_unit(int t) { return ((t >> 6) << 5) | (t & 31); }
@@ -96,9 +97,8 @@ HDN_HD bool fftc_load(int ph, const FftBufs &b, int unit, float (&re)[64], float
     if (ph == FFT_PH_R) {
         if (unit >= Cfg::R_UNITS) return false;
         const int p = unit / Cfg::R_UNITS_PLANE, j = unit - p * Cfg::R_UNITS_PLANE;
-        const bool ktype = j < Cfg::KH;
-        const int r1 = j;  // j < KH: (x_j, k_j);  else (x_j, x_{j + R_PAIRS})
-        const float *xrow = b.rawx + p * Cfg::XPL + fft_src_row<Cfg>(r1) * Cfg::WX;
+        const bool ktype = j < Cfg::KH;  // (x_j, k_j);  else (x_j, x_{j + R_PAIRS})
+        const float *xrow = b.rawx + p * Cfg::XPL + fft_src_row<Cfg>(j) * Cfg::WX;
 #pragma unroll
         for (int n = 0; n < 64; ++n) {
             int q = n - Cfg::PW;  // compile-time: replicate padding of the columns
@@ -110,9 +110,9 @@ HDN_HD bool fftc_load(int ph, const FftBufs &b, int unit, float (&re)[64], float
 #pragma unroll
             for (int n = 0; n < 64; ++n) im[n] = n < Cfg::KW ? krow[n] : 0.f;
         } else {
-            const int r2 = r1 + Cfg::R_PAIRS;
+            const int r2 = j + Cfg::R_PAIRS;
             const bool has2 = r2 < Cfg::HP;
-            const float *xrow2 = b.rawx + p * Cfg::XPL + fft_src_row<Cfg>(has2 ? r2 : r1) * Cfg::WX;
+            const float *xrow2 = b.rawx + p * Cfg::XPL + fft_src_row<Cfg>(has2 ? r2 : j) * Cfg::WX;
 #pragma unroll
             for (int n = 0; n < 64; ++n) {
                 int q = n - Cfg::PW;
@@ -122,55 +122,19 @@ HDN_HD bool fftc_load(int ph, const FftBufs &b, int unit, float (&re)[64], float
         }
         return true;
     }
-    if (ph == FFT_PH_O) {
-        if (unit >= Cfg::O_UNITS) return false;
-        const int m = unit / Cfg::HO, i = unit - m * Cfg::HO;
-        const float2 *rp = b.KR + (2 * m) * Cfg::KR_PLANE + i * Cfg::PITCH, *rq = rp + Cfg::KR_PLANE;
-        // stored rows are conj(c~) (slot 0 = (c~(0), -c~(32)), both real); build conj(Q), Q(f) = c~_p(f) + i*c~_q(f), Q(-f) by symmetry
-        {
-            const float2 a = rp[0], c = rq[0];
-            re[0] = a.x; im[0] = -c.x; re[32] = -a.y; im[32] = c.y;
-        }
-#pragma unroll
-        for (int f = 1; f < 32; ++f) {
-            const float2 a = rp[f], c = rq[f];
-            re[f] = a.x + c.y; im[f] = a.y - c.x;
-            re[64 - f] = a.x - c.y; im[64 - f] = -a.y - c.x;
-        }
-        return true;
+    if (unit >= Cfg::O_UNITS) return false;
+    const int m = unit / Cfg::HO, i = unit - m * Cfg::HO;
+    const float2 *rp = b.CT + (2 * m) * Cfg::CT_PLANE + i * Cfg::PITCH, *rq = rp + Cfg::CT_PLANE;
+    // stored rows are conj(c~) (slot 0 = (c~(0), -c~(32)), both real); build conj(Q), Q(f) = c~_p(f) + i*c~_q(f), Q(-f) by symmetry
+    {
+        const float2 a = rp[0], c = rq[0];
+        re[0] = a.x; im[0] = -c.x; re[32] = -a.y; im[32] = c.y;
     }
-    // column phases: unit = (plane, frequency column f)
-    if (unit >= Cfg::C_UNITS) return false;
-    const int p = unit >> 5, f = unit & 31;
-    if (ph == FFT_PH_CK) {
-        const float2 *kc = b.KR + p * Cfg::KR_PLANE + f;
 #pragma unroll
-        for (int r = 0; r < 64; ++r) {
-            if (r < Cfg::KH) {
-                const float2 t = kc[r * Cfg::PITCH];
-                re[r] = t.x; im[r] = t.y;
-            } else {
-                re[r] = im[r] = 0.f;
-            }
-        }
-    } else if (ph == FFT_PH_CX) {  // row spectra: HP rows, the rest is zero padding (never read)
-        const float2 *xc = b.XR + p * Cfg::XR_PLANE + f;
-#pragma unroll
-        for (int r = 0; r < 64; ++r) {
-            if (r < Cfg::HP) {
-                const float2 t = xc[r * Cfg::PITCH];
-                re[r] = t.x; im[r] = t.y;
-            } else {
-                re[r] = im[r] = 0.f;
-            }
-        }
-    } else {  // CI: conj(P), all 64 rows
-        const float2 *xc = b.XR + p * Cfg::XR_PLANE + f;
-#pragma unroll
-        for (int r = 0; r < 64; ++r) {
-            const float2 t = xc[r * Cfg::PITCH];
-            re[r] = t.x; im[r] = t.y;
-        }
+    for (int f = 1; f < 32; ++f) {
+        const float2 a = rp[f], c = rq[f];
+        re[f] = a.x + c.y; im[f] = a.y - c.x;
+        re[64 - f] = a.x - c.y; im[64 - f] = -a.y - c.x;
     }
     return true;
 }
@@ -182,10 +146,9 @@ HDN_HD void fftc_store_R(const FftBufs &b, int unit, const float (&re)[64], cons
     using namespace fft;
     const int p = unit / Cfg::R_UNITS_PLANE, j = unit - p * Cfg::R_UNITS_PLANE;
     const bool ktype = j < Cfg::KH;
-    const int r1 = j;
-    float2 *d1 = b.XR + p * Cfg::XR_PLANE + r1 * Cfg::PITCH;
+    float2 *d1 = b.XR + p * Cfg::XR_PLANE + j * Cfg::PITCH;
     float2 *d2 = ktype ? b.KR + p * Cfg::KR_PLANE + j * Cfg::PITCH : d1 + Cfg::R_PAIRS * Cfg::PITCH;
-    const bool has2 = ktype || r1 + Cfg::R_PAIRS < Cfg::HP;
+    const bool has2 = ktype || j + Cfg::R_PAIRS < Cfg::HP;
     if (H == 0) {
         d1[0] = float2{2.f * re[HPOS(0)], 2.f * re[HPOS(32)]};
         if (has2) d2[0] = float2{2.f * im[HPOS(0)], 2.f * im[HPOS(32)]};
@@ -206,64 +169,70 @@ HDN_HD void fftc_store(int ph, const FftBufs &b, int unit, int h, const float (&
         else fftc_store_R<Cfg, 1>(b, unit, re, im);
         return;
     }
-    if (ph == FFT_PH_O) {
-        const int m = unit / Cfg::HO, i = unit - m * Cfg::HO;
-        constexpr float SCALE = 1.0f / 16384.0f;
-        float *op = b.out + (2 * m) * Cfg::OPL + i * Cfg::WO + h, *oq = op + Cfg::OPL;
+    const int m = unit / Cfg::HO, i = unit - m * Cfg::HO;
+    constexpr float SCALE = 1.0f / 256.0f;
+    float *op = b.out + (2 * m) * Cfg::OPL + i * Cfg::WO + h, *oq = op + Cfg::OPL;
 #pragma unroll
-        for (int mm = 0; 2 * mm < Cfg::WO; ++mm) {
-            if (2 * mm + 1 < Cfg::WO || h == 0) {
-                op[2 * mm] = re[POS32(mm)] * SCALE;
-                oq[2 * mm] = im[POS32(mm)] * -SCALE;
-            }
-        }
-        return;
-    }
-    const int p = unit >> 5, f = unit & 31;
-    float2 *xc = b.XR + p * Cfg::XR_PLANE + f + h * Cfg::PITCH;  // row 2m + h of column f
-    if (ph == FFT_PH_CX) {
-#pragma unroll
-        for (int mm = 0; mm < 32; ++mm) xc[2 * mm * Cfg::PITCH] = float2{re[POS32(mm)], im[POS32(mm)]};
-    } else if (ph == FFT_PH_CI) {
-        float2 *kc = b.KR + p * Cfg::KR_PLANE + f + h * Cfg::PITCH;
-#pragma unroll
-        for (int mm = 0; 2 * mm < Cfg::HO; ++mm)
-            if (2 * mm + 1 < Cfg::HO || h == 0) kc[2 * mm * Cfg::PITCH] = float2{re[POS32(mm)], im[POS32(mm)]};
-    } else if (f != 0) {  // CK: conj(P) = conj(X^) * K^ over X^
-#pragma unroll
-        for (int mm = 0; mm < 32; ++mm) {
-            const float2 x = xc[2 * mm * Cfg::PITCH];
-            const float kr = re[POS32(mm)], ki = im[POS32(mm)];
-            xc[2 * mm * Cfg::PITCH] = float2{x.x * kr + x.y * ki, x.x * ki - x.y * kr};
-        }
-    } else {
-        // CK, column 0 = the packed pair of real-row columns (0 and 32): W = V0 + i*V32 with V0, V32 Hermitian in fr.  For (fr, -fr):
-        //   4*X0 = A + conj B,  4*X32 = (A - conj B)/i   (A = Wx(fr), B = Wx(-fr));  likewise K from C = Wk(fr), D = Wk(-fr)
-        //   Q(fr) = P0 + i*P32,  Q(-fr) = conj P0 + i*conj P32,  P = X * conj K;  conj(Q) is stored; 1/4 restores the scale.
-        // One lane per plane runs this, so it is a ROLLED loop over shared memory (K^ parked in the spare pad column 32 of XR) to
-        // keep it out of the instruction-cache footprint; fr and -fr have the parity of h, i.e. both were written by this thread.
-        float2 *kp = xc + 32;
-#pragma unroll
-        for (int mm = 0; mm < 32; ++mm) kp[2 * mm * Cfg::PITCH] = float2{re[POS32(mm)], im[POS32(mm)]};
-        float2 *c0 = b.XR + p * Cfg::XR_PLANE;
-#pragma unroll 1
-        for (int fr = h; fr <= 32; fr += 2) {
-            const int mf = (64 - fr) & 63;
-            const float2 A = c0[fr * Cfg::PITCH], B = c0[mf * Cfg::PITCH], Cc = c0[fr * Cfg::PITCH + 32], D = c0[mf * Cfg::PITCH + 32];
-            const float ur = A.x + B.x, ui = A.y - B.y, vr = A.y + B.y, vi = B.x - A.x;
-            const float sr = Cc.x + D.x, si = Cc.y - D.y, tr = Cc.y + D.y, ti = D.x - Cc.x;
-            const float p0r = 0.25f * (ur * sr + ui * si), p0i = 0.25f * (ui * sr - ur * si);
-            const float p1r = 0.25f * (vr * tr + vi * ti), p1i = 0.25f * (vi * tr - vr * ti);
-            c0[fr * Cfg::PITCH] = float2{p0r - p1i, -p0i - p1r};
-            if (mf != fr) c0[mf * Cfg::PITCH] = float2{p0r + p1i, p0i - p1r};
+    for (int mm = 0; 2 * mm < Cfg::WO; ++mm) {
+        if (2 * mm + 1 < Cfg::WO || h == 0) {
+            op[2 * mm] = re[POS32(mm)] * SCALE;
+            oq[2 * mm] = im[POS32(mm)] * -SCALE;
         }
     }
 }
 
-// number of tasks of a phase
 template <class Cfg>
 HDN_HD int fftc_tasks(int ph) {
-    return ph == FFT_PH_R ? Cfg::R_TASKS : (ph == FFT_PH_O ? Cfg::O_TASKS : Cfg::C_TASKS);
+    return ph == FFT_PH_R ? Cfg::R_TASKS : Cfg::O_TASKS;
+}
+
+// ---- column stage ----------------------------------------------------------------------------------------------------------
+// conj c~(i,f) = sum_u conj X'(i+u,f) * K'(u,f)  for the SEG output rows of the task's segment; NTAP taps per block, the
+// SEG + NTAP - 1 input rows of a block are held in registers (one shared load feeds ~NTAP complex MACs).  Slot 0 (f == 0) packs
+// two REAL columns (f = 0 in .x, f = 32 in .y): its MAC is component-wise, (x.x*k.x, -x.y*k.y), obtained branch-free by
+// editing the tap.
+template <class Cfg, int NTAP>
+HDN_HD void fftc_col_block(const float2 *xc, const float2 *kc, int u0, bool f0, float (&ar)[Cfg::SEG], float (&ai)[Cfg::SEG]) {
+    float wr[Cfg::SEG + NTAP - 1], wi[Cfg::SEG + NTAP - 1];
+#pragma unroll
+    for (int d = 0; d < Cfg::SEG + NTAP - 1; ++d) {
+        const float2 t = xc[(u0 + d) * Cfg::PITCH];
+        wr[d] = t.x; wi[d] = t.y;
+    }
+#pragma unroll
+    for (int tt = 0; tt < NTAP; ++tt) {
+        const float2 k = kc[(u0 + tt) * Cfg::PITCH];
+        const float q = f0 ? 0.f : k.y, ns = f0 ? -k.y : -k.x;
+#pragma unroll
+        for (int i = 0; i < Cfg::SEG; ++i) {
+            ar[i] = wr[i + tt] * k.x + ar[i];
+            ar[i] = wi[i + tt] * q + ar[i];
+            ai[i] = wr[i + tt] * q + ai[i];
+            ai[i] = wi[i + tt] * ns + ai[i];
+        }
+    }
+}
+
+template <class Cfg>
+HDN_HD void fftc_col(const FftBufs &b, int task) {
+    const int f = task & 31, ws = task >> 5;
+    const int p = ws / Cfg::NSEG, i0 = (ws - p * Cfg::NSEG) * Cfg::SEG;
+    const float2 *xc = b.XR + p * Cfg::XR_PLANE + i0 * Cfg::PITCH + f;
+    const float2 *kc = b.KR + p * Cfg::KR_PLANE + f;
+    const bool f0 = f == 0;
+    float ar[Cfg::SEG], ai[Cfg::SEG];
+#pragma unroll
+    for (int i = 0; i < Cfg::SEG; ++i) ar[i] = ai[i] = 0.f;
+    constexpr int FULL = Cfg::KH / Cfg::TB * Cfg::TB, REM = Cfg::KH - FULL;
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+    for (int u0 = 0; u0 < FULL; u0 += Cfg::TB) fftc_col_block<Cfg, Cfg::TB>(xc, kc, u0, f0, ar, ai);
+    if (REM > 0) fftc_col_block<Cfg, (REM > 0 ? REM : 1)>(xc, kc, FULL, f0, ar, ai);
+    float2 *ct = b.CT + p * Cfg::CT_PLANE + i0 * Cfg::PITCH + f;
+#pragma unroll
+    for (int i = 0; i < Cfg::SEG; ++i)
+        if (i0 + i < Cfg::HO) ct[i * Cfg::PITCH] = float2{ar[i], ai[i]};
 }
 
 }  // namespace hdn

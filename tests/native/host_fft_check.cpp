@@ -1,5 +1,5 @@
 // host_fft_check.cpp -- CPU check of the FFT correlation arithmetic (hdn_b200/csrc/xcorr_fft.cuh, fft64.cuh).
-// Runs the kernel's five phases task by task on one group of planes -- in the order the kernel's barriers impose, once with the
+// Runs the kernel's three phases (row FFTs, column correlation, output FFTs) task by task on one group of planes -- in the order the kernel's barriers impose, once with the
 // tasks of a phase in ascending and once in descending order (a result that depended on the order inside a phase would be a
 // race on the device) -- and compares with a direct double-precision correlation.  Test infrastructure only: built and run
 // by tests/test_fft_host.py with g++; prints "<config> max_err <e> max_ref <m>" per shape, exit code 1 on failure.
@@ -19,32 +19,27 @@ struct Regs {
 
 template <class Cfg>
 static void run_group(const std::vector<float> &raw, std::vector<float> &out, bool reverse) {
-    std::vector<float2> XR(Cfg::G * Cfg::XR_PLANE), KR(Cfg::G * Cfg::KR_PLANE);
+    std::vector<float2> XR(Cfg::G * Cfg::XR_PLANE), KR(Cfg::G * Cfg::KR_PLANE), CT(Cfg::G * Cfg::CT_PLANE);
     for (auto &v : XR) v = float2{NAN, NAN};  // anything read before it is written poisons the result
     for (auto &v : KR) v = float2{NAN, NAN};
-    FftBufs b{raw.data(), raw.data() + Cfg::G * Cfg::XPL, XR.data(), KR.data(), out.data()};
-    for (int ph = 0; ph < FFT_PHASES; ++ph) {
+    for (auto &v : CT) v = float2{NAN, NAN};
+    // the kernel stages the output tile over XR; here it is a separate array so that a phase-O read of XR would show up as NaN
+    FftBufs b{raw.data(), raw.data() + Cfg::G * Cfg::XPL, XR.data(), KR.data(), CT.data(), out.data()};
+    auto order = [&](int s, int n) { return reverse ? n - 1 - s : s; };
+    auto fft_phase = [&](int ph) {
         const int ntask = fftc_tasks<Cfg>(ph);
-        auto finish = [&](int t, Regs &r) {
-            if (!r.active) return;
-            const int h = fft_task_half(t), unit = fft_task_unit(t);
+        for (int s = 0; s < ntask; ++s) {
+            const int t = order(s, ntask), h = fft_task_half(t), unit = fft_task_unit(t);
+            Regs r;
+            if (!fftc_load<Cfg>(ph, b, unit, r.re, r.im)) continue;
             fft::half_butterfly(h, r.re, r.im);
             fft::fft32_fwd(r.re, r.im);
             fftc_store<Cfg>(ph, b, unit, h, r.re, r.im);
-        };
-        if (ph == FFT_PH_CX) {  // the kernel has a barrier between the loads and the stores of this phase
-            std::vector<Regs> regs(ntask);
-            for (int t = 0; t < ntask; ++t) regs[t].active = fftc_load<Cfg>(ph, b, fft_task_unit(t), regs[t].re, regs[t].im);
-            for (int t = 0; t < ntask; ++t) finish(t, regs[t]);
-        } else {
-            for (int s = 0; s < ntask; ++s) {
-                const int t = reverse ? ntask - 1 - s : s;
-                Regs r;
-                r.active = fftc_load<Cfg>(ph, b, fft_task_unit(t), r.re, r.im);
-                finish(t, r);
-            }
         }
-    }
+    };
+    fft_phase(FFT_PH_R);
+    for (int s = 0; s < Cfg::COL_TASKS; ++s) fftc_col<Cfg>(b, order(s, Cfg::COL_TASKS));
+    fft_phase(FFT_PH_O);
 }
 
 template <class Cfg>
