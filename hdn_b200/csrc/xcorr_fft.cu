@@ -112,15 +112,19 @@ static int launch_fft(const XProblems &P, int n, int B, int C, long long kbs, cu
 }
 
 //                     KH  KW  HX  WX  circ  G   NT
-#ifndef HDN_FFT_G
-#define HDN_FFT_G 2
-#endif
+// threads per CTA (tunable at build time for A/B runs): the column stage splits a plane's output rows over NT / 64 warps
 #ifndef HDN_FFT_NT1
-#define HDN_FFT_NT1 (96 * HDN_FFT_G)
+#define HDN_FFT_NT1 192
 #endif
-using F256 = FCfg<29, 29, 61, 61, false, HDN_FFT_G, HDN_FFT_NT1>;       // 256/512 crops, similarity branch (phase R = one round of 6 warps)
-using F256Lp = FCfg<29, 29, 29, 29, true, HDN_FFT_G, 64 * HDN_FFT_G>;   // 256/512 crops, log-polar branch (INSTANCE_SIZE = 512)
-using FWin15 = FCfg<15, 15, 39, 39, false, HDN_FFT_G, 64 * HDN_FFT_G>;  // 15x15 large-displacement window
+#ifndef HDN_FFT_NT2
+#define HDN_FFT_NT2 128
+#endif
+#ifndef HDN_FFT_NT3
+#define HDN_FFT_NT3 128
+#endif
+using F256 = FCfg<29, 29, 61, 61, false, 2, HDN_FFT_NT1>;    // 256/512 crops, similarity branch
+using F256Lp = FCfg<29, 29, 29, 29, true, 2, HDN_FFT_NT2>;   // 256/512 crops, log-polar branch (INSTANCE_SIZE = 512)
+using FWin15 = FCfg<15, 15, 39, 39, false, 2, HDN_FFT_NT3>;  // 15x15 large-displacement window
 
 #define HDN_FFT_SHAPES(X) X(F256) X(F256Lp) X(FWin15)
 

@@ -33,6 +33,10 @@ struct float2 {
 };
 #endif
 
+#ifndef HDN_FFT_TB
+#define HDN_FFT_TB 8  // taps per register-window block of the column stage (build-time tunable)
+#endif
+
 namespace hdn {
 
 template <int KH_, int KW_, int HX_, int WX_, bool CIRC_, int G_, int NT_>
@@ -45,7 +49,8 @@ struct FCfg {
     static constexpr int XPL = HX * WX, KPL = KH * KW, OPL = HO * WO;
     static constexpr int PITCH = 33;
     // column stage: a warp = (plane, segment of SEG consecutive output rows), lane = frequency column
-    static constexpr int NSEG = NT / (32 * G) > 0 ? NT / (32 * G) : 1, SEG = (HO + NSEG - 1) / NSEG, TB = 8;
+    static constexpr int NSEG = NT / (32 * G) > 0 ? NT / (32 * G) : 1, SEG = (HO + NSEG - 1) / NSEG;
+    static constexpr int TB = HDN_FFT_TB;  // taps per register-window block of the column stage
     static constexpr int XR_ROWS = NSEG * SEG + KH - 1 > HP ? NSEG * SEG + KH - 1 : HP;  // rows past HP are read (never used) by the last segment
     static constexpr int XR_PLANE = XR_ROWS * PITCH, KR_PLANE = KH * PITCH, CT_PLANE = HO * PITCH;  // complex elements
     // A group's x / k planes are fetched as 16-byte-aligned windows (TMA bulk copies need 16-byte addresses and sizes): a group of 2

@@ -59,8 +59,8 @@ XCORR_ALGOS = {"auto": 0, "direct": 1, "fft": 2}
 
 
 def set_xcorr_algo(name):
-    """'auto' (default): the 29x29-template shapes run the 64x64 FFT correlation kernel (xcorr_fft.cu); 'fft': every shape that has
-    an FFT kernel does (also the 15x15 window); 'direct': every shape runs the direct register-tiled sum (xcorr.cu).  Process-wide."""
+    """'auto' (default) / 'fft': the 29x29- and 15x15-template shapes run the transform-domain kernel (xcorr_fft.cu);
+    'direct': every shape runs the direct register-tiled sum (xcorr.cu).  Process-wide."""
     _lib.check(_lib.lib().hdn_xcorr_set_algo(XCORR_ALGOS[name]), "hdn_xcorr_set_algo")
 
 

@@ -64,8 +64,8 @@ int hdn_xcorr_dw_multi_f32(int n, const float *const *x_host, const float *const
                            int Wx, int Hk, int Wk, int circular, int64_t k_batch_stride, hdn_stream_t stream);
 
 /* Algorithm of K1/K2 for the shapes that have both kernels (29x29 and 15x15 templates, where the direct sum is FMA-bound at
- * 30-140 flop/B): HDN_XCORR_DIRECT = the direct register-tiled sum, HDN_XCORR_FFT = 64x64 FFT correlation wherever a kernel
- * exists, HDN_XCORR_AUTO (default) = whichever measured faster on a B200 (FFT for the 29x29 templates, direct for 15x15).
+ * 30-140 flop/B): HDN_XCORR_DIRECT = the direct register-tiled sum; HDN_XCORR_FFT / HDN_XCORR_AUTO (default) = the transform-domain
+ * kernel (row FFTs + per-frequency column correlation + inverse row FFTs, xcorr_fft.cu), faster on a B200 for all of them.
  * Process-wide; both give the reference's result to ~3e-7 of max|out|.  hdn_xcorr_uses_fft: 1 if that shape now takes the FFT kernel. */
 enum hdn_xcorr_algo { HDN_XCORR_AUTO = 0, HDN_XCORR_DIRECT = 1, HDN_XCORR_FFT = 2 };
 int hdn_xcorr_set_algo(int algo);

@@ -40,12 +40,12 @@ def uses_fft(C, Hx, Wx, Hk, Wk, circ):
 
 def test_fft_kernel_is_the_default_for_the_fma_bound_shapes():
     ops().set_xcorr_algo("auto")
-    for Hx, Hk, circ in ((61, 29, 0), (29, 29, 1)):
+    for Hx, Hk, circ in ((61, 29, 0), (29, 29, 1), (39, 15, 0)):
         assert uses_fft(256, Hx, Hx, Hk, Hk, circ)
-    for Hx, Hk, circ in ((29, 5, 0), (13, 13, 1), (39, 15, 0)):
-        assert not uses_fft(256, Hx, Hx, Hk, Hk, circ)  # HBM-bound / tiny / measured slower: direct sum
-    ops().set_xcorr_algo("fft")
-    assert uses_fft(256, 39, 39, 15, 15, 0)
+    for Hx, Hk, circ in ((29, 5, 0), (13, 13, 1)):
+        assert not uses_fft(256, Hx, Hx, Hk, Hk, circ)  # HBM-bound / tiny: direct sum
+    ops().set_xcorr_algo("direct")
+    assert not uses_fft(256, 61, 61, 29, 29, 0)
     ops().set_xcorr_algo("auto")
 
 
