@@ -39,7 +39,7 @@ struct float2 {
 
 namespace hdn {
 
-template <int KH_, int KW_, int HX_, int WX_, bool CIRC_, int G_, int NT_>
+template <int KH_, int KW_, int HX_, int WX_, bool CIRC_, int G_, int NT_, int TB_ = HDN_FFT_TB>
 struct FCfg {
     static constexpr int KH = KH_, KW = KW_, HX = HX_, WX = WX_, G = G_, NT = NT_;
     static constexpr bool CIRC = CIRC_;
@@ -50,7 +50,7 @@ struct FCfg {
     static constexpr int PITCH = 33;
     // column stage: a warp = (plane, segment of SEG consecutive output rows), lane = frequency column
     static constexpr int NSEG = NT / (32 * G) > 0 ? NT / (32 * G) : 1, SEG = (HO + NSEG - 1) / NSEG;
-    static constexpr int TB = HDN_FFT_TB;  // taps per register-window block of the column stage
+    static constexpr int TB = TB_;  // taps per register-window block of the column stage
     static constexpr int XR_ROWS = NSEG * SEG + KH - 1 > HP ? NSEG * SEG + KH - 1 : HP;  // rows past HP are read (never used) by the last segment
     static constexpr int XR_PLANE = XR_ROWS * PITCH, KR_PLANE = KH * PITCH, CT_PLANE = HO * PITCH;  // complex elements
     // A group's x / k planes are fetched as 16-byte-aligned windows (TMA bulk copies need 16-byte addresses and sizes): a group of 2

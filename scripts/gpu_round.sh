@@ -18,4 +18,8 @@ timeout 300 python bench.py --no-cpu --no-e2e --xcorr-algo direct > gpurun_out/b
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_gemm -c 1 -s 2 -o gpurun_out/prof_conv_gemm -f \
     python scripts/tune/conv_one.py > gpurun_out/prof_conv.log 2>&1
 timeout 300 python -m hdn_b200.runner --sequences 2 --frames 40 > gpurun_out/runner.json 2> gpurun_out/runner.err
+timeout 300 python scripts/tune/tracker_profile.py > gpurun_out/tracker_profile.txt 2>&1
+timeout 300 python scripts/tune/backbone_profile.py > gpurun_out/backbone_profile.txt 2>&1
+HDN_B200_TCGEN05=0 timeout 300 python scripts/tune/backbone_profile.py > gpurun_out/backbone_profile_cudnn.txt 2>&1
+timeout 300 python scripts/tune/backbone_bench.py > gpurun_out/backbone_bench.txt 2>&1
 tail -3 gpurun_out/pytest_gpu.log; cat gpurun_out/bench.json
