@@ -2,7 +2,7 @@
 
 cuDNN has no fast fp32 kernel for the stride-8 backbone's DILATED 3x3 convolutions at tracking batch sizes: with TF32
 off it falls back to `conv2d_grouped_direct_kernel`, 2.7 ms for one 512->512 31x31 dilation-4 layer on a B200
-(1.7 TFLOP/s) -- three such layers are 61 % of the whole ResNet-50 forward (profiles/r01_backbone_profile.txt).
+(1.7 TFLOP/s) -- three such layers were 61 % of the whole ResNet-50 forward (13.6 ms at batch 1; profiles/README.md).
 
 `dilated_conv3x3` computes the same convolution as 9 plain fp32 GEMMs (cuBLAS, TF32 off): with the input zero-padded
 by the dilation d and each plane flattened, tap (ky,kx) reads the contiguous slice starting at ky*d*Wp + kx*d, so
