@@ -57,6 +57,19 @@ def test_argument_validation_without_device(lib):
         _lib.check(-2, "x")
 
 
+def test_xcorr_algorithm_selector(lib):
+    """AUTO / FFT: the 29x29- and 15x15-template shapes take the transform-domain kernel; DIRECT: none does; bad values are rejected."""
+    shapes = ((61, 29, 0), (29, 29, 1), (39, 15, 0))
+    for algo, expect in ((0, 1), (2, 1), (1, 0), (0, 1)):
+        assert lib.hdn_xcorr_set_algo(algo) == 0
+        for Hx, Hk, circ in shapes:
+            assert lib.hdn_xcorr_uses_fft(256, Hx, Hx, Hk, Hk, circ, 256 * Hk * Hk) == expect
+            assert lib.hdn_xcorr_uses_fft(256, Hx, Hx, Hk, Hk, circ, 0) == expect          # shared template
+    assert lib.hdn_xcorr_uses_fft(256, 29, 29, 5, 5, 0, 256 * 25) == 0                     # HBM-bound native shape: direct sum
+    assert lib.hdn_xcorr_uses_fft(6, 61, 61, 29, 29, 0, 6 * 841) == 0                      # C % 4 != 0: planes would straddle a window
+    assert lib.hdn_xcorr_set_algo(7) == -4
+
+
 def test_ops_reject_cpu_tensors():
     import torch
     from hdn_b200 import ops
