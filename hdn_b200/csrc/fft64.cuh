@@ -1,17 +1,16 @@
-// fft64.cuh -- a 64-point complex FFT held entirely in one thread's registers (radix 8 x 8, fully unrolled, twiddles are
-// compile-time immediates), the building block of the FFT correlation kernels (xcorr_fft.cu).
+// fft64.cuh -- a 64-point complex FFT split over TWO threads and held entirely in their registers, the building block of the
+// transform-domain correlation kernels (xcorr_fft.cu).
 //
-// Host-compilable (tests/host_fft_check.cpp builds it with g++ to check the arithmetic against a direct correlation):
-// everything here is plain C++ on float arrays with compile-time indices.
+//   X[f] = sum_n a[n] * exp(-2*pi*i * f*n / 64)         (forward, unnormalised; inverses are taken as conj(FFT(conj .)))
 //
-//   X[f] = sum_n v[n] * exp(S * 2*pi*i * f*n / 64)        S = -1 forward, +1 inverse (unnormalised)
+// Decimation in frequency: half h in {0,1} owns the outputs X[2m + h] = FFT32(s)[m] with
+//   s[n] = a[n] + a[n+32]  (h = 0),     s[n] = (a[n] - a[n+32]) * W64^n  (h = 1),      n < 32.
+// The caller forms a[n] +- a[n+32] while loading (one FFMA per value with the sign as a warp-uniform operand), applies
+// half_twiddle() when h = 1 and runs fft32_fwd(): a radix-4 x 8 FFT, fully unrolled, twiddles are compile-time immediates
+// (n = 8a + b, m = c + 4d:  W32^(mn) = W4^(ac) * W32^(bc) * W8^(bd)).  Y[m] is left at POS32(m) = 8*(m%4) + m/4, i.e.
+// X[f] of the owning half at HPOS(f).
 //
-// With n = 8a + b and f = c + 8d:   exp(..fn/64) = W8^(ac) * W64^(bc) * W8^(bd).
-//   fft64_nr: natural-order input (v[n]), output X[f] left at position POS(f) = 8*(f%8) + f/8   ("digit reversed")
-//   fft64_rn: input X[f] at position POS(f), natural-order output -- the transposed flow graph; a forward nr followed by
-//             an inverse rn therefore needs no reordering in between (point-wise products are done in place).
-// NZ  = number of leading non-zero inputs of fft64_nr (the rest are never read: zero padding is pruned);
-// REAL = the imaginary parts of the inputs are zero (never read).
+// Host-compilable (tests/native/host_fft_check.cpp builds it with g++): plain C++ on float arrays with compile-time indices.
 #pragma once
 
 #if defined(__CUDACC__)
@@ -22,8 +21,6 @@
 
 namespace hdn {
 namespace fft {
-
-HDN_HD constexpr int POS(int f) { return 8 * (f & 7) + (f >> 3); }
 
 // cos(2*pi*k/64), k = 0..16 (quarter wave); everything else by symmetry, folded at compile time after unrolling
 HDN_HD constexpr float cos64(int k) {
@@ -98,120 +95,21 @@ HDN_HD void dft8(float (&r)[8], float (&i)[8]) {
     r[7] = c1r + S * c3i; i[7] = c1i - S * c3r;
 }
 
-template <int S, int B, int C = 0>
-struct TwiddleRow {  // (r[c], i[c]) *= W64^(S*B*c), c = C..7
-    static HDN_HD void run(float (&r)[8], float (&i)[8]) {
-        twiddle<S, B * C>(r[C], i[C]);
-        TwiddleRow<S, B, C + 1>::run(r, i);
-    }
-};
-template <int S, int B>
-struct TwiddleRow<S, B, 8> {
-    static HDN_HD void run(float (&)[8], float (&)[8]) {}
-};
-
-template <int S, int NZ, bool REAL, int B = 0>
-struct Pass1 {  // nr, step 1+2: for each b, DFT8 over a (stride-8 inputs), twiddle by W64^(bc), result at [8c + b]
-    static HDN_HD void run(float (&re)[64], float (&im)[64]) {
-        constexpr int NA = (NZ - B + 7) / 8;  // inputs 8a + B < NZ  <=>  a < NA
-        float r[8], i[8];
-#pragma unroll
-        for (int a = 0; a < 8; ++a) {
-            r[a] = a < NA ? re[8 * a + B] : 0.f;
-            i[a] = (a < NA && !REAL) ? im[8 * a + B] : 0.f;
-        }
-        dft8<S, (NA <= 4 ? 4 : 8), REAL>(r, i);
-        TwiddleRow<S, B>::run(r, i);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            re[8 * c + B] = r[c];
-            im[8 * c + B] = i[c];
-        }
-        Pass1<S, NZ, REAL, B + 1>::run(re, im);
-    }
-};
-template <int S, int NZ, bool REAL>
-struct Pass1<S, NZ, REAL, 8> {
-    static HDN_HD void run(float (&)[64], float (&)[64]) {}
-};
-
-// natural-order input -> X[f] at POS(f)
-template <int S, int NZ = 64, bool REAL = false>
-HDN_HD void fft64_nr(float (&re)[64], float (&im)[64]) {
-    Pass1<S, NZ, REAL>::run(re, im);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {  // step 3: DFT8 over b of the contiguous block [8c + b] -> [8c + d] = X[c + 8d]
-        float r[8], i[8];
-#pragma unroll
-        for (int b = 0; b < 8; ++b) { r[b] = re[8 * c + b]; i[b] = im[8 * c + b]; }
-        dft8<S>(r, i);
-#pragma unroll
-        for (int d = 0; d < 8; ++d) { re[8 * c + d] = r[d]; im[8 * c + d] = i[d]; }
-    }
-}
-
-template <int S, int C = 0>
-struct PassT {  // rn, step 1'+2': for each c, DFT8 over d of the block [8c + d], twiddle by W64^(bc), result at [8c + b]
-    static HDN_HD void run(float (&re)[64], float (&im)[64]) {
-        float r[8], i[8];
-#pragma unroll
-        for (int d = 0; d < 8; ++d) { r[d] = re[8 * C + d]; i[d] = im[8 * C + d]; }
-        dft8<S>(r, i);
-        TwiddleRow<S, C>::run(r, i);  // index here is b; the factor W64^(b*C) is symmetric in (b, c)
-#pragma unroll
-        for (int b = 0; b < 8; ++b) { re[8 * C + b] = r[b]; im[8 * C + b] = i[b]; }
-        PassT<S, C + 1>::run(re, im);
-    }
-};
-template <int S>
-struct PassT<S, 8> {
-    static HDN_HD void run(float (&)[64], float (&)[64]) {}
-};
-
-// X[f] at POS(f) -> natural-order output x[n] (outputs the caller never reads are dead code for the compiler)
-template <int S>
-HDN_HD void fft64_rn(float (&re)[64], float (&im)[64]) {
-    PassT<S>::run(re, im);
-#pragma unroll
-    for (int b = 0; b < 8; ++b) {  // step 3': DFT8 over c (stride 8) -> x[8a + b]
-        float r[8], i[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) { r[c] = re[8 * c + b]; i[c] = im[8 * c + b]; }
-        dft8<S>(r, i);
-#pragma unroll
-        for (int a = 0; a < 8; ++a) { re[8 * a + b] = r[a]; im[8 * a + b] = i[a]; }
-    }
-}
-
-// ---- 64-point FFT split over two threads (decimation in frequency) ---------------------------------------------------------
-// Half h in {0,1} of X = FFT64(a), S = -1:   X[2m + h] = FFT32( s )[m],   s[n] = a[n] + a[n+32]            (h = 0)
-//                                                                          s[n] = (a[n] - a[n+32]) * W64^n  (h = 1)
-// Both halves need all 64 inputs; each keeps 32 outputs.  half_butterfly leaves s in (re, im)[0..31].
+// (s[N]) *= W64^(-N), N = 1..31: the h = 1 half's twiddles
 template <int N = 1>
-struct HalfTw {  // (re[N], im[N]) = (d[N]) * W64^(-N), N = 1..31
-    static HDN_HD void run(float (&re)[64], float (&im)[64]) {
+struct HalfTw {
+    static HDN_HD void run(float (&re)[32], float (&im)[32]) {
         twiddle<-1, N>(re[N], im[N]);
         HalfTw<N + 1>::run(re, im);
     }
 };
 template <>
 struct HalfTw<32> {
-    static HDN_HD void run(float (&)[64], float (&)[64]) {}
+    static HDN_HD void run(float (&)[32], float (&)[32]) {}
 };
+HDN_HD void half_twiddle(float (&re)[32], float (&im)[32]) { HalfTw<>::run(re, im); }
 
-HDN_HD void half_butterfly(int h, float (&re)[64], float (&im)[64]) {
-    if (h == 0) {
-#pragma unroll
-        for (int n = 0; n < 32; ++n) { re[n] += re[n + 32]; im[n] += im[n + 32]; }
-    } else {
-#pragma unroll
-        for (int n = 0; n < 32; ++n) { re[n] -= re[n + 32]; im[n] -= im[n + 32]; }
-        HalfTw<>::run(re, im);
-    }
-}
-
-// 32-point forward FFT on (re, im)[0..31], natural order in, Y[m] left at POS32(m) = 8*(m%4) + m/4.
-// n = 8a + b (a < 4, b < 8), m = c + 4d (c < 4, d < 8):  W32^(mn) = W4^(ac) * W32^(bc) * W8^(bd).
+// 32-point forward FFT, natural order in, Y[m] left at POS32(m).
 HDN_HD constexpr int POS32(int m) { return 8 * (m & 3) + (m >> 2); }
 
 HDN_HD void dft4_fwd(float (&r)[4], float (&i)[4]) {  // W4 = -i
@@ -225,7 +123,7 @@ HDN_HD void dft4_fwd(float (&r)[4], float (&i)[4]) {  // W4 = -i
 
 template <int B = 0>
 struct Pass32 {  // for each b: DFT4 over a (stride 8), twiddle by W32^(bc) = W64^(2bc), result at [8c + b]
-    static HDN_HD void run(float (&re)[64], float (&im)[64]) {
+    static HDN_HD void run(float (&re)[32], float (&im)[32]) {
         float r[4], i[4];
 #pragma unroll
         for (int a = 0; a < 4; ++a) { r[a] = re[8 * a + B]; i[a] = im[8 * a + B]; }
@@ -240,10 +138,10 @@ struct Pass32 {  // for each b: DFT4 over a (stride 8), twiddle by W32^(bc) = W6
 };
 template <>
 struct Pass32<8> {
-    static HDN_HD void run(float (&)[64], float (&)[64]) {}
+    static HDN_HD void run(float (&)[32], float (&)[32]) {}
 };
 
-HDN_HD void fft32_fwd(float (&re)[64], float (&im)[64]) {
+HDN_HD void fft32_fwd(float (&re)[32], float (&im)[32]) {
     Pass32<>::run(re, im);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {  // DFT8 over b of the block [8c + b] -> [8c + d] = Y[c + 4d]
@@ -256,7 +154,7 @@ HDN_HD void fft32_fwd(float (&re)[64], float (&im)[64]) {
     }
 }
 
-// X[f] of the half that owns parity f % 2, after half_butterfly + fft32_fwd:  X[f] = Y[f / 2]
+// X[f] of the half that owns parity f % 2:  X[f] = Y[f / 2]
 HDN_HD constexpr int HPOS(int f) { return POS32(f >> 1); }
 
 }  // namespace fft

@@ -69,9 +69,9 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::CTAS)
             for (int t0 = 0; t0 < ntask; t0 += Cfg::NT) {
                 const int t = t0 + tid;
                 const int h = fft_task_half(t), unit = fft_task_unit(t);
-                float re[64], im[64];
-                if (t < ntask && fftc_load<Cfg>(ph, bufs, unit, re, im)) {
-                    fft::half_butterfly(h, re, im);
+                float re[32], im[32];
+                if (t < ntask && fftc_load<Cfg>(ph, bufs, unit, h, re, im)) {
+                    if (h) fft::half_twiddle(re, im);
                     fft::fft32_fwd(re, im);
                     fftc_store<Cfg>(ph, bufs, unit, h, re, im);
                 }

@@ -96,50 +96,63 @@ HDN_HD int fft_src_row(int r) {
     return sr;
 }
 
-// ---- loads: all 64 complex inputs of the unit's transform -----------------------------------------------------------------
+// ---- loads: the 64 complex inputs a[n] of the unit's transform, folded on the fly into the half's 32 values ---------------------
+//      s[n] = a[n] + sgn * a[n+32]      sgn = +1 (h = 0) / -1 (h = 1), one FFMA per value; 64 live registers instead of 128
 template <class Cfg>
-HDN_HD bool fftc_load(int ph, const FftBufs &b, int unit, float (&re)[64], float (&im)[64]) {
+HDN_HD void fftc_fold_row(const float *row, bool valid, float sgn, float (&s)[32]) {  // a[n] = padded row, zero past WP
+#pragma unroll
+    for (int n = 0; n < 32; ++n) {
+        int q = n - Cfg::PW, q2 = n + 32 - Cfg::PW;  // compile-time: replicate padding of the columns
+        q = q < 0 ? 0 : (q > Cfg::WX - 1 ? Cfg::WX - 1 : q);
+        q2 = q2 < 0 ? 0 : (q2 > Cfg::WX - 1 ? Cfg::WX - 1 : q2);
+        const float lo = (n < Cfg::WP && valid) ? row[q] : 0.f;
+        s[n] = (n + 32 < Cfg::WP && valid) ? row[q2] * sgn + lo : lo;
+    }
+}
+
+template <class Cfg>
+HDN_HD bool fftc_load(int ph, const FftBufs &b, int unit, int h, float (&re)[32], float (&im)[32]) {
+    const float sgn = h ? -1.f : 1.f;
     if (ph == FFT_PH_R) {
         if (unit >= Cfg::R_UNITS) return false;
         const int p = unit / Cfg::R_UNITS_PLANE, j = unit - p * Cfg::R_UNITS_PLANE;
-        const bool ktype = j < Cfg::KH;  // (x_j, k_j);  else (x_j, x_{j + R_PAIRS})
-        const float *xrow = b.rawx + p * Cfg::XPL + fft_src_row<Cfg>(j) * Cfg::WX;
-#pragma unroll
-        for (int n = 0; n < 64; ++n) {
-            int q = n - Cfg::PW;  // compile-time: replicate padding of the columns
-            q = q < 0 ? 0 : (q > Cfg::WX - 1 ? Cfg::WX - 1 : q);
-            re[n] = n < Cfg::WP ? xrow[q] : 0.f;
-        }
-        if (ktype) {
+        fftc_fold_row<Cfg>(b.rawx + p * Cfg::XPL + fft_src_row<Cfg>(j) * Cfg::WX, true, sgn, re);
+        if (j < Cfg::KH) {  // (x_j, k_j)
             const float *krow = b.rawk + p * Cfg::KPL + j * Cfg::KW;
 #pragma unroll
-            for (int n = 0; n < 64; ++n) im[n] = n < Cfg::KW ? krow[n] : 0.f;
-        } else {
+            for (int n = 0; n < 32; ++n) {
+                const float lo = n < Cfg::KW ? krow[n] : 0.f;
+                im[n] = n + 32 < Cfg::KW ? krow[n + 32] * sgn + lo : lo;
+            }
+        } else {  // (x_j, x_{j + R_PAIRS})
             const int r2 = j + Cfg::R_PAIRS;
             const bool has2 = r2 < Cfg::HP;
-            const float *xrow2 = b.rawx + p * Cfg::XPL + fft_src_row<Cfg>(has2 ? r2 : j) * Cfg::WX;
-#pragma unroll
-            for (int n = 0; n < 64; ++n) {
-                int q = n - Cfg::PW;
-                q = q < 0 ? 0 : (q > Cfg::WX - 1 ? Cfg::WX - 1 : q);
-                im[n] = (n < Cfg::WP && has2) ? xrow2[q] : 0.f;
-            }
+            fftc_fold_row<Cfg>(b.rawx + p * Cfg::XPL + fft_src_row<Cfg>(has2 ? r2 : j) * Cfg::WX, has2, sgn, im);
         }
         return true;
     }
     if (unit >= Cfg::O_UNITS) return false;
     const int m = unit / Cfg::HO, i = unit - m * Cfg::HO;
     const float2 *rp = b.CT + (2 * m) * Cfg::CT_PLANE + i * Cfg::PITCH, *rq = rp + Cfg::CT_PLANE;
-    // stored rows are conj(c~) (slot 0 = (c~(0), -c~(32)), both real); build conj(Q), Q(f) = c~_p(f) + i*c~_q(f), Q(-f) by symmetry
+    // Stored rows are conj(c~) (slot 0 = (c~(0), -c~(32)), both real).  The transform's input is a = conj(Q), Q(f) = c~_p(f) + i*c~_q(f):
+    //   a[f]    = (A.x + C.y,  A.y - C.x)      f = 1..31, A = rp[f], C = rq[f]
+    //   a[64-f] = (A.x - C.y, -A.y - C.x)      (Hermitian extension)
+    //   a[0]    = (A0.x, -C0.x),  a[32] = (-A0.y, C0.y)
+    // s[n] = a[n] + sgn * a[n+32] pairs slot n with slot 32 - n, so n and 32 - n are produced from the same four loads.
     {
-        const float2 a = rp[0], c = rq[0];
-        re[0] = a.x; im[0] = -c.x; re[32] = -a.y; im[32] = c.y;
+        const float2 A = rp[0], C = rq[0];
+        re[0] = A.x - sgn * A.y; im[0] = sgn * C.y - C.x;
+        const float2 A16 = rp[16], C16 = rq[16];
+        re[16] = (A16.x + C16.y) + sgn * (A16.x - C16.y);
+        im[16] = (A16.y - C16.x) - sgn * (A16.y + C16.x);
     }
 #pragma unroll
-    for (int f = 1; f < 32; ++f) {
-        const float2 a = rp[f], c = rq[f];
-        re[f] = a.x + c.y; im[f] = a.y - c.x;
-        re[64 - f] = a.x - c.y; im[64 - f] = -a.y - c.x;
+    for (int n = 1; n < 16; ++n) {
+        const float2 A = rp[n], C = rq[n], B = rp[32 - n], D = rq[32 - n];
+        const float ar = A.x + C.y, ai = A.y - C.x, amr = A.x - C.y, ami = -A.y - C.x;  // a[n], a[64 - n]
+        const float br = B.x + D.y, bi = B.y - D.x, bmr = B.x - D.y, bmi = -B.y - D.x;  // a[32 - n], a[32 + n]
+        re[n] = bmr * sgn + ar; im[n] = bmi * sgn + ai;            // a[n] + sgn * a[n + 32]
+        re[32 - n] = amr * sgn + br; im[32 - n] = ami * sgn + bi;  // a[32 - n] + sgn * a[64 - n]
     }
     return true;
 }
@@ -147,7 +160,7 @@ HDN_HD bool fftc_load(int ph, const FftBufs &b, int unit, float (&re)[64], float
 // ---- stores: the half's 32 outputs X[2m + h] are at (re, im)[POS32(m)] ------------------------------------------------------
 // Phase R needs the half as a compile-time constant (the partner X[64 - f] of X[f] sits at a register index that depends on it).
 template <class Cfg, int H>
-HDN_HD void fftc_store_R(const FftBufs &b, int unit, const float (&re)[64], const float (&im)[64]) {
+HDN_HD void fftc_store_R(const FftBufs &b, int unit, const float (&re)[32], const float (&im)[32]) {
     using namespace fft;
     const int p = unit / Cfg::R_UNITS_PLANE, j = unit - p * Cfg::R_UNITS_PLANE;
     const bool ktype = j < Cfg::KH;
@@ -167,7 +180,7 @@ HDN_HD void fftc_store_R(const FftBufs &b, int unit, const float (&re)[64], cons
 }
 
 template <class Cfg>
-HDN_HD void fftc_store(int ph, const FftBufs &b, int unit, int h, const float (&re)[64], const float (&im)[64]) {
+HDN_HD void fftc_store(int ph, const FftBufs &b, int unit, int h, const float (&re)[32], const float (&im)[32]) {
     using namespace fft;
     if (ph == FFT_PH_R) {
         if (h == 0) fftc_store_R<Cfg, 0>(b, unit, re, im);

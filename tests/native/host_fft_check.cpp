@@ -13,8 +13,7 @@
 using namespace hdn;
 
 struct Regs {
-    float re[64], im[64];
-    bool active;
+    float re[32], im[32];
 };
 
 template <class Cfg>
@@ -31,8 +30,8 @@ static void run_group(const std::vector<float> &raw, std::vector<float> &out, bo
         for (int s = 0; s < ntask; ++s) {
             const int t = order(s, ntask), h = fft_task_half(t), unit = fft_task_unit(t);
             Regs r;
-            if (!fftc_load<Cfg>(ph, b, unit, r.re, r.im)) continue;
-            fft::half_butterfly(h, r.re, r.im);
+            if (!fftc_load<Cfg>(ph, b, unit, h, r.re, r.im)) continue;
+            if (h) fft::half_twiddle(r.re, r.im);
             fft::fft32_fwd(r.re, r.im);
             fftc_store<Cfg>(ph, b, unit, h, r.re, r.im);
         }
