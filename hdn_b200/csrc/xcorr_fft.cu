@@ -3,19 +3,17 @@
 // Replaces hdn/core/xcorr.py:37-46 / :48-61 at 256/512 crops (61x61 (*) 29x29, 29x29 circular (*) 29x29) and the 15x15
 // large-displacement window (39x39 (*) 15x15).  Algorithm and phase functions: xcorr_fft.cuh; 64-point FFT: fft64.cuh.
 //
-// Kernel structure (persistent CTAs, two or three per SM; G = 2 planes per group, 6-10 warps per CTA):
+// Kernel structure (persistent CTAs, two or three per SM; G = 2 planes per group, 4-6 warps per CTA):
 //   * the x and k planes of a group are two contiguous byte ranges -> two 1-D TMA bulk copies (UBLKCP) onto an mbarrier.  Two
 //     planes of odd size start 0 or 8 bytes past a 16-byte boundary, so the copy fetches the enclosing 16-byte-aligned window (it
 //     stays inside the tensor: C % 4 == 0 makes the tensor's own ends aligned) and the phases index from the offset.  The NEXT
 //     group's copies are issued as soon as phase R has consumed the landing buffer, so they fly during the column stage;
-//   * two barrier-separated stages per iteration, software-pipelined over the CTA's groups:
-//       FFT stage     row FFTs of group g (phase R) side by side with the inverse row FFTs of group g-1 (phase O): an FFT task is
-//                     one half of a 64-point FFT, register-resident, and both phases run ONE copy of the half-FFT code (a fully
-//                     specialised straight-line kernel, one FFT body per phase = 130 KB of SASS, spent half of its issue slots
-//                     waiting for instruction fetch).  Phase O alone would keep 2 of the CTA's warps busy;
-//       column stage  the tile of group g-1 is copied out (coalesced stores), then the direct complex correlation per
-//                     frequency column of group g: a dense FFMA loop;
-//   * the CTAs of an SM run unsynchronised, so one CTA's shared-memory-bound load section overlaps another's arithmetic.
+//   * phase R (row FFTs) -> column stage (direct complex correlation per frequency column, a dense FFMA loop) -> phase O
+//     (inverse row FFTs), separated by __syncthreads().  An FFT task = one half of a 64-point FFT, register-resident; R and O
+//     share ONE copy of the half-FFT code (the phase only selects the load / store code around it) -- a fully specialised
+//     straight-line kernel (one FFT body per phase, 130 KB of SASS) spent half of its issue slots waiting for instruction fetch;
+//   * the CTAs of an SM run unsynchronised, so one CTA's shared-memory-bound load section overlaps another's arithmetic;
+//   * the finished tile (staged over the dead row-spectrum buffer) is copied out with coalesced stores.
 // HBM traffic is the algorithmic bytes (each plane read once, each output written once).
 #include "common.cuh"
 #include "xcorr_fft.cuh"
@@ -25,14 +23,13 @@ namespace hdn {
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::NT, Cfg::CTAS)
     xcorr_fft_kernel(XProblems P, int groups_per_problem, int n_groups, int C, long long k_bstride) {
-    static_assert(Cfg::NT >= Cfg::FFT_TASKS, "the merged FFT stage is one round: one thread per task");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *raw = reinterpret_cast<float *>(smem_raw);
-    float *so = raw + Cfg::RAW_FLOATS;
-    float2 *XR = reinterpret_cast<float2 *>(so + Cfg::OUT_FLOATS);
+    float2 *XR = reinterpret_cast<float2 *>(raw + Cfg::RAW_FLOATS);
     float2 *KR = XR + Cfg::G * Cfg::XR_PLANE;
     float2 *CT = KR + Cfg::G * Cfg::KR_PLANE;
     uint64_t *full = reinterpret_cast<uint64_t *>(CT + Cfg::G * Cfg::CT_PLANE);
+    float *so = reinterpret_cast<float *>(XR);  // output tile: XR is dead once the column stage is done
     const int tid = threadIdx.x;
     if (tid == 0) {
         mbar_init(full, 1);
@@ -58,47 +55,42 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::CTAS)
     };
     if (tid == 0 && (int)blockIdx.x < n_groups) issue(blockIdx.x);
 
-    // my FFT task: phase R (this group) for the first R_TASKS threads, phase O (previous group) for the next O_TASKS
-    const int ph = fftc_task_phase<Cfg>(tid), tt = ph == FFT_PH_R ? tid : tid - Cfg::R_TASKS;
-    const int h = fft_task_half(tt), unit = fft_task_unit(tt);
-    const bool has_task = tid < Cfg::FFT_TASKS;
-
-    float *prev_dst = nullptr;  // where the previous group's tile goes
     int it = 0;
-    for (int g = blockIdx.x;; g += gridDim.x, ++it) {
-        const bool live = g < n_groups;  // false: drain iteration (phase O + copy-out of the last group only)
-        if (!live && prev_dst == nullptr) break;
-        int prob = 0;
-        long long xoff = 0, koff = 0, ooff = 0;
-        if (live) locate(g, prob, xoff, koff, ooff);
+    for (int g = blockIdx.x; g < n_groups; g += gridDim.x, ++it) {
+        int prob;
+        long long xoff, koff, ooff;
+        locate(g, prob, xoff, koff, ooff);
         const FftBufs bufs{raw + (int)(xoff & 3), raw + Cfg::XWIN + (int)(koff & 3), XR, KR, CT, so};
-        if (live) mbar_wait(full, it & 1);
-        // ---- FFT stage: R(g) || O(previous g) ------------------------------------------------------------------------------------
-        if (has_task && (ph == FFT_PH_R ? live : prev_dst != nullptr)) {
-            float re[32], im[32];
-            if (fftc_load<Cfg>(ph, bufs, unit, h, re, im)) {
-                if (h) fft::half_twiddle(re, im);
-                fft::fft32_fwd(re, im);
-                fftc_store<Cfg>(ph, bufs, unit, h, re, im);
+        mbar_wait(full, it & 1);
+#pragma unroll 1
+        for (int ph = 0; ph < FFT_PHASES; ++ph) {
+            const int ntask = fftc_tasks<Cfg>(ph);
+#pragma unroll 1
+            for (int t0 = 0; t0 < ntask; t0 += Cfg::NT) {
+                const int t = t0 + tid;
+                const int h = fft_task_half(t), unit = fft_task_unit(t);
+                float re[32], im[32];
+                if (t < ntask && fftc_load<Cfg>(ph, bufs, unit, h, re, im)) {
+                    if (h) fft::half_twiddle(re, im);
+                    fft::fft32_fwd(re, im);
+                    fftc_store<Cfg>(ph, bufs, unit, h, re, im);
+                }
+            }
+            __syncthreads();
+            if (ph == FFT_PH_R) {
+                if (tid == 0) {  // landing buffer consumed
+                    const int gn = g + gridDim.x;
+                    if (gn < n_groups) issue(gn);
+                }
+#pragma unroll 1
+                for (int t = tid; t < Cfg::COL_TASKS; t += Cfg::NT) fftc_col<Cfg>(bufs, t);
+                __syncthreads();
             }
         }
-        __syncthreads();
-        // ---- column stage of g; the previous tile leaves ----------------------------------------------------------------------------
-        if (live && tid == 0) {  // landing buffer consumed
-            const int gn = g + gridDim.x;
-            if (gn < n_groups) issue(gn);
-        }
-        if (prev_dst != nullptr) {
+        float *dst = P.out[prob] + ooff;
 #pragma unroll 2
-            for (int e = tid; e < Cfg::OUT_FLOATS; e += Cfg::NT) prev_dst[e] = so[e];
-        }
-        if (live) {
-#pragma unroll 1
-            for (int t = tid; t < Cfg::COL_TASKS; t += Cfg::NT) fftc_col<Cfg>(bufs, t);
-        }
-        prev_dst = live ? P.out[prob] + ooff : nullptr;
-        __syncthreads();
-        if (!live) break;
+        for (int e = tid; e < Cfg::OUT_FLOATS; e += Cfg::NT) dst[e] = so[e];
+        __syncthreads();  // the tile aliases XR, which the next group's phase R writes
     }
 }
 
@@ -120,16 +112,15 @@ static int launch_fft(const XProblems &P, int n, int B, int C, long long kbs, cu
 }
 
 //                     KH  KW  HX  WX  circ  G   NT
-// threads per CTA = FFT tasks of one iteration (phase R of a group + phase O of the previous one); the column stage splits a
-// plane's output rows over NT / 64 warps
+// threads per CTA (tunable at build time for A/B runs): the column stage splits a plane's output rows over NT / 64 warps
 #ifndef HDN_FFT_NT1
-#define HDN_FFT_NT1 320  // 192 row-FFT tasks + 128 output-FFT tasks
+#define HDN_FFT_NT1 192
 #endif
 #ifndef HDN_FFT_NT2
-#define HDN_FFT_NT2 256  // 192 + 64
+#define HDN_FFT_NT2 128
 #endif
 #ifndef HDN_FFT_NT3
-#define HDN_FFT_NT3 192  // 128 + 64
+#define HDN_FFT_NT3 128
 #endif
 using F256 = FCfg<29, 29, 61, 61, false, 2, HDN_FFT_NT1>;    // 256/512 crops, similarity branch
 using F256Lp = FCfg<29, 29, 29, 29, true, 2, HDN_FFT_NT2, 4>;  // 256/512 crops, log-polar branch (INSTANCE_SIZE = 512); 15-row segments: 4-tap blocks

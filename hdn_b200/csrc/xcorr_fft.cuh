@@ -64,9 +64,9 @@ struct FCfg {
     static constexpr int pad32(int n) { return (n + 31) / 32 * 32; }
     // FFT tasks = (unit, half); warps alternate halves so a warp runs one half only:  task t -> h = (t/32) % 2, unit = (t/64)*32 + t%32
     static constexpr int R_TASKS = 2 * pad32(R_UNITS), O_TASKS = 2 * pad32(O_UNITS), COL_TASKS = G * NSEG * 32;
-    static constexpr int FFT_TASKS = R_TASKS + O_TASKS;  // phase R of one group and phase O of the previous one run side by side
-    static constexpr unsigned long long SMEM =
-        (unsigned long long)(RAW_FLOATS + OUT_FLOATS) * 4 + (unsigned long long)G * (XR_PLANE + KR_PLANE + CT_PLANE) * 8 + 16;
+    // the output tile is staged over XR (dead once the column stage is done)
+    static_assert((unsigned long long)G * XR_PLANE * 8 >= (unsigned long long)OUT_FLOATS * 4, "output tile must fit the XR region it aliases");
+    static constexpr unsigned long long SMEM = (unsigned long long)RAW_FLOATS * 4 + (unsigned long long)G * (XR_PLANE + KR_PLANE + CT_PLANE) * 8 + 16;
     static constexpr int CTAS = SMEM <= 75 * 1024 ? 3 : (SMEM <= 113 * 1024 ? 2 : 1);  // resident CTAs per SM (228 KB of shared memory)
     static_assert(HP <= 64 && WP <= 64, "padded input must fit the 64-point transform");
     static_assert(KH <= HP && KW <= WP && HO <= 64 && WO <= 64, "shape");
@@ -77,7 +77,7 @@ struct FCfg {
 struct FftBufs {
     const float *rawx, *rawk;  // landed planes of the group (dense)
     float2 *XR, *KR, *CT;
-    float *out;  // output tile of the group (dense)
+    float *out;  // output tile of the group (dense); aliases XR
 };
 
 enum { FFT_PH_R = 0, FFT_PH_O = 1, FFT_PHASES = 2 };
@@ -203,9 +203,6 @@ template <class Cfg>
 HDN_HD int fftc_tasks(int ph) {
     return ph == FFT_PH_R ? Cfg::R_TASKS : Cfg::O_TASKS;
 }
-// task of the merged FFT stage -> phase (R tasks first, then O tasks), task index inside the phase
-template <class Cfg>
-HDN_HD int fftc_task_phase(int t) { return t < Cfg::R_TASKS ? FFT_PH_R : FFT_PH_O; }
 
 // ---- column stage ----------------------------------------------------------------------------------------------------------
 // conj c~(i,f) = sum_u conj X'(i+u,f) * K'(u,f)  for the SEG output rows of the task's segment; NTAP taps per block, the
