@@ -10,11 +10,11 @@
 //                 2A(f) = Z(f) + conj Z(-f), 2B(f) = (Z(f) - conj Z(-f))/i): (x_r, k_r) for r < KH, then (x_r, x_{r+np}).
 //                 Only f = 0..32 is kept (Hermitian); the real values at f = 0 and f = 32 share slot 0 -> 32 complex per row.
 //   COL  columns  c~(i,f) = sum_u X'(i+u,f) * conj K'(u,f)       a 1-D complex correlation per frequency column: KH complex
-//                 MACs per output instead of KH*KW real ones.  (Slot 0 holds two real columns: component-wise products.)
+//                 MACs (3 FFMAs each) per output instead of KH*KW real ones.  (Slot 0 holds two real columns: component-wise.)
 //   O    outputs  out(i,:) = IFFT64_f c~(i,f), two planes per complex FFT:  Q(f) = c~_p(i,f) + i*c~_q(i,f), extended to f > 32
 //                 by Hermitian symmetry;  out_p(i,:) + i*out_q(i,:) = IFFT(Q) = conj(FFT(conj Q)).
 //
-// Per output this is ~4*KH + 2 * (64-point FFT / 33) instead of KH*KW operations, fp32-accurate (3e-7 of max|out|).  A full
+// Per output this is ~3*KH + 2 * (64-point FFT / 33) instead of KH*KW operations, fp32-accurate (3e-7 of max|out|).  A full
 // 2-D FFT (columns transformed too) has the same operation count but needs five barrier-separated phases of twiddle-heavy
 // code; the direct column stage is a dense FFMA loop like the direct kernel's.
 //
@@ -205,28 +205,28 @@ HDN_HD int fftc_tasks(int ph) {
 }
 
 // ---- column stage ----------------------------------------------------------------------------------------------------------
-// conj c~(i,f) = sum_u conj X'(i+u,f) * K'(u,f)  for the SEG output rows of the task's segment; NTAP taps per block, the
-// SEG + NTAP - 1 input rows of a block are held in registers (one shared load feeds ~NTAP complex MACs).  Slot 0 (f == 0) packs
-// two REAL columns (f = 0 in .x, f = 32 in .y): its MAC is component-wise, (x.x*k.x, -x.y*k.y), obtained branch-free by
-// editing the tap.
+// conj c~(i,f) = sum_u conj X'(i+u,f) * K'(u,f)  for the SEG output rows of the task's segment.  NTAP taps per block; the
+// SEG + NTAP - 1 input rows of a block are held in registers (one shared load feeds ~NTAP complex MACs).  A complex MAC costs
+// THREE FFMAs (Gauss): with  a1 = sum xr*kr,  a2 = sum xi*ki,  a3 = sum (xr + xi)*(kr - ki)
+//     Re = a1 + a2,    Im(x * conj k) = a3 - a1 + a2        (the stored conjugate has the imaginary part a1 - a2 - a3).
+// Slot 0 (f == 0) packs two REAL columns (f = 0 in .x, f = 32 in .y) whose products must not mix: it simply keeps (a1, -a2).
 template <class Cfg, int NTAP>
-HDN_HD void fftc_col_block(const float2 *xc, const float2 *kc, int u0, bool f0, float (&ar)[Cfg::SEG], float (&ai)[Cfg::SEG]) {
-    float wr[Cfg::SEG + NTAP - 1], wi[Cfg::SEG + NTAP - 1];
+HDN_HD void fftc_col_block(const float2 *xc, const float2 *kc, int u0, float (&a1)[Cfg::SEG], float (&a2)[Cfg::SEG], float (&a3)[Cfg::SEG]) {
+    float wr[Cfg::SEG + NTAP - 1], wi[Cfg::SEG + NTAP - 1], ws[Cfg::SEG + NTAP - 1];
 #pragma unroll
     for (int d = 0; d < Cfg::SEG + NTAP - 1; ++d) {
         const float2 t = xc[(u0 + d) * Cfg::PITCH];
-        wr[d] = t.x; wi[d] = t.y;
+        wr[d] = t.x; wi[d] = t.y; ws[d] = t.x + t.y;
     }
 #pragma unroll
     for (int tt = 0; tt < NTAP; ++tt) {
         const float2 k = kc[(u0 + tt) * Cfg::PITCH];
-        const float q = f0 ? 0.f : k.y, ns = f0 ? -k.y : -k.x;
+        const float kd = k.x - k.y;
 #pragma unroll
         for (int i = 0; i < Cfg::SEG; ++i) {
-            ar[i] = wr[i + tt] * k.x + ar[i];
-            ar[i] = wi[i + tt] * q + ar[i];
-            ai[i] = wr[i + tt] * q + ai[i];
-            ai[i] = wi[i + tt] * ns + ai[i];
+            a1[i] = wr[i + tt] * k.x + a1[i];
+            a2[i] = wi[i + tt] * k.y + a2[i];
+            a3[i] = ws[i + tt] * kd + a3[i];
         }
     }
 }
@@ -237,20 +237,19 @@ HDN_HD void fftc_col(const FftBufs &b, int task) {
     const int p = ws / Cfg::NSEG, i0 = (ws - p * Cfg::NSEG) * Cfg::SEG;
     const float2 *xc = b.XR + p * Cfg::XR_PLANE + i0 * Cfg::PITCH + f;
     const float2 *kc = b.KR + p * Cfg::KR_PLANE + f;
-    const bool f0 = f == 0;
-    float ar[Cfg::SEG], ai[Cfg::SEG];
+    float a1[Cfg::SEG], a2[Cfg::SEG], a3[Cfg::SEG];
 #pragma unroll
-    for (int i = 0; i < Cfg::SEG; ++i) ar[i] = ai[i] = 0.f;
+    for (int i = 0; i < Cfg::SEG; ++i) a1[i] = a2[i] = a3[i] = 0.f;
     constexpr int FULL = Cfg::KH / Cfg::TB * Cfg::TB, REM = Cfg::KH - FULL;
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
-    for (int u0 = 0; u0 < FULL; u0 += Cfg::TB) fftc_col_block<Cfg, Cfg::TB>(xc, kc, u0, f0, ar, ai);
-    if (REM > 0) fftc_col_block<Cfg, (REM > 0 ? REM : 1)>(xc, kc, FULL, f0, ar, ai);
+    for (int u0 = 0; u0 < FULL; u0 += Cfg::TB) fftc_col_block<Cfg, Cfg::TB>(xc, kc, u0, a1, a2, a3);
+    if (REM > 0) fftc_col_block<Cfg, (REM > 0 ? REM : 1)>(xc, kc, FULL, a1, a2, a3);
     float2 *ct = b.CT + p * Cfg::CT_PLANE + i0 * Cfg::PITCH + f;
 #pragma unroll
     for (int i = 0; i < Cfg::SEG; ++i)
-        if (i0 + i < Cfg::HO) ct[i * Cfg::PITCH] = float2{ar[i], ai[i]};
+        if (i0 + i < Cfg::HO) ct[i * Cfg::PITCH] = f == 0 ? float2{a1[i], -a2[i]} : float2{a1[i] + a2[i], a1[i] - a2[i] - a3[i]};
 }
 
 }  // namespace hdn
