@@ -74,7 +74,7 @@ static int check(const char *name, unsigned seed) {
 
 int main() {
     int bad = 0;
-    bad += check<FCfg<29, 29, 61, 61, false, 2, 128>>("k1_256", 1);
+    bad += check<FCfg<29, 29, 61, 61, false, 2, 192>>("k1_256", 1);
     bad += check<FCfg<29, 29, 29, 29, true, 2, 128>>("k2_256", 2);
     bad += check<FCfg<15, 15, 39, 39, false, 2, 128>>("win15", 3);
     bad += check<FCfg<13, 11, 40, 37, false, 4, 256>>("ragged", 4);
