@@ -17,50 +17,72 @@
 namespace hdn {
 
 // ------------------------------------------------------------------------------------------ K3
-// out[b,ch,i,j]: i = angle index, j = log-radius index.  One thread per (b,i,j); channels looped so
-// the transcendental work and the four neighbour offsets are shared by all channels.
-__global__ void __launch_bounds__(256)
-    logpolar_kernel(const float *__restrict__ img, const float *__restrict__ polar, float rot_delta, float *__restrict__ out, int B, int Ch,
-                    int H, int W, int S, float mag) {
-    const long long total = (long long)B * S * S;
+// out[b,ch,i,j]: i = angle index, j = log-radius index.  One thread per (batch chunk, i, j): the sampling position depends on
+// the batch item only through `polar`, so without it (the tracker always passes zeros, hdn_tracker_proj_e2e.py:194) the
+// transcendental work, the IEEE divisions and the four neighbour offsets are computed once and shared by the BC items of the
+// chunk and all channels -- and the BC * Ch * 4 gathers of a thread are independent loads in flight.
+struct LpSample {
+    int o00;
+    bool xin, yin;
+    float w00, w10, w01, w11;
+};
+
+__device__ __forceinline__ LpSample logpolar_sample_pos(int i, int j, float px, float py, float rot_delta, float mag, int H, int W, int S) {
     const float pi_f = 3.14159265358979323846f;
     const float fS = (float)S, fW = (float)W, fH = (float)H;
     const float half_h = (float)(H / 2), half_w = (float)(W / 2);
+    // theta = i*2*pi/S + delta  (logpolar.py:66, evaluated left to right in fp32)
+    const float theta = __fadd_rn(__fdiv_rn(__fmul_rn(__fmul_rn((float)i, 2.0f), pi_f), fS), rot_delta);
+    float st, ct;
+    sincosf(theta, &st, &ct);
+    const float rho = __fsub_rn(expf(__fmul_rn(mag, (float)j)), 1.0f);  // :65
+    // normalised grid (:113-117): x over size(2)//2, y over size(3)//2
+    const float gx = __fdiv_rn(__fadd_rn(__fmul_rn(rho, ct), px), half_h);
+    const float gy = __fdiv_rn(__fadd_rn(__fmul_rn(rho, st), py), half_w);
+    // grid_sample: unnormalise (align_corners=False), clip to the border, bilinear
+    float ix = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), fW), 1.f), 2.f);
+    float iy = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), fH), 1.f), 2.f);
+    ix = fminf(fmaxf(ix, 0.f), fW - 1.f);
+    iy = fminf(fmaxf(iy, 0.f), fH - 1.f);
+    const float fx = floorf(ix), fy = floorf(iy);
+    const int x0 = (int)fx, y0 = (int)fy;
+    LpSample s;
+    s.xin = x0 + 1 <= W - 1;
+    s.yin = y0 + 1 <= H - 1;
+    const float wx1 = __fsub_rn(ix, fx), wx0 = __fsub_rn(__fadd_rn(fx, 1.f), ix);
+    const float wy1 = __fsub_rn(iy, fy), wy0 = __fsub_rn(__fadd_rn(fy, 1.f), iy);
+    s.w00 = __fmul_rn(wx0, wy0); s.w10 = __fmul_rn(wx1, wy0); s.w01 = __fmul_rn(wx0, wy1); s.w11 = __fmul_rn(wx1, wy1);
+    s.o00 = y0 * W + x0;
+    return s;
+}
+
+template <int BC>
+__global__ void __launch_bounds__(256)
+    logpolar_kernel(const float *__restrict__ img, const float *__restrict__ polar, float rot_delta, float *__restrict__ out, int B, int Ch,
+                    int H, int W, int S, float mag) {
+    const int chunks = (B + BC - 1) / BC;
+    const long long total = (long long)chunks * S * S;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const int j = (int)(e % S);
         const int i = (int)((e / S) % S);
-        const int b = (int)(e / ((long long)S * S));
-        const float px = polar ? __ldg(polar + 2 * b) : 0.f, py = polar ? __ldg(polar + 2 * b + 1) : 0.f;
-        // theta = i*2*pi/S + delta  (logpolar.py:66, evaluated left to right in fp32)
-        const float theta = __fadd_rn(__fdiv_rn(__fmul_rn(__fmul_rn((float)i, 2.0f), pi_f), fS), rot_delta);
-        float st, ct;
-        sincosf(theta, &st, &ct);
-        const float rho = __fsub_rn(expf(__fmul_rn(mag, (float)j)), 1.0f);  // :65
-        // normalised grid (:113-117): x over size(2)//2, y over size(3)//2
-        const float gx = __fdiv_rn(__fadd_rn(__fmul_rn(rho, ct), px), half_h);
-        const float gy = __fdiv_rn(__fadd_rn(__fmul_rn(rho, st), py), half_w);
-        // grid_sample: unnormalise (align_corners=False), clip to the border, bilinear
-        float ix = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), fW), 1.f), 2.f);
-        float iy = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), fH), 1.f), 2.f);
-        ix = fminf(fmaxf(ix, 0.f), fW - 1.f);
-        iy = fminf(fmaxf(iy, 0.f), fH - 1.f);
-        const float fx = floorf(ix), fy = floorf(iy);
-        const int x0 = (int)fx, y0 = (int)fy;
-        const bool xin = x0 + 1 <= W - 1, yin = y0 + 1 <= H - 1;
-        const float wx1 = __fsub_rn(ix, fx), wx0 = __fsub_rn(__fadd_rn(fx, 1.f), ix);
-        const float wy1 = __fsub_rn(iy, fy), wy0 = __fsub_rn(__fadd_rn(fy, 1.f), iy);
-        const float w00 = __fmul_rn(wx0, wy0), w10 = __fmul_rn(wx1, wy0), w01 = __fmul_rn(wx0, wy1), w11 = __fmul_rn(wx1, wy1);
-        const int o00 = y0 * W + x0;
-        const float *ip = img + (long long)b * Ch * H * W;
-        float *op = out + ((long long)b * Ch * S + i) * S + j;
-        for (int c = 0; c < Ch; ++c) {
-            float v = __fmul_rn(__ldg(ip + o00), w00);
-            if (xin) v = __fadd_rn(v, __fmul_rn(__ldg(ip + o00 + 1), w10));
-            if (yin) v = __fadd_rn(v, __fmul_rn(__ldg(ip + o00 + W), w01));
-            if (xin && yin) v = __fadd_rn(v, __fmul_rn(__ldg(ip + o00 + W + 1), w11));
-            *op = v;
-            ip += (long long)H * W;
-            op += (long long)S * S;
+        const int b0 = (int)(e / ((long long)S * S)) * BC;
+        LpSample s = logpolar_sample_pos(i, j, 0.f, 0.f, rot_delta, mag, H, W, S);
+#pragma unroll
+        for (int bb = 0; bb < BC; ++bb) {
+            const int b = b0 + bb;
+            if (b >= B) break;
+            if (polar) s = logpolar_sample_pos(i, j, __ldg(polar + 2 * b), __ldg(polar + 2 * b + 1), rot_delta, mag, H, W, S);
+            const float *ip = img + (long long)b * Ch * H * W + s.o00;
+            float *op = out + ((long long)b * Ch * S + i) * S + j;
+            for (int c = 0; c < Ch; ++c) {
+                float v = __fmul_rn(__ldg(ip), s.w00);
+                if (s.xin) v = __fadd_rn(v, __fmul_rn(__ldg(ip + 1), s.w10));
+                if (s.yin) v = __fadd_rn(v, __fmul_rn(__ldg(ip + W), s.w01));
+                if (s.xin && s.yin) v = __fadd_rn(v, __fmul_rn(__ldg(ip + W + 1), s.w11));
+                *op = v;
+                ip += (long long)H * W;
+                op += (long long)S * S;
+            }
         }
     }
 }
@@ -243,11 +265,16 @@ extern "C" int hdn_logpolar_f32(const float *img, const float *polar, float rot_
     if (!img || !out) return HDN_ERR_NULL;
     if (B < 1 || Ch < 1 || H < 2 || W < 2 || S < 2) return HDN_ERR_SHAPE;
     const float mag = (float)(log((double)S / 2.0) / (double)S);  // logpolar.py:63
-    const long long total = (long long)B * S * S;
-    long long blocks = (total + 255) / 256;
+    // batch items per thread: as many as still leave a few waves of CTAs
     const long long cap = (long long)sm_count() * 8;
-    if (blocks > cap) blocks = cap;
-    logpolar_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(img, polar, rot_delta, out, B, Ch, H, W, S, mag);
+    auto launch = [&](auto kern, int bc) {
+        const long long total = (long long)((B + bc - 1) / bc) * S * S;
+        long long blocks = (total + 255) / 256;
+        if (blocks > cap) blocks = cap;
+        kern<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(img, polar, rot_delta, out, B, Ch, H, W, S, mag);
+    };
+    if ((long long)B * S * S >= 4 * cap * 256) launch(logpolar_kernel<4>, 4);
+    else launch(logpolar_kernel<1>, 1);
     count_launch();
     return launch_status();
 }
