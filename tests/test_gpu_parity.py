@@ -161,6 +161,20 @@ def test_logpolar_golden(name):
     assert_close(out.cpu().numpy(), c_oracle.logpolar(img, g["polar"], float(g["delta"][1]), S), what=name + " vs C")
 
 
+def test_logpolar_batch_chunked_path_equals_per_item_path():
+    """Large batches share the sampling position across 4 items per thread (or recompute it per item when `polar` is given):
+    bit-identical to the one-item-per-thread path small batches take."""
+    B, H, W, S = 24, 512, 512, 256
+    gen = torch.Generator(device=DEV).manual_seed(9)
+    img = torch.rand((B, 3, H, W), device=DEV, generator=gen) * 255.0
+    for polar in (None, (torch.rand((B, 2), device=DEV, generator=gen) - 0.5) * 40.0):
+        big = ops().logpolar_sample(img, polar, 0.25, S)
+        small = torch.cat([ops().logpolar_sample(img[b:b + 2], None if polar is None else polar[b:b + 2], 0.25, S) for b in range(0, B, 2)])
+        assert torch.equal(big, small)
+    ref = c_oracle.logpolar(img[:2].cpu().numpy(), polar[:2].cpu().numpy(), 0.25, S)
+    assert_close(big[:2].cpu().numpy(), ref, what="chunked log-polar vs C oracle")
+
+
 def test_logpolar_full_size_affine_reproduction():
     """[64,3,512,512] -> [64,3,256,256]: bilinear sampling reproduces an affine image exactly at the sample point."""
     B, H, W, S = 64, 512, 512, 256
