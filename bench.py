@@ -151,13 +151,18 @@ def cpu_chain_rate(workload, seconds, threads=None, steps=None, warmup=1):
             "ms_per_step": 1e3 * dt / steps, "pairs": n}
 
 
+def workload_name(workload):
+    return "%s crops: 6xK1 + 6xK2 + K3 + K5/K4 + 2xK6 per pair" % workload if workload != "win15" else "15x15 window K1 only (config 5)"
+
+
 def run_reference(a, rank):
     if rank != 0:
         return
     r = cpu_chain_rate(a.workload, a.cpu_seconds, steps=a.steps, warmup=max(a.warmup, 1))
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%s corr+warp+DLT chain, CPU, %d pair(s)/step" % (a.workload, r["pairs"])},
+            "config": {"workload": workload_name(a.workload), "sample_pairs_per_step": r["pairs"], "channels": 256, "template": "per pair",
+                       "parallelism": "host cores of rank 0 (CPU arm)"},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -325,7 +330,7 @@ def main():
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%s crops: 6xK1 + 6xK2 + K3 + K5/K4 + 2xK6 per pair" % a.workload if full else "15x15 window K1 only (config 5)",
+            "config": {"workload": workload_name(a.workload),
                        "pairs_per_gpu": B, "global_batch": B * world, "channels": engine.C,
                        "template": "shared, NCCL broadcast from rank 0" if shared else "per pair",
                        "parallelism": "pairs sharded over %d GPU(s), no data-path collective" % world,
