@@ -22,9 +22,13 @@
 
 namespace hdn {
 
-template <int KH_, int KW_, int HX_, int WX_, bool CIRC_, int G_, int NT_, int STAGES_, int KSPLIT_, bool SPILL_, int CTAS_ = 1>
+// PPW_ > 0: a warp owns PPW_ whole planes (lane = plane-in-warp * HO + row, the remaining lanes idle) instead of the dense
+// thread = row numbering.  A plane's rows are an odd pitch apart, so lanes inside one plane never share a bank, but a warp that
+// straddles two planes in the dense numbering does (plane pitch = pitch^2: 4 of 7 straddling lanes collide at 29x29, doubling the
+// wavefronts of every load) -- which made the HBM-bound 5x5 kernel shared-memory-bound (84 % pipe utilisation, 43 % conflicts).
+template <int KH_, int KW_, int HX_, int WX_, bool CIRC_, int G_, int NT_, int STAGES_, int KSPLIT_, bool SPILL_, int CTAS_ = 1, int PPW_ = 0>
 struct XCfg {
-    static constexpr int KH = KH_, KW = KW_, HX = HX_, WX = WX_, G = G_, NT = NT_, STAGES = STAGES_, KSPLIT = KSPLIT_, CTAS = CTAS_;
+    static constexpr int KH = KH_, KW = KW_, HX = HX_, WX = WX_, G = G_, NT = NT_, STAGES = STAGES_, KSPLIT = KSPLIT_, CTAS = CTAS_, PPW = PPW_;
     static constexpr bool CIRC = CIRC_, SPILL = SPILL_;
     static constexpr int PH = CIRC ? HX / 2 : 0, PW = CIRC ? WX / 2 : 0;
     static constexpr int HO = HX + 2 * PH - KH + 1, WO = WX + 2 * PW - KW + 1;
@@ -36,6 +40,7 @@ struct XCfg {
     static_assert(!SPILL || (HO == 33 && NT == 32 * G * KSPLIT), "row-spill mapping is for 33-row outputs");
     static_assert(SMEM * CTAS <= 227 * 1024 - 1024 * CTAS, "shared memory budget");
     static_assert(256 % G == 0, "G must divide the network's 256 channels or the staged path is never taken");
+    static_assert(PPW == 0 || (KSPLIT == 1 && !SPILL && PPW * (HX + 2 * PH - KH + 1) <= 32 && NT * PPW == 32 * G), "warp-per-plane mapping");
 };
 
 // Accumulate kernel rows [u0,u1) of output row i into acc[WO].
@@ -70,7 +75,19 @@ __device__ __forceinline__ void row_accumulate(const float *__restrict__ xp, con
 template <class Cfg>
 __device__ __forceinline__ void compute_group(const float *__restrict__ sx, const float *__restrict__ sk, float *__restrict__ so, int tid) {
     constexpr int ROWS = Cfg::G * Cfg::HO;
-    if constexpr (!Cfg::SPILL) {
+    if constexpr (Cfg::PPW > 0) {
+        const int lane = tid & 31, pl = lane / Cfg::HO, i = lane - pl * Cfg::HO;
+        if (pl < Cfg::PPW) {
+            const int p = (tid >> 5) * Cfg::PPW + pl;
+            float acc[Cfg::WO];
+#pragma unroll
+            for (int c = 0; c < Cfg::WO; ++c) acc[c] = 0.f;
+            row_accumulate<Cfg>(sx + p * Cfg::XPL, sk + p * Cfg::KPL, i, 0, Cfg::KH, acc);
+            float *o = so + p * Cfg::OPL + i * Cfg::WO;
+#pragma unroll
+            for (int c = 0; c < Cfg::WO; ++c) o[c] = acc[c];
+        }
+    } else if constexpr (!Cfg::SPILL) {
 #pragma unroll 1
         for (int ks = 0; ks < Cfg::KSPLIT; ++ks) {
             // split-K slices are combined in slice order (deterministic)
@@ -449,8 +466,13 @@ static int launch_staged(const XProblems &P, int n, int B, int C, long long kbs,
 }
 
 //                       KH  KW  HX  WX  circ   G   NT  ST KS spill
-using CfgNative = XCfg<5, 5, 29, 29, false, 8, 224, 2, 1, false, 2>;   // 127/255 crops (HBM-bound), 2 CTAs/SM
-using CfgNativeLp = XCfg<13, 13, 13, 13, true, 32, 416, 3, 1, false>;  // lp branch, 127 crops
+#ifndef HDN_NATIVE_DENSE  // A/B switch: the dense thread = row numbering these two shapes used before
+using CfgNative = XCfg<5, 5, 29, 29, false, 8, 256, 2, 1, false, 2, 1>;     // 127/255 crops (HBM-bound), 2 CTAs/SM, a warp = one plane (25 rows)
+using CfgNativeLp = XCfg<13, 13, 13, 13, true, 32, 512, 3, 1, false, 1, 2>;  // lp branch, 127 crops, a warp = two planes (2 x 13 rows)
+#else
+using CfgNative = XCfg<5, 5, 29, 29, false, 8, 224, 2, 1, false, 2>;
+using CfgNativeLp = XCfg<13, 13, 13, 13, true, 32, 416, 3, 1, false>;
+#endif
 //                     KH  KW  HX  WX  circ   G   NT KS  XP  KP  tail
 using Cfg256 = VCfg<29, 29, 61, 61, false, 4, 256, 2, 68, 36, true>;    // 256/512 crops (FMA-bound), LDS.128 operands
 using Cfg256Lp = VCfg<29, 29, 29, 29, true, 8, 256, 1, 36, 36, false>;  // lp branch, INSTANCE_SIZE=512

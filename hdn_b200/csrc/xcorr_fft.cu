@@ -122,7 +122,10 @@ static int launch_fft(const XProblems &P, int n, int B, int C, long long kbs, cu
 #ifndef HDN_FFT_NT3
 #define HDN_FFT_NT3 128
 #endif
-using F256 = FCfg<29, 29, 61, 61, false, 2, HDN_FFT_NT1>;    // 256/512 crops, similarity branch
+#ifndef HDN_FFT_G1
+#define HDN_FFT_G1 2
+#endif
+using F256 = FCfg<29, 29, 61, 61, false, HDN_FFT_G1, HDN_FFT_NT1>;    // 256/512 crops, similarity branch
 using F256Lp = FCfg<29, 29, 29, 29, true, 2, HDN_FFT_NT2>;   // 256/512 crops, log-polar branch (INSTANCE_SIZE = 512)
 using FWin15 = FCfg<15, 15, 39, 39, false, 2, HDN_FFT_NT3>;  // 15x15 large-displacement window
 
