@@ -466,13 +466,13 @@ static int launch_staged(const XProblems &P, int n, int B, int C, long long kbs,
 }
 
 //                       KH  KW  HX  WX  circ   G   NT  ST KS spill
-#ifndef HDN_NATIVE_DENSE  // A/B switch: the dense thread = row numbering these two shapes used before
-using CfgNative = XCfg<5, 5, 29, 29, false, 8, 256, 2, 1, false, 2, 1>;     // 127/255 crops (HBM-bound), 2 CTAs/SM, a warp = one plane (25 rows)
-using CfgNativeLp = XCfg<13, 13, 13, 13, true, 32, 512, 3, 1, false, 1, 2>;  // lp branch, 127 crops, a warp = two planes (2 x 13 rows)
+#ifndef HDN_NATIVE_DENSE  // A/B switch: the dense thread = row numbering this shape used before (0.963 ms vs 0.932 ms at batch 512)
+using CfgNative = XCfg<5, 5, 29, 29, false, 8, 256, 2, 1, false, 2, 1>;  // 127/255 crops (HBM-bound), 2 CTAs/SM, a warp = one plane (25 rows)
 #else
 using CfgNative = XCfg<5, 5, 29, 29, false, 8, 224, 2, 1, false, 2>;
-using CfgNativeLp = XCfg<13, 13, 13, 13, true, 32, 416, 3, 1, false>;
 #endif
+// lp branch, 127 crops: FMA-bound (28 flop/B); two planes per warp (26 of 32 lanes) measured slower than the dense numbering (1.207 vs 1.148 ms)
+using CfgNativeLp = XCfg<13, 13, 13, 13, true, 32, 416, 3, 1, false>;
 //                     KH  KW  HX  WX  circ   G   NT KS  XP  KP  tail
 using Cfg256 = VCfg<29, 29, 61, 61, false, 4, 256, 2, 68, 36, true>;    // 256/512 crops (FMA-bound), LDS.128 operands
 using Cfg256Lp = VCfg<29, 29, 29, 29, true, 8, 256, 1, 36, 36, false>;  // lp branch, INSTANCE_SIZE=512
