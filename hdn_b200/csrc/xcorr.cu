@@ -26,8 +26,14 @@ namespace hdn {
 // thread = row numbering.  A plane's rows are an odd pitch apart, so lanes inside one plane never share a bank, but a warp that
 // straddles two planes in the dense numbering does (plane pitch = pitch^2: 4 of 7 straddling lanes collide at 29x29, doubling the
 // wavefronts of every load) -- which made the HBM-bound 5x5 kernel shared-memory-bound (84 % pipe utilisation, 43 % conflicts).
-template <int KH_, int KW_, int HX_, int WX_, bool CIRC_, int G_, int NT_, int STAGES_, int KSPLIT_, bool SPILL_, int CTAS_ = 1, int PPW_ = 0>
+// RP_: row-pair mode for the HBM-bound 5x5 shape (implies two planes per warp): a thread owns TWO consecutive output rows and
+// keeps them as the halves of float2 registers, so one packed FFMA2 (fma.rn.f32x2) updates both -- half the FMA issue slots for the
+// same shared loads (each thread needs the same rows as before).  Lane stride is then two rows (even), which still maps the 13
+// row pairs of a plane to distinct even banks, and the neighbouring plane (pitch^2 = 9 mod 32) to the odd ones.
+template <int KH_, int KW_, int HX_, int WX_, bool CIRC_, int G_, int NT_, int STAGES_, int KSPLIT_, bool SPILL_, int CTAS_ = 1, int PPW_ = 0,
+          bool RP_ = false>
 struct XCfg {
+    static constexpr bool RP = RP_;
     static constexpr int KH = KH_, KW = KW_, HX = HX_, WX = WX_, G = G_, NT = NT_, STAGES = STAGES_, KSPLIT = KSPLIT_, CTAS = CTAS_, PPW = PPW_;
     static constexpr bool CIRC = CIRC_, SPILL = SPILL_;
     static constexpr int PH = CIRC ? HX / 2 : 0, PW = CIRC ? WX / 2 : 0;
@@ -40,7 +46,9 @@ struct XCfg {
     static_assert(!SPILL || (HO == 33 && NT == 32 * G * KSPLIT), "row-spill mapping is for 33-row outputs");
     static_assert(SMEM * CTAS <= 227 * 1024 - 1024 * CTAS, "shared memory budget");
     static_assert(256 % G == 0, "G must divide the network's 256 channels or the staged path is never taken");
-    static_assert(PPW == 0 || (KSPLIT == 1 && !SPILL && PPW * (HX + 2 * PH - KH + 1) <= 32 && NT * PPW == 32 * G), "warp-per-plane mapping");
+    static_assert(PPW == 0 || (KSPLIT == 1 && !SPILL && PPW * ((HX + 2 * PH - KH + 1 + (RP ? 1 : 0)) / (RP ? 2 : 1)) <= 32 && NT * PPW == 32 * G),
+                  "warp-per-plane mapping");
+    static_assert(!RP || (PPW == 2 && !CIRC), "row-pair mode: two planes per warp, plain correlation");
 };
 
 // Accumulate kernel rows [u0,u1) of output row i into acc[WO].
@@ -75,7 +83,41 @@ __device__ __forceinline__ void row_accumulate(const float *__restrict__ xp, con
 template <class Cfg>
 __device__ __forceinline__ void compute_group(const float *__restrict__ sx, const float *__restrict__ sk, float *__restrict__ so, int tid) {
     constexpr int ROWS = Cfg::G * Cfg::HO;
-    if constexpr (Cfg::PPW > 0) {
+    if constexpr (Cfg::RP) {
+        constexpr int NP = (Cfg::HO + 1) / 2;  // row pairs per plane
+        const int lane = tid & 31, pl = lane / NP, j = lane - pl * NP;
+        if (pl < 2) {
+            const int p = (tid >> 5) * 2 + pl, i = 2 * j;
+            const float *xp = sx + p * Cfg::XPL, *kp = sk + p * Cfg::KPL;
+            float2 acc[Cfg::WO];
+#pragma unroll
+            for (int c = 0; c < Cfg::WO; ++c) acc[c] = make_float2(0.f, 0.f);
+#pragma unroll 1
+            for (int u = 0; u < Cfg::KH; ++u) {
+                // rows i+u (-> .x) and i+u+1 (-> .y); for the last, odd row pair the second row lies past the plane: it is read (the
+                // stage buffer continues with the next plane / the templates) and its results are never stored
+                const float *x0 = xp + (i + u) * Cfg::WX;
+                float2 xv[Cfg::WX];
+#pragma unroll
+                for (int c = 0; c < Cfg::WX; ++c) xv[c] = make_float2(x0[c], x0[c + Cfg::WX]);
+                const float *kr = kp + u * Cfg::KW;
+#pragma unroll
+                for (int v = 0; v < Cfg::KW; ++v) {
+                    const float kv = kr[v];
+                    const float2 kk = make_float2(kv, kv);
+#pragma unroll
+                    for (int c = 0; c < Cfg::WO; ++c) acc[c] = __ffma2_rn(xv[c + v], kk, acc[c]);
+                }
+            }
+            float *o = so + p * Cfg::OPL + i * Cfg::WO;
+#pragma unroll
+            for (int c = 0; c < Cfg::WO; ++c) o[c] = acc[c].x;
+            if (i + 1 < Cfg::HO) {
+#pragma unroll
+                for (int c = 0; c < Cfg::WO; ++c) o[Cfg::WO + c] = acc[c].y;
+            }
+        }
+    } else if constexpr (Cfg::PPW > 0) {
         const int lane = tid & 31, pl = lane / Cfg::HO, i = lane - pl * Cfg::HO;
         if (pl < Cfg::PPW) {
             const int p = (tid >> 5) * Cfg::PPW + pl;
@@ -467,7 +509,11 @@ static int launch_staged(const XProblems &P, int n, int B, int C, long long kbs,
 
 //                       KH  KW  HX  WX  circ   G   NT  ST KS spill
 #ifndef HDN_NATIVE_DENSE  // A/B switch: the dense thread = row numbering this shape used before (0.963 ms vs 0.932 ms at batch 512)
-using CfgNative = XCfg<5, 5, 29, 29, false, 8, 256, 2, 1, false, 2, 1>;  // 127/255 crops (HBM-bound), 2 CTAs/SM, a warp = one plane (25 rows)
+#ifndef HDN_NATIVE_ROWPAIR_OFF
+using CfgNative = XCfg<5, 5, 29, 29, false, 8, 128, 2, 1, false, 2, 2, true>;  // 127/255 crops (HBM-bound): 2 CTAs/SM, a warp = two planes x 13 row pairs, FFMA2
+#else
+using CfgNative = XCfg<5, 5, 29, 29, false, 8, 256, 2, 1, false, 2, 1>;  // a warp = one plane (25 rows), scalar FFMA
+#endif
 #else
 using CfgNative = XCfg<5, 5, 29, 29, false, 8, 224, 2, 1, false, 2>;
 #endif
