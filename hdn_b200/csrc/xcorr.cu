@@ -41,7 +41,10 @@ struct XCfg {
     static constexpr int XPL = HX * WX, KPL = KH * KW, OPL = HO * WO;
     static constexpr int STAGE_FLOATS = G * (XPL + KPL);
     static constexpr int OUT_FLOATS = G * OPL;
-    static constexpr size_t SMEM = (size_t)(STAGES * STAGE_FLOATS + 2 * OUT_FLOATS) * 4 + STAGES * 8 + 16;
+    // STAGES == 1: single-buffered input and output tile -- half the shared memory per CTA, twice the resident CTAs, which overlap each
+    // other's copies instead of a CTA overlapping its own
+    static constexpr int OUT_BUFS = STAGES == 1 ? 1 : 2;
+    static constexpr size_t SMEM = (size_t)(STAGES * STAGE_FLOATS + OUT_BUFS * OUT_FLOATS) * 4 + STAGES * 8 + 16;
     static_assert(G % 4 == 0, "bulk copies need 16-byte multiples");
     static_assert(!SPILL || (HO == 33 && NT == 32 * G * KSPLIT), "row-spill mapping is for 33-row outputs");
     static_assert(SMEM * CTAS <= 227 * 1024 - 1024 * CTAS, "shared memory budget");
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::CTAS)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *sin = reinterpret_cast<float *>(smem_raw);
     float *sout = sin + Cfg::STAGES * Cfg::STAGE_FLOATS;
-    uint64_t *full = reinterpret_cast<uint64_t *>(sout + 2 * Cfg::OUT_FLOATS);
+    uint64_t *full = reinterpret_cast<uint64_t *>(sout + Cfg::OUT_BUFS * Cfg::OUT_FLOATS);
     const int tid = threadIdx.x;
 
     if (tid == 0) {
@@ -232,11 +235,15 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::CTAS)
     int it = 0;
     for (int g = blockIdx.x; g < n_groups; g += gridDim.x, ++it) {
         const int s = it % Cfg::STAGES;
+        if (Cfg::OUT_BUFS == 1) {  // the previous tile must have left the (only) output buffer before anyone writes it again
+            if (tid == 0) bulk_wait_read<0>();
+            __syncthreads();
+        }
         mbar_wait(&full[s], (it / Cfg::STAGES) & 1);
         const float *sx = sin + s * Cfg::STAGE_FLOATS;
-        float *so = sout + (it & 1) * Cfg::OUT_FLOATS;
+        float *so = sout + (Cfg::OUT_BUFS == 2 ? (it & 1) * Cfg::OUT_FLOATS : 0);
         compute_group<Cfg>(sx, sx + Cfg::G * Cfg::XPL, so, tid);
-        if (tid == 0) bulk_wait_read<0>();  // store of iteration it-1 has left its buffer (reused at it+1)
+        if (Cfg::OUT_BUFS == 2 && tid == 0) bulk_wait_read<0>();  // store of iteration it-1 has left its buffer (reused at it+1)
         fence_proxy_async_smem();           // my so[] writes -> visible to the TMA store
         __syncthreads();                    // all rows written; all reads of stage s finished
         if (tid == 0) {
@@ -510,7 +517,11 @@ static int launch_staged(const XProblems &P, int n, int B, int C, long long kbs,
 //                       KH  KW  HX  WX  circ   G   NT  ST KS spill
 #ifndef HDN_NATIVE_DENSE  // A/B switch: the dense thread = row numbering this shape used before (0.963 ms vs 0.932 ms at batch 512)
 #ifndef HDN_NATIVE_ROWPAIR_OFF
-using CfgNative = XCfg<5, 5, 29, 29, false, 8, 128, 2, 1, false, 2, 2, true>;  // 127/255 crops (HBM-bound): 2 CTAs/SM, a warp = two planes x 13 row pairs, FFMA2
+#ifndef HDN_NATIVE_STAGES
+#define HDN_NATIVE_STAGES 1
+#endif
+// 127/255 crops (HBM-bound): a warp = two planes x 13 row pairs, FFMA2; single-buffered 4-warp CTAs, four per SM
+using CfgNative = XCfg<5, 5, 29, 29, false, 8, 128, HDN_NATIVE_STAGES, 1, false, HDN_NATIVE_STAGES == 1 ? 4 : 2, 2, true>;
 #else
 using CfgNative = XCfg<5, 5, 29, 29, false, 8, 256, 2, 1, false, 2, 1>;  // a warp = one plane (25 rows), scalar FFMA
 #endif
