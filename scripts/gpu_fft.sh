@@ -1,5 +1,5 @@
 #!/bin/bash
-# GPU pass for the FFT correlation kernel: parity tests, A/B bench (FFT vs direct, 2-plane vs 4-plane groups), ncu --set full.
+# GPU pass for the transform-domain correlation kernel: parity tests, A/B bench (vs the direct kernels), ncu --set full.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "xcorr or fft" > gpurun_out/pytest_fft.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_fft.log
@@ -7,12 +7,9 @@ tail -5 gpurun_out/pytest_fft.log
 timeout 300 python bench.py --no-cpu --no-e2e --xcorr-algo direct > gpurun_out/bench_direct.json 2> gpurun_out/bench_fft.err
 timeout 300 python bench.py --no-cpu --no-e2e > gpurun_out/bench_fft.json 2>> gpurun_out/bench_fft.err
 timeout 300 python bench.py --no-cpu --no-e2e --workload win15 --xcorr-algo fft > gpurun_out/bench_fft_win15.json 2>> gpurun_out/bench_fft.err
-if [ -f build/libhdn_b200_g4.so ]; then
-  HDN_B200_LIB=$PWD/build/libhdn_b200_g4.so timeout 300 python bench.py --no-cpu --no-e2e > gpurun_out/bench_fft_g4.json 2>> gpurun_out/bench_fft.err
-fi
 python - <<'PY'
 import json
-for f in ("bench_direct", "bench_fft", "bench_fft_g4", "bench_fft_win15"):
+for f in ("bench_direct", "bench_fft", "bench_fft_win15"):
     try:
         d = json.load(open("gpurun_out/%s.json" % f))
         print(f, "value %.0f" % d["value"], "ms/step %.3f" % d["ms_per_step"], {k: round(v, 3) for k, v in d["roofline"]["kernel_ms"].items()})
