@@ -207,27 +207,41 @@ HDN_HD int fftc_tasks(int ph) {
 // ---- column stage ----------------------------------------------------------------------------------------------------------
 // conj c~(i,f) = sum_u conj X'(i+u,f) * K'(u,f)  for the SEG output rows of the task's segment.  NTAP taps per block; the
 // SEG + NTAP - 1 input rows of a block are held in registers (one shared load feeds ~NTAP complex MACs).  A complex MAC costs
-// THREE FFMAs (Gauss): with  a1 = sum xr*kr,  a2 = sum xi*ki,  a3 = sum (xr + xi)*(kr - ki)
+// THREE FMAs (Gauss), issued as 1.5 packed FFMA2: with  a1 = sum xr*kr,  a2 = sum xi*ki,  a3 = sum (xr + xi)*(kr - ki)
 //     Re = a1 + a2,    Im(x * conj k) = a3 - a1 + a2        (the stored conjugate has the imaginary part a1 - a2 - a3).
 // Slot 0 (f == 0) packs two REAL columns (f = 0 in .x, f = 32 in .y) whose products must not mix: it simply keeps (a1, -a2).
+// d = a * b + c on both halves: one packed FFMA2 (fma.rn.f32x2) on sm_100, i.e. one issue slot for two FMAs
+HDN_HD float2 fftc_fma2(float2 a, float2 b, float2 c) {
+#if defined(__CUDA_ARCH__)
+    return __ffma2_rn(a, b, c);
+#else
+    return float2{a.x * b.x + c.x, a.y * b.y + c.y};
+#endif
+}
+
+// Accumulators: a12[i] = (a1, a2) of output row i  -- its update is ONE FFMA2 of the loaded pairs (xr, xi) * (kr, ki);
+//               a3p[m] = a3 of rows (2m, 2m+1)     -- one FFMA2 of (xs[d], xs[d+1]) * (kd, kd), xs = xr + xi kept as overlapping pairs
 template <class Cfg, int NTAP>
-HDN_HD void fftc_col_block(const float2 *xc, const float2 *kc, int u0, float (&a1)[Cfg::SEG], float (&a2)[Cfg::SEG], float (&a3)[Cfg::SEG]) {
-    float wr[Cfg::SEG + NTAP - 1], wi[Cfg::SEG + NTAP - 1], ws[Cfg::SEG + NTAP - 1];
+HDN_HD void fftc_col_block(const float2 *xc, const float2 *kc, int u0, float2 (&a12)[Cfg::SEG], float2 (&a3p)[(Cfg::SEG + 1) / 2]) {
+    constexpr int NW = Cfg::SEG + NTAP - 1;
+    float2 w[NW], ws2[NW];
 #pragma unroll
-    for (int d = 0; d < Cfg::SEG + NTAP - 1; ++d) {
-        const float2 t = xc[(u0 + d) * Cfg::PITCH];
-        wr[d] = t.x; wi[d] = t.y; ws[d] = t.x + t.y;
+    for (int d = 0; d < NW; ++d) {
+        w[d] = xc[(u0 + d) * Cfg::PITCH];
+        const float sum = w[d].x + w[d].y;
+        ws2[d].x = sum;
+        ws2[d].y = 0.f;
+        if (d > 0) ws2[d - 1].y = sum;
     }
 #pragma unroll
     for (int tt = 0; tt < NTAP; ++tt) {
         const float2 k = kc[(u0 + tt) * Cfg::PITCH];
         const float kd = k.x - k.y;
+        const float2 kdd = float2{kd, kd};
 #pragma unroll
-        for (int i = 0; i < Cfg::SEG; ++i) {
-            a1[i] = wr[i + tt] * k.x + a1[i];
-            a2[i] = wi[i + tt] * k.y + a2[i];
-            a3[i] = ws[i + tt] * kd + a3[i];
-        }
+        for (int i = 0; i < Cfg::SEG; ++i) a12[i] = fftc_fma2(w[i + tt], k, a12[i]);
+#pragma unroll
+        for (int m = 0; m < (Cfg::SEG + 1) / 2; ++m) a3p[m] = fftc_fma2(ws2[2 * m + tt], kdd, a3p[m]);  // odd SEG: the last .y is never used
     }
 }
 
@@ -237,19 +251,23 @@ HDN_HD void fftc_col(const FftBufs &b, int task) {
     const int p = ws / Cfg::NSEG, i0 = (ws - p * Cfg::NSEG) * Cfg::SEG;
     const float2 *xc = b.XR + p * Cfg::XR_PLANE + i0 * Cfg::PITCH + f;
     const float2 *kc = b.KR + p * Cfg::KR_PLANE + f;
-    float a1[Cfg::SEG], a2[Cfg::SEG], a3[Cfg::SEG];
+    float2 a12[Cfg::SEG], a3p[(Cfg::SEG + 1) / 2];
 #pragma unroll
-    for (int i = 0; i < Cfg::SEG; ++i) a1[i] = a2[i] = a3[i] = 0.f;
+    for (int i = 0; i < Cfg::SEG; ++i) a12[i] = float2{0.f, 0.f};
+#pragma unroll
+    for (int m = 0; m < (Cfg::SEG + 1) / 2; ++m) a3p[m] = float2{0.f, 0.f};
     constexpr int FULL = Cfg::KH / Cfg::TB * Cfg::TB, REM = Cfg::KH - FULL;
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
-    for (int u0 = 0; u0 < FULL; u0 += Cfg::TB) fftc_col_block<Cfg, Cfg::TB>(xc, kc, u0, a1, a2, a3);
-    if (REM > 0) fftc_col_block<Cfg, (REM > 0 ? REM : 1)>(xc, kc, FULL, a1, a2, a3);
+    for (int u0 = 0; u0 < FULL; u0 += Cfg::TB) fftc_col_block<Cfg, Cfg::TB>(xc, kc, u0, a12, a3p);
+    if (REM > 0) fftc_col_block<Cfg, (REM > 0 ? REM : 1)>(xc, kc, FULL, a12, a3p);
     float2 *ct = b.CT + p * Cfg::CT_PLANE + i0 * Cfg::PITCH + f;
 #pragma unroll
-    for (int i = 0; i < Cfg::SEG; ++i)
-        if (i0 + i < Cfg::HO) ct[i * Cfg::PITCH] = f == 0 ? float2{a1[i], -a2[i]} : float2{a1[i] + a2[i], a1[i] - a2[i] - a3[i]};
+    for (int i = 0; i < Cfg::SEG; ++i) {
+        const float a1 = a12[i].x, a2 = a12[i].y, a3 = (i & 1) ? a3p[i / 2].y : a3p[i / 2].x;
+        if (i0 + i < Cfg::HO) ct[i * Cfg::PITCH] = f == 0 ? float2{a1, -a2} : float2{a1 + a2, a1 - a2 - a3};
+    }
 }
 
 }  // namespace hdn
