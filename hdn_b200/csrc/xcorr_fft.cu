@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::CTAS)
 #pragma unroll 1
             for (int t0 = 0; t0 < ntask; t0 += Cfg::NT) {
                 const int t = t0 + tid;
-                const int h = fft_task_half(t), unit = fft_task_unit(t);
+                const int h = fft_task_half<Cfg>(ph, t), unit = fft_task_unit<Cfg>(ph, t);
                 float re[32], im[32];
                 if (t < ntask && fftc_load<Cfg>(ph, bufs, unit, h, re, im)) {
                     if (h) fft::half_twiddle(re, im);

@@ -63,7 +63,10 @@ struct FCfg {
     static constexpr int R_UNITS = G * R_UNITS_PLANE, O_UNITS = (G / 2) * HO;
     static constexpr int pad32(int n) { return (n + 31) / 32 * 32; }
     // FFT tasks = (unit, half); warps alternate halves so a warp runs one half only:  task t -> h = (t/32) % 2, unit = (t/64)*32 + t%32
-    static constexpr int R_TASKS = 2 * pad32(R_UNITS), O_TASKS = 2 * pad32(O_UNITS), COL_TASKS = G * NSEG * 32;
+    // Phase O with 33 units would fill 2 + 2 warps, the last two with one lane each: its tasks are numbered densely instead
+    // (h = t / units), one warp then mixes both halves (it runs the h = 1 twiddles predicated) and a warp is saved.
+    static constexpr bool O_DENSE = pad32(2 * O_UNITS) < 2 * pad32(O_UNITS);
+    static constexpr int R_TASKS = 2 * pad32(R_UNITS), O_TASKS = O_DENSE ? pad32(2 * O_UNITS) : 2 * pad32(O_UNITS), COL_TASKS = G * NSEG * 32;
     // the output tile is staged over XR (dead once the column stage is done)
     static_assert((unsigned long long)G * XR_PLANE * 8 >= (unsigned long long)OUT_FLOATS * 4, "output tile must fit the XR region it aliases");
     static constexpr unsigned long long SMEM = (unsigned long long)RAW_FLOATS * 4 + (unsigned long long)G * (XR_PLANE + KR_PLANE + CT_PLANE) * 8 + 16;
@@ -82,8 +85,14 @@ struct FftBufs {
 
 enum { FFT_PH_R = 0, FFT_PH_O = 1, FFT_PHASES = 2 };
 
-HDN_HD int fft_task_half(int t) { return (t >> 5) & 1; }
-HDN_HD int fft_task_unit(int t) { return ((t >> 6) << 5) | (t & 31); }
+template <class Cfg>
+HDN_HD int fft_task_half(int ph, int t) {
+    return (ph == FFT_PH_O && Cfg::O_DENSE) ? (t >= Cfg::O_UNITS ? 1 : 0) : (t >> 5) & 1;
+}
+template <class Cfg>
+HDN_HD int fft_task_unit(int ph, int t) {  // may be >= the phase's unit count: fftc_load() rejects it
+    return (ph == FFT_PH_O && Cfg::O_DENSE) ? (t >= Cfg::O_UNITS ? t - Cfg::O_UNITS : t) : ((t >> 6) << 5) | (t & 31);
+}
 
 // source row of padded row r (circular rows for K2)
 template <class Cfg>

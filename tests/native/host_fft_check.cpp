@@ -28,7 +28,7 @@ static void run_group(const std::vector<float> &raw, std::vector<float> &out, bo
     auto fft_phase = [&](int ph) {
         const int ntask = fftc_tasks<Cfg>(ph);
         for (int s = 0; s < ntask; ++s) {
-            const int t = order(s, ntask), h = fft_task_half(t), unit = fft_task_unit(t);
+            const int t = order(s, ntask), h = fft_task_half<Cfg>(ph, t), unit = fft_task_unit<Cfg>(ph, t);
             Regs r;
             if (!fftc_load<Cfg>(ph, b, unit, h, r.re, r.im)) continue;
             if (h) fft::half_twiddle(r.re, r.im);
