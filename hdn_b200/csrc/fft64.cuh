@@ -5,9 +5,8 @@
 //
 // Decimation in frequency: half h in {0,1} owns the outputs X[2m + h] = FFT32(s)[m] with
 //   s[n] = a[n] + a[n+32]  (h = 0),     s[n] = (a[n] - a[n+32]) * W64^n  (h = 1),      n < 32.
-// The caller forms a[n] +- a[n+32] while loading (one FFMA2 per complex value with the sign as a warp-uniform operand), applies
-// half_twiddle() when h = 1 and runs fft32_fwd(): a radix-4 x 8 FFT on float2 (re, im) register pairs with the packed fp32x2
-// instructions of sm_100 (a complex add or subtract is one issue slot), fully unrolled, twiddles are compile-time immediates
+// The caller forms a[n] +- a[n+32] while loading (one FFMA per value with the sign as a warp-uniform operand), applies
+// half_twiddle() when h = 1 and runs fft32_fwd(): a radix-4 x 8 FFT, fully unrolled, twiddles are compile-time immediates
 // (n = 8a + b, m = c + 4d:  W32^(mn) = W4^(ac) * W32^(bc) * W8^(bd)).  Y[m] is left at POS32(m) = 8*(m%4) + m/4, i.e.
 // X[f] of the owning half at HPOS(f).
 //
@@ -18,12 +17,6 @@
 #define HDN_HD __host__ __device__ __forceinline__
 #else
 #define HDN_HD inline
-#endif
-
-#if !defined(__CUDACC__)
-struct float2 {
-    float x, y;
-};
 #endif
 
 namespace hdn {
@@ -54,123 +47,110 @@ HDN_HD constexpr float cos64(int k) {
 }
 HDN_HD constexpr float sin64(int k) { return cos64(k - 16); }
 
-// ---- packed fp32x2 arithmetic: a complex value is a float2 (re, im) in an aligned register pair; sm_100 adds / multiplies /
-//      FMAs both halves with ONE instruction (add.f32x2, mul.f32x2, fma.rn.f32x2 -> FADD2 / FMUL2 / FFMA2), i.e. one issue slot
-HDN_HD float2 f2(float x, float y) { return float2{x, y}; }
-HDN_HD float2 fma2(float2 a, float2 b, float2 c) {  // a * b + c
-#if defined(__CUDA_ARCH__)
-    return __ffma2_rn(a, b, c);
-#else
-    return float2{a.x * b.x + c.x, a.y * b.y + c.y};
-#endif
-}
-HDN_HD float2 add2(float2 a, float2 b) {
-#if defined(__CUDA_ARCH__)
-    return __fadd2_rn(a, b);
-#else
-    return float2{a.x + b.x, a.y + b.y};
-#endif
-}
-HDN_HD float2 mul2(float2 a, float2 b) {
-#if defined(__CUDA_ARCH__)
-    return __fmul2_rn(a, b);
-#else
-    return float2{a.x * b.x, a.y * b.y};
-#endif
-}
-HDN_HD float2 sub2(float2 a, float2 b) { return fma2(b, f2(-1.f, -1.f), a); }
-HDN_HD float2 swp(float2 a) { return float2{a.y, a.x}; }
-HDN_HD float2 add_mi(float2 a, float2 t) { return fma2(swp(t), f2(1.f, -1.f), a); }  // a + (-i) * t
-HDN_HD float2 add_pi(float2 a, float2 t) { return fma2(swp(t), f2(-1.f, 1.f), a); }  // a + (+i) * t
-
-// z * exp(-2*pi*i * K / 64)
-template <int K>
-HDN_HD float2 twiddle(float2 z) {
+// (r, i) *= exp(S * 2*pi*i * K / 64)
+template <int S, int K>
+HDN_HD void twiddle(float &r, float &i) {
     constexpr int k = K & 63;
-    if (k == 0) return z;
-    if (k == 16) return float2{z.y, -z.x};
-    if (k == 32) return float2{-z.x, -z.y};
-    if (k == 48) return float2{-z.y, z.x};
-    constexpr float c = cos64(k), s = sin64(k);  // (r + i*m)(c - i*s) = (r*c + m*s) + i*(m*c - r*s)
-    return fma2(swp(z), f2(s, -s), mul2(z, f2(c, c)));
+    if (k == 0) return;
+    if (k == 16) { const float t = r; r = -S * i; i = S * t; return; }
+    if (k == 32) { r = -r; i = -i; return; }
+    if (k == 48) { const float t = r; r = S * i; i = -S * t; return; }
+    constexpr float c = cos64(k), s = S * sin64(k);
+    const float t = r * c - i * s;
+    i = r * s + i * c;
+    r = t;
 }
 
-// (s[N]) *= W64^N, N = 1..31: the h = 1 half's twiddles
+// 8-point DFT, in place, natural order in and out.  NA = number of leading non-zero inputs (4 or 8).
+template <int S, int NA = 8, bool REAL = false>
+HDN_HD void dft8(float (&r)[8], float (&i)[8]) {
+    constexpr float H = 0.70710678118654752440f;
+    float a0r, a1r, a2r, a3r, a4r, a5r, a6r, a7r, a0i, a1i, a2i, a3i, a4i, a5i, a6i, a7i;
+    if (NA <= 4) {  // x4..x7 = 0
+        a0r = a1r = r[0]; a2r = a3r = r[2]; a4r = a5r = r[1]; a6r = a7r = r[3];
+        a0i = a1i = i[0]; a2i = a3i = i[2]; a4i = a5i = i[1]; a6i = a7i = i[3];
+    } else {
+        a0r = r[0] + r[4]; a1r = r[0] - r[4]; a2r = r[2] + r[6]; a3r = r[2] - r[6];
+        a4r = r[1] + r[5]; a5r = r[1] - r[5]; a6r = r[3] + r[7]; a7r = r[3] - r[7];
+        a0i = i[0] + i[4]; a1i = i[0] - i[4]; a2i = i[2] + i[6]; a3i = i[2] - i[6];
+        a4i = i[1] + i[5]; a5i = i[1] - i[5]; a6i = i[3] + i[7]; a7i = i[3] - i[7];
+    }
+    if (REAL) a0i = a1i = a2i = a3i = a4i = a5i = a6i = a7i = 0.f;
+    // even outputs: DFT4 of (a0, a4, a2, a6);  W4 = S*i
+    const float b0r = a0r + a2r, b0i = a0i + a2i, b1r = a0r - a2r, b1i = a0i - a2i;
+    const float b2r = a4r + a6r, b2i = a4i + a6i, b3r = a4r - a6r, b3i = a4i - a6i;
+    r[0] = b0r + b2r; i[0] = b0i + b2i;
+    r[4] = b0r - b2r; i[4] = b0i - b2i;
+    r[2] = b1r - S * b3i; i[2] = b1i + S * b3r;  // b1 + (S*i)*b3
+    r[6] = b1r + S * b3i; i[6] = b1i - S * b3r;
+    // odd outputs: DFT4 of (z0, z1, z2, z3) = (a1, a5*W8, a3*W4, a7*W8^3)
+    const float z1r = H * (a5r - S * a5i), z1i = H * (a5i + S * a5r);    // a5 * (1 + S*i)/sqrt2
+    const float z3r = H * (-a7r - S * a7i), z3i = H * (-a7i + S * a7r);  // a7 * (-1 + S*i)/sqrt2
+    const float z2r = -S * a3i, z2i = S * a3r;                           // a3 * (S*i)
+    const float c0r = a1r + z2r, c0i = a1i + z2i, c1r = a1r - z2r, c1i = a1i - z2i;
+    const float c2r = z1r + z3r, c2i = z1i + z3i, c3r = z1r - z3r, c3i = z1i - z3i;
+    r[1] = c0r + c2r; i[1] = c0i + c2i;
+    r[5] = c0r - c2r; i[5] = c0i - c2i;
+    r[3] = c1r - S * c3i; i[3] = c1i + S * c3r;
+    r[7] = c1r + S * c3i; i[7] = c1i - S * c3r;
+}
+
+// (s[N]) *= W64^(-N), N = 1..31: the h = 1 half's twiddles
 template <int N = 1>
 struct HalfTw {
-    static HDN_HD void run(float2 (&s)[32]) {
-        s[N] = twiddle<N>(s[N]);
-        HalfTw<N + 1>::run(s);
+    static HDN_HD void run(float (&re)[32], float (&im)[32]) {
+        twiddle<-1, N>(re[N], im[N]);
+        HalfTw<N + 1>::run(re, im);
     }
 };
 template <>
 struct HalfTw<32> {
-    static HDN_HD void run(float2 (&)[32]) {}
+    static HDN_HD void run(float (&)[32], float (&)[32]) {}
 };
-HDN_HD void half_twiddle(float2 (&s)[32]) { HalfTw<>::run(s); }
-
-// forward DFTs, in place, natural order in and out;  W4 = -i, W8 = (1 - i)/sqrt2, W8^3 = (-1 - i)/sqrt2
-HDN_HD void dft4_fwd(float2 (&v)[4]) {
-    const float2 b0 = add2(v[0], v[2]), b1 = sub2(v[0], v[2]), b2 = add2(v[1], v[3]), b3 = sub2(v[1], v[3]);
-    v[0] = add2(b0, b2);
-    v[2] = sub2(b0, b2);
-    v[1] = add_mi(b1, b3);
-    v[3] = add_pi(b1, b3);
-}
-
-HDN_HD void dft8_fwd(float2 (&v)[8]) {
-    constexpr float H = 0.70710678118654752440f;
-    const float2 a0 = add2(v[0], v[4]), a1 = sub2(v[0], v[4]), a2 = add2(v[2], v[6]), a3 = sub2(v[2], v[6]);
-    const float2 a4 = add2(v[1], v[5]), a5 = sub2(v[1], v[5]), a6 = add2(v[3], v[7]), a7 = sub2(v[3], v[7]);
-    // even outputs: DFT4 of (a0, a4, a2, a6)
-    const float2 b0 = add2(a0, a2), b1 = sub2(a0, a2), b2 = add2(a4, a6), b3 = sub2(a4, a6);
-    v[0] = add2(b0, b2);
-    v[4] = sub2(b0, b2);
-    v[2] = add_mi(b1, b3);
-    v[6] = add_pi(b1, b3);
-    // odd outputs: DFT4 of (a1, a5*W8, a3*W4, a7*W8^3)
-    const float2 z1 = fma2(swp(a5), f2(H, -H), mul2(a5, f2(H, H)));    // H * (a5 + (-i)*a5)
-    const float2 z3 = fma2(swp(a7), f2(H, -H), mul2(a7, f2(-H, -H)));  // H * ((-i)*a7 - a7)
-    const float2 c0 = add_mi(a1, a3), c1 = add_pi(a1, a3);             // a1 +- (-i)*a3
-    const float2 c2 = add2(z1, z3), c3 = sub2(z1, z3);
-    v[1] = add2(c0, c2);
-    v[5] = sub2(c0, c2);
-    v[3] = add_mi(c1, c3);
-    v[7] = add_pi(c1, c3);
-}
+HDN_HD void half_twiddle(float (&re)[32], float (&im)[32]) { HalfTw<>::run(re, im); }
 
 // 32-point forward FFT, natural order in, Y[m] left at POS32(m).
 HDN_HD constexpr int POS32(int m) { return 8 * (m & 3) + (m >> 2); }
 
+HDN_HD void dft4_fwd(float (&r)[4], float (&i)[4]) {  // W4 = -i
+    const float b0r = r[0] + r[2], b0i = i[0] + i[2], b1r = r[0] - r[2], b1i = i[0] - i[2];
+    const float b2r = r[1] + r[3], b2i = i[1] + i[3], b3r = r[1] - r[3], b3i = i[1] - i[3];
+    r[0] = b0r + b2r; i[0] = b0i + b2i;
+    r[2] = b0r - b2r; i[2] = b0i - b2i;
+    r[1] = b1r + b3i; i[1] = b1i - b3r;  // b1 + (-i)*b3
+    r[3] = b1r - b3i; i[3] = b1i + b3r;
+}
+
 template <int B = 0>
 struct Pass32 {  // for each b: DFT4 over a (stride 8), twiddle by W32^(bc) = W64^(2bc), result at [8c + b]
-    static HDN_HD void run(float2 (&s)[32]) {
-        float2 v[4];
+    static HDN_HD void run(float (&re)[32], float (&im)[32]) {
+        float r[4], i[4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) v[a] = s[8 * a + B];
-        dft4_fwd(v);
-        s[B] = v[0];
-        s[8 + B] = twiddle<2 * B * 1>(v[1]);
-        s[16 + B] = twiddle<2 * B * 2>(v[2]);
-        s[24 + B] = twiddle<2 * B * 3>(v[3]);
-        Pass32<B + 1>::run(s);
+        for (int a = 0; a < 4; ++a) { r[a] = re[8 * a + B]; i[a] = im[8 * a + B]; }
+        dft4_fwd(r, i);
+        twiddle<-1, 2 * B * 1>(r[1], i[1]);
+        twiddle<-1, 2 * B * 2>(r[2], i[2]);
+        twiddle<-1, 2 * B * 3>(r[3], i[3]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { re[8 * c + B] = r[c]; im[8 * c + B] = i[c]; }
+        Pass32<B + 1>::run(re, im);
     }
 };
 template <>
 struct Pass32<8> {
-    static HDN_HD void run(float2 (&)[32]) {}
+    static HDN_HD void run(float (&)[32], float (&)[32]) {}
 };
 
-HDN_HD void fft32_fwd(float2 (&s)[32]) {
-    Pass32<>::run(s);
+HDN_HD void fft32_fwd(float (&re)[32], float (&im)[32]) {
+    Pass32<>::run(re, im);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {  // DFT8 over b of the block [8c + b] -> [8c + d] = Y[c + 4d]
-        float2 v[8];
+        float r[8], i[8];
 #pragma unroll
-        for (int b = 0; b < 8; ++b) v[b] = s[8 * c + b];
-        dft8_fwd(v);
+        for (int b = 0; b < 8; ++b) { r[b] = re[8 * c + b]; i[b] = im[8 * c + b]; }
+        dft8<-1>(r, i);
 #pragma unroll
-        for (int d = 0; d < 8; ++d) s[8 * c + d] = v[d];
+        for (int d = 0; d < 8; ++d) { re[8 * c + d] = r[d]; im[8 * c + d] = i[d]; }
     }
 }
 

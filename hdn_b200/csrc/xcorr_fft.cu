@@ -69,11 +69,11 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::CTAS)
             for (int t0 = 0; t0 < ntask; t0 += Cfg::NT) {
                 const int t = t0 + tid;
                 const int h = fft_task_half<Cfg>(ph, t), unit = fft_task_unit<Cfg>(ph, t);
-                float2 s[32];
-                if (t < ntask && fftc_load<Cfg>(ph, bufs, unit, h, s)) {
-                    if (h) fft::half_twiddle(s);
-                    fft::fft32_fwd(s);
-                    fftc_store<Cfg>(ph, bufs, unit, h, s);
+                float re[32], im[32];
+                if (t < ntask && fftc_load<Cfg>(ph, bufs, unit, h, re, im)) {
+                    if (h) fft::half_twiddle(re, im);
+                    fft::fft32_fwd(re, im);
+                    fftc_store<Cfg>(ph, bufs, unit, h, re, im);
                 }
             }
             __syncthreads();

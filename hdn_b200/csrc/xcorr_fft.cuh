@@ -27,6 +27,12 @@
 #pragma once
 #include "fft64.cuh"
 
+#if !defined(__CUDACC__)
+struct float2 {
+    float x, y;
+};
+#endif
+
 #ifndef HDN_FFT_TB
 #define HDN_FFT_TB 8  // taps per register-window block of the column stage (build-time tunable)
 #endif
@@ -100,40 +106,37 @@ HDN_HD int fft_src_row(int r) {
 }
 
 // ---- loads: the 64 complex inputs a[n] of the unit's transform, folded on the fly into the half's 32 values ---------------------
-//      s[n] = a[n] + sgn * a[n+32]      sgn = +1 (h = 0) / -1 (h = 1), one packed FFMA2 per complex value
+//      s[n] = a[n] + sgn * a[n+32]      sgn = +1 (h = 0) / -1 (h = 1), one FFMA per value; 64 live registers instead of 128
 template <class Cfg>
-HDN_HD int fft_col_of(int n) {  // source column of padded column n (compile-time after unrolling): replicate padding
-    const int q = n - Cfg::PW;
-    return q < 0 ? 0 : (q > Cfg::WX - 1 ? Cfg::WX - 1 : q);
+HDN_HD void fftc_fold_row(const float *row, bool valid, float sgn, float (&s)[32]) {  // a[n] = padded row, zero past WP
+#pragma unroll
+    for (int n = 0; n < 32; ++n) {
+        int q = n - Cfg::PW, q2 = n + 32 - Cfg::PW;  // compile-time: replicate padding of the columns
+        q = q < 0 ? 0 : (q > Cfg::WX - 1 ? Cfg::WX - 1 : q);
+        q2 = q2 < 0 ? 0 : (q2 > Cfg::WX - 1 ? Cfg::WX - 1 : q2);
+        const float lo = (n < Cfg::WP && valid) ? row[q] : 0.f;
+        s[n] = (n + 32 < Cfg::WP && valid) ? row[q2] * sgn + lo : lo;
+    }
 }
 
 template <class Cfg>
-HDN_HD bool fftc_load(int ph, const FftBufs &b, int unit, int h, float2 (&s)[32]) {
-    using namespace fft;
+HDN_HD bool fftc_load(int ph, const FftBufs &b, int unit, int h, float (&re)[32], float (&im)[32]) {
     const float sgn = h ? -1.f : 1.f;
-    const float2 sg = f2(sgn, sgn);
     if (ph == FFT_PH_R) {
         if (unit >= Cfg::R_UNITS) return false;
         const int p = unit / Cfg::R_UNITS_PLANE, j = unit - p * Cfg::R_UNITS_PLANE;
-        const float *xrow = b.rawx + p * Cfg::XPL + fft_src_row<Cfg>(j) * Cfg::WX;
-        if (j < Cfg::KH) {  // z = x_j + i * k_j
+        fftc_fold_row<Cfg>(b.rawx + p * Cfg::XPL + fft_src_row<Cfg>(j) * Cfg::WX, true, sgn, re);
+        if (j < Cfg::KH) {  // (x_j, k_j)
             const float *krow = b.rawk + p * Cfg::KPL + j * Cfg::KW;
 #pragma unroll
             for (int n = 0; n < 32; ++n) {
-                const float2 lo = f2(n < Cfg::WP ? xrow[fft_col_of<Cfg>(n)] : 0.f, n < Cfg::KW ? krow[n] : 0.f);
-                const float2 hi = f2(n + 32 < Cfg::WP ? xrow[fft_col_of<Cfg>(n + 32)] : 0.f, n + 32 < Cfg::KW ? krow[n + 32] : 0.f);
-                s[n] = (n + 32 < Cfg::WP || n + 32 < Cfg::KW) ? fma2(hi, sg, lo) : lo;
+                const float lo = n < Cfg::KW ? krow[n] : 0.f;
+                im[n] = n + 32 < Cfg::KW ? krow[n + 32] * sgn + lo : lo;
             }
-        } else {  // z = x_j + i * x_{j + R_PAIRS}
+        } else {  // (x_j, x_{j + R_PAIRS})
             const int r2 = j + Cfg::R_PAIRS;
             const bool has2 = r2 < Cfg::HP;
-            const float *xrow2 = b.rawx + p * Cfg::XPL + fft_src_row<Cfg>(has2 ? r2 : j) * Cfg::WX;
-#pragma unroll
-            for (int n = 0; n < 32; ++n) {
-                const float2 lo = f2(n < Cfg::WP ? xrow[fft_col_of<Cfg>(n)] : 0.f, (n < Cfg::WP && has2) ? xrow2[fft_col_of<Cfg>(n)] : 0.f);
-                const float2 hi = f2(n + 32 < Cfg::WP ? xrow[fft_col_of<Cfg>(n + 32)] : 0.f, (n + 32 < Cfg::WP && has2) ? xrow2[fft_col_of<Cfg>(n + 32)] : 0.f);
-                s[n] = n + 32 < Cfg::WP ? fma2(hi, sg, lo) : lo;
-            }
+            fftc_fold_row<Cfg>(b.rawx + p * Cfg::XPL + fft_src_row<Cfg>(has2 ? r2 : j) * Cfg::WX, has2, sgn, im);
         }
         return true;
     }
@@ -147,17 +150,18 @@ HDN_HD bool fftc_load(int ph, const FftBufs &b, int unit, int h, float2 (&s)[32]
     // s[n] = a[n] + sgn * a[n+32] pairs slot n with slot 32 - n, so n and 32 - n are produced from the same four loads.
     {
         const float2 A = rp[0], C = rq[0];
-        s[0] = f2(A.x - sgn * A.y, sgn * C.y - C.x);
+        re[0] = A.x - sgn * A.y; im[0] = sgn * C.y - C.x;
         const float2 A16 = rp[16], C16 = rq[16];
-        s[16] = f2((A16.x + C16.y) + sgn * (A16.x - C16.y), (A16.y - C16.x) - sgn * (A16.y + C16.x));
+        re[16] = (A16.x + C16.y) + sgn * (A16.x - C16.y);
+        im[16] = (A16.y - C16.x) - sgn * (A16.y + C16.x);
     }
 #pragma unroll
     for (int n = 1; n < 16; ++n) {
         const float2 A = rp[n], C = rq[n], B = rp[32 - n], D = rq[32 - n];
-        const float2 an = f2(A.x + C.y, A.y - C.x), am = f2(A.x - C.y, -A.y - C.x);    // a[n], a[64 - n]
-        const float2 bn = f2(B.x + D.y, B.y - D.x), bm = f2(B.x - D.y, -B.y - D.x);    // a[32 - n], a[32 + n]
-        s[n] = fma2(bm, sg, an);       // a[n] + sgn * a[n + 32]
-        s[32 - n] = fma2(am, sg, bn);  // a[32 - n] + sgn * a[64 - n]
+        const float ar = A.x + C.y, ai = A.y - C.x, amr = A.x - C.y, ami = -A.y - C.x;  // a[n], a[64 - n]
+        const float br = B.x + D.y, bi = B.y - D.x, bmr = B.x - D.y, bmi = -B.y - D.x;  // a[32 - n], a[32 + n]
+        re[n] = bmr * sgn + ar; im[n] = bmi * sgn + ai;            // a[n] + sgn * a[n + 32]
+        re[32 - n] = amr * sgn + br; im[32 - n] = ami * sgn + bi;  // a[32 - n] + sgn * a[64 - n]
     }
     return true;
 }
@@ -165,7 +169,7 @@ HDN_HD bool fftc_load(int ph, const FftBufs &b, int unit, int h, float2 (&s)[32]
 // ---- stores: the half's 32 outputs X[2m + h] are at (re, im)[POS32(m)] ------------------------------------------------------
 // Phase R needs the half as a compile-time constant (the partner X[64 - f] of X[f] sits at a register index that depends on it).
 template <class Cfg, int H>
-HDN_HD void fftc_store_R(const FftBufs &b, int unit, const float2 (&s)[32]) {
+HDN_HD void fftc_store_R(const FftBufs &b, int unit, const float (&re)[32], const float (&im)[32]) {
     using namespace fft;
     const int p = unit / Cfg::R_UNITS_PLANE, j = unit - p * Cfg::R_UNITS_PLANE;
     const bool ktype = j < Cfg::KH;
@@ -173,23 +177,23 @@ HDN_HD void fftc_store_R(const FftBufs &b, int unit, const float2 (&s)[32]) {
     float2 *d2 = ktype ? b.KR + p * Cfg::KR_PLANE + j * Cfg::PITCH : d1 + Cfg::R_PAIRS * Cfg::PITCH;
     const bool has2 = ktype || j + Cfg::R_PAIRS < Cfg::HP;
     if (H == 0) {
-        d1[0] = float2{2.f * s[HPOS(0)].x, 2.f * s[HPOS(32)].x};
-        if (has2) d2[0] = float2{2.f * s[HPOS(0)].y, 2.f * s[HPOS(32)].y};
+        d1[0] = float2{2.f * re[HPOS(0)], 2.f * re[HPOS(32)]};
+        if (has2) d2[0] = float2{2.f * im[HPOS(0)], 2.f * im[HPOS(32)]};
     }
 #pragma unroll
     for (int f = 2 - H; f < 32; f += 2) {  // 2A(f) = Z(f) + conj Z(-f),  2B(f) = (Z(f) - conj Z(-f)) / i
-        const float ar = s[HPOS(f)].x, ai = s[HPOS(f)].y, br = s[HPOS(64 - f)].x, bi = s[HPOS(64 - f)].y;
+        const float ar = re[HPOS(f)], ai = im[HPOS(f)], br = re[HPOS(64 - f)], bi = im[HPOS(64 - f)];
         d1[f] = float2{ar + br, ai - bi};
         if (has2) d2[f] = float2{ai + bi, br - ar};
     }
 }
 
 template <class Cfg>
-HDN_HD void fftc_store(int ph, const FftBufs &b, int unit, int h, const float2 (&s)[32]) {
+HDN_HD void fftc_store(int ph, const FftBufs &b, int unit, int h, const float (&re)[32], const float (&im)[32]) {
     using namespace fft;
     if (ph == FFT_PH_R) {
-        if (h == 0) fftc_store_R<Cfg, 0>(b, unit, s);
-        else fftc_store_R<Cfg, 1>(b, unit, s);
+        if (h == 0) fftc_store_R<Cfg, 0>(b, unit, re, im);
+        else fftc_store_R<Cfg, 1>(b, unit, re, im);
         return;
     }
     const int m = unit / Cfg::HO, i = unit - m * Cfg::HO;
@@ -198,8 +202,8 @@ HDN_HD void fftc_store(int ph, const FftBufs &b, int unit, int h, const float2 (
 #pragma unroll
     for (int mm = 0; 2 * mm < Cfg::WO; ++mm) {
         if (2 * mm + 1 < Cfg::WO || h == 0) {
-            op[2 * mm] = s[POS32(mm)].x * SCALE;
-            oq[2 * mm] = s[POS32(mm)].y * -SCALE;
+            op[2 * mm] = re[POS32(mm)] * SCALE;
+            oq[2 * mm] = im[POS32(mm)] * -SCALE;
         }
     }
 }
@@ -215,6 +219,15 @@ HDN_HD int fftc_tasks(int ph) {
 // THREE FMAs (Gauss), issued as 1.5 packed FFMA2: with  a1 = sum xr*kr,  a2 = sum xi*ki,  a3 = sum (xr + xi)*(kr - ki)
 //     Re = a1 + a2,    Im(x * conj k) = a3 - a1 + a2        (the stored conjugate has the imaginary part a1 - a2 - a3).
 // Slot 0 (f == 0) packs two REAL columns (f = 0 in .x, f = 32 in .y) whose products must not mix: it simply keeps (a1, -a2).
+// d = a * b + c on both halves: one packed FFMA2 (fma.rn.f32x2) on sm_100, i.e. one issue slot for two FMAs
+HDN_HD float2 fftc_fma2(float2 a, float2 b, float2 c) {
+#if defined(__CUDA_ARCH__)
+    return __ffma2_rn(a, b, c);
+#else
+    return float2{a.x * b.x + c.x, a.y * b.y + c.y};
+#endif
+}
+
 // Accumulators: a12[i] = (a1, a2) of output row i  -- its update is ONE FFMA2 of the loaded pairs (xr, xi) * (kr, ki);
 //               a3p[m] = a3 of rows (2m, 2m+1)     -- one FFMA2 of (xs[d], xs[d+1]) * (kd, kd), xs = xr + xi kept as overlapping pairs
 template <class Cfg, int NTAP>
@@ -235,9 +248,9 @@ HDN_HD void fftc_col_block(const float2 *xc, const float2 *kc, int u0, float2 (&
         const float kd = k.x - k.y;
         const float2 kdd = float2{kd, kd};
 #pragma unroll
-        for (int i = 0; i < Cfg::SEG; ++i) a12[i] = fft::fma2(w[i + tt], k, a12[i]);
+        for (int i = 0; i < Cfg::SEG; ++i) a12[i] = fftc_fma2(w[i + tt], k, a12[i]);
 #pragma unroll
-        for (int m = 0; m < (Cfg::SEG + 1) / 2; ++m) a3p[m] = fft::fma2(ws2[2 * m + tt], kdd, a3p[m]);  // odd SEG: the last .y is never used
+        for (int m = 0; m < (Cfg::SEG + 1) / 2; ++m) a3p[m] = fftc_fma2(ws2[2 * m + tt], kdd, a3p[m]);  // odd SEG: the last .y is never used
     }
 }
 

@@ -13,7 +13,7 @@
 using namespace hdn;
 
 struct Regs {
-    float2 s[32];
+    float re[32], im[32];
 };
 
 template <class Cfg>
@@ -30,10 +30,10 @@ static void run_group(const std::vector<float> &raw, std::vector<float> &out, bo
         for (int s = 0; s < ntask; ++s) {
             const int t = order(s, ntask), h = fft_task_half<Cfg>(ph, t), unit = fft_task_unit<Cfg>(ph, t);
             Regs r;
-            if (!fftc_load<Cfg>(ph, b, unit, h, r.s)) continue;
-            if (h) fft::half_twiddle(r.s);
-            fft::fft32_fwd(r.s);
-            fftc_store<Cfg>(ph, b, unit, h, r.s);
+            if (!fftc_load<Cfg>(ph, b, unit, h, r.re, r.im)) continue;
+            if (h) fft::half_twiddle(r.re, r.im);
+            fft::fft32_fwd(r.re, r.im);
+            fftc_store<Cfg>(ph, b, unit, h, r.re, r.im);
         }
     };
     fft_phase(FFT_PH_R);
