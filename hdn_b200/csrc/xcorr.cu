@@ -51,7 +51,8 @@ struct XCfg {
     static_assert(256 % G == 0, "G must divide the network's 256 channels or the staged path is never taken");
     static_assert(PPW == 0 || (KSPLIT == 1 && !SPILL && PPW * ((HX + 2 * PH - KH + 1 + (RP ? 1 : 0)) / (RP ? 2 : 1)) <= 32 && NT * PPW == 32 * G),
                   "warp-per-plane mapping");
-    static_assert(!RP || (PPW == 2 && !CIRC), "row-pair mode: two planes per warp, plain correlation");
+    static_assert(!RP || ((PPW == 2 || PPW == 0) && KSPLIT == 1 && !SPILL && NT >= (PPW == 2 ? 16 * G : G * ((HX + 2 * PH - KH + 2) / 2))),
+                  "row-pair mode: two planes per warp or dense numbering");
 };
 
 // Accumulate kernel rows [u0,u1) of output row i into acc[WO].
@@ -88,28 +89,48 @@ __device__ __forceinline__ void compute_group(const float *__restrict__ sx, cons
     constexpr int ROWS = Cfg::G * Cfg::HO;
     if constexpr (Cfg::RP) {
         constexpr int NP = (Cfg::HO + 1) / 2;  // row pairs per plane
-        const int lane = tid & 31, pl = lane / NP, j = lane - pl * NP;
-        if (pl < 2) {
-            const int p = (tid >> 5) * 2 + pl, i = 2 * j;
+        // PPW == 2: a warp owns two whole planes (lane = plane-in-warp * NP + pair); PPW == 0: dense thread = (plane, pair) numbering
+        int p, j;
+        bool active;
+        if (Cfg::PPW == 2) {
+            const int lane = tid & 31, pl = lane / NP;
+            p = (tid >> 5) * 2 + pl; j = lane - pl * NP; active = pl < 2;
+        } else {
+            p = tid / NP; j = tid - p * NP; active = tid < Cfg::G * NP;
+        }
+        if (active) {
+            const int i = 2 * j;
             const float *xp = sx + p * Cfg::XPL, *kp = sk + p * Cfg::KPL;
             float2 acc[Cfg::WO];
 #pragma unroll
             for (int c = 0; c < Cfg::WO; ++c) acc[c] = make_float2(0.f, 0.f);
 #pragma unroll 1
             for (int u = 0; u < Cfg::KH; ++u) {
-                // rows i+u (-> .x) and i+u+1 (-> .y); for the last, odd row pair the second row lies past the plane: it is read (the
-                // stage buffer continues with the next plane / the templates) and its results are never stored
-                const float *x0 = xp + (i + u) * Cfg::WX;
+                // input rows of output rows i (-> .x) and i+1 (-> .y).  Plain: rows i+u, i+u+1 -- for the last, odd pair the second row lies
+                // past the plane: it is read (the stage buffer continues with the next plane / the templates), its results are never
+                // stored.  Circular: both rows wrap inside the plane.
+                int r0 = i + u - Cfg::PH, r1 = r0 + 1;
+                if (Cfg::CIRC) {
+                    if (r0 < 0) r0 += Cfg::HX;
+                    else if (r0 >= Cfg::HX) r0 -= Cfg::HX;
+                    if (r1 < 0) r1 += Cfg::HX;
+                    else if (r1 >= Cfg::HX) r1 -= Cfg::HX;
+                }
+                const float *x0 = xp + r0 * Cfg::WX, *x1 = xp + r1 * Cfg::WX;
                 float2 xv[Cfg::WX];
 #pragma unroll
-                for (int c = 0; c < Cfg::WX; ++c) xv[c] = make_float2(x0[c], x0[c + Cfg::WX]);
+                for (int c = 0; c < Cfg::WX; ++c) xv[c] = make_float2(x0[c], x1[c]);
                 const float *kr = kp + u * Cfg::KW;
 #pragma unroll
                 for (int v = 0; v < Cfg::KW; ++v) {
                     const float kv = kr[v];
                     const float2 kk = make_float2(kv, kv);
 #pragma unroll
-                    for (int c = 0; c < Cfg::WO; ++c) acc[c] = __ffma2_rn(xv[c + v], kk, acc[c]);
+                    for (int c = 0; c < Cfg::WO; ++c) {
+                        int q = c + v - Cfg::PW;  // compile-time after unrolling: replicate padding of the columns
+                        q = q < 0 ? 0 : (q > Cfg::WX - 1 ? Cfg::WX - 1 : q);
+                        acc[c] = __ffma2_rn(xv[q], kk, acc[c]);
+                    }
                 }
             }
             float *o = so + p * Cfg::OPL + i * Cfg::WO;
@@ -528,8 +549,12 @@ using CfgNative = XCfg<5, 5, 29, 29, false, 8, 256, 2, 1, false, 2, 1>;  // a wa
 #else
 using CfgNative = XCfg<5, 5, 29, 29, false, 8, 224, 2, 1, false, 2>;
 #endif
-// lp branch, 127 crops: FMA-bound (28 flop/B); two planes per warp (26 of 32 lanes) measured slower than the dense numbering (1.207 vs 1.148 ms)
+// lp branch, 127 crops: FMA-bound (28 flop/B).  Row pairs + FFMA2 in the dense numbering (two planes per warp, 26 of 32 lanes, measured slower)
+#ifndef HDN_NATIVE_LP_SCALAR
+using CfgNativeLp = XCfg<13, 13, 13, 13, true, 32, 224, 1, 1, false, 3, 0, true>;  // 32 planes x 7 row pairs; single-buffered, 3 CTAs/SM
+#else
 using CfgNativeLp = XCfg<13, 13, 13, 13, true, 32, 416, 3, 1, false>;
+#endif
 //                     KH  KW  HX  WX  circ   G   NT KS  XP  KP  tail
 using Cfg256 = VCfg<29, 29, 61, 61, false, 4, 256, 2, 68, 36, true>;    // 256/512 crops (FMA-bound), LDS.128 operands
 using Cfg256Lp = VCfg<29, 29, 29, 29, true, 8, 256, 1, 36, 36, false>;  // lp branch, INSTANCE_SIZE=512
