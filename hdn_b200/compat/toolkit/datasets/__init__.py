@@ -23,6 +23,29 @@ class Video:
         if first is None:
             raise FileNotFoundError(self.img_names[0])
         self.height, self.width = first.shape[:2]
+        self.pred_trajs = {}
+        self.tracker_names = []
+
+    def load_tracker(self, path, tracker_names=None, store=True):
+        """Results of `tracker_names` for this video (toolkit/datasets/pot.py:35-67, video.py:31-56): one line of 8 space-separated
+        corner coordinates per frame.  `<path>/<tracker>/<video>.txt` is what tools/test.py:237-243 writes (every frame);
+        `<path>/<tracker>/<video>_<tracker>.txt` is the POT submission layout, of which the reference keeps frame 0 and the odd frames."""
+        if isinstance(tracker_names, str):
+            tracker_names = [tracker_names]
+        for name in tracker_names or sorted(os.listdir(path)):
+            plain = os.path.join(path, name, self.name + ".txt")
+            pot = os.path.join(path, name, "%s_%s.txt" % (self.name, name))
+            src = plain if os.path.exists(plain) else (pot if os.path.exists(pot) else None)
+            if src is None:
+                continue
+            with open(src) as fh:
+                traj = [[float(v) for v in line.replace(",", " ").split()] for line in fh if line.strip()]
+            if src == pot:
+                traj = [x for i, x in enumerate(traj) if i == 0 or i % 2 == 1]
+            if not store:
+                return traj
+            self.pred_trajs[name] = traj
+        self.tracker_names = list(self.pred_trajs)
 
     def __len__(self):
         return len(self.img_names)
@@ -41,6 +64,11 @@ class POTDataset:
         with open(os.path.join(dataset_root, name + ".json")) as fh:
             meta = json.load(fh)
         self.videos = {k: Video(k, dataset_root, v, load_img) for k, v in meta.items()}
+        self.tracker_path, self.tracker_names = None, []
+
+    def set_tracker(self, path, tracker_names):
+        """toolkit/datasets/dataset.py:23-30."""
+        self.tracker_path, self.tracker_names = path, [tracker_names] if isinstance(tracker_names, str) else list(tracker_names)
 
     def __len__(self):
         return len(self.videos)

@@ -33,6 +33,7 @@ def parse():
     ap.add_argument("--graphs", type=int, default=1, help="replay the three network stages from CUDA graphs")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--lockstep", type=int, default=0, help="advance this many sequences per GPU in lock-step (0 = one at a time)")
+    ap.add_argument("--results", default="", help="directory for per-sequence result files (8 corner coordinates per line, the format tools/test.py writes)")
     return ap.parse_args()
 
 
@@ -137,12 +138,36 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.all_reduce(slot)  # disjoint slots -> sum == gather
+    accuracy = None
+    if rank == 0:
+        # accuracy of the gathered trajectories against the synthetic ground truth, scored like the reference's HomoBenchmark
+        # (alignment-error precision, first frame dropped); optionally the result files tools/test.py would write
+        from toolkit.evaluation import HomoBenchmark
+        pred = slot.cpu().numpy()
+
+        class _V:
+            pass
+        videos = []
+        for sid in range(a.sequences):
+            polys = seqs[sid][1] if sid in seqs else synthetic.sequence(100 + sid, a.frames, size=(H, W), obj=(H // 3, W // 3))[1]
+            gt = np.asarray(polys, np.float64).reshape(a.frames, 8)
+            v = _V()
+            v.name, v.gt_traj, v.pred_trajs = "seq%03d" % sid, gt, {"hdn_b200": np.concatenate([gt[:1], pred[sid]], axis=0)}
+            videos.append(v)
+            if a.results:
+                os.makedirs(os.path.join(a.results, "hdn_b200"), exist_ok=True)
+                with open(os.path.join(a.results, "hdn_b200", v.name + ".txt"), "w") as fh:
+                    for x in v.pred_trajs["hdn_b200"]:
+                        fh.write(" ".join(str(float(i)) for i in x) + "\n")
+        bench = HomoBenchmark(type("DS", (list,), {"tracker_names": ["hdn_b200"], "tracker_path": a.results or None})(videos))
+        accuracy = HomoBenchmark.summary(bench.eval_4pts_precision()["hdn_b200"])
     if rank == 0:
         line = {"metric": "tracker frames/sec (hdnTrackerHomo.track_new, native 127/255 crops)", "value": total_frames / wall_max, "unit": "frames/s",
                 "n_gpus": world, "sequences": a.sequences, "frames_per_sequence": a.frames, "frame_size": [H, W],
                 "per_rank_fps": n_frames / busy if busy else None, "ms_per_frame": 1e3 * busy / max(n_frames, 1), "cuda_graphs": bool(a.graphs), "lockstep_per_gpu": a.lockstep,
                 "weights": a.snapshot or "seeded fixture (hdn_b200.synthetic.fill_weights)", "data": "synthetic homography walk",
-                "polygon_checksum": float(slot.abs().sum().item())}
+                "polygon_checksum": float(slot.abs().sum().item()),
+                "accuracy_vs_synthetic_gt": accuracy}
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
