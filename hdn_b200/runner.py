@@ -167,7 +167,8 @@ def main():
                 "per_rank_fps": n_frames / busy if busy else None, "ms_per_frame": 1e3 * busy / max(n_frames, 1), "cuda_graphs": bool(a.graphs), "lockstep_per_gpu": a.lockstep,
                 "weights": a.snapshot or "seeded fixture (hdn_b200.synthetic.fill_weights)", "data": "synthetic homography walk",
                 "polygon_checksum": float(slot.abs().sum().item()),
-                "accuracy_vs_synthetic_gt": accuracy}
+                "accuracy_vs_synthetic_gt": accuracy,
+                "accuracy_note": "HomoBenchmark alignment-error precision; %s" % ("checkpoint " + a.snapshot if a.snapshot else "UNTRAINED seeded weights -- the numbers only exercise the scoring path, parity with the reference on the same weights is what tests/test_gpu_model.py checks")}
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
