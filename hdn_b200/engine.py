@@ -118,6 +118,7 @@ class M1Engine:
         self.graph = None
         self.use_graph = use_graph
         self.launches_per_step = 6 if self.full else 1
+        self.h2d_streams = 1  # run_host: number of upload streams (2 = alternate the copies between two copy engines)
 
     # ---- device-resident path ---------------------------------------------------------------------
     def bind(self, inputs):
@@ -184,7 +185,7 @@ class M1Engine:
                        for k, v in host_inputs.items()}
         self.host_out = {k: ([torch.empty_like(t, device="cpu").pin_memory() for t in v] if isinstance(v, list)
                              else torch.empty_like(v, device="cpu").pin_memory()) for k, v in self.out.items()}
-        self.s_h2d, self.s_cmp, self.s_d2h = (torch.cuda.Stream(device=self.device) for _ in range(3))
+        self.s_h2d, self.s_cmp, self.s_d2h, self.s_h2d2 = (torch.cuda.Stream(device=self.device) for _ in range(4))
         nbytes = lambda d: sum(sum(t.numel() * t.element_size() for t in v) if isinstance(v, list) else v.numel() * v.element_size()  # noqa: E731
                                for v in d.values())
         return nbytes(host_inputs), nbytes(self.host_out)
@@ -194,26 +195,33 @@ class M1Engine:
         while slice i computes and slice i-1 downloads (three streams, events between them)."""
         B = self.B
         cur = torch.cuda.current_stream(self.device)
-        for s in (self.s_h2d, self.s_cmp, self.s_d2h):
+        up = (self.s_h2d, self.s_h2d2) if self.h2d_streams == 2 else (self.s_h2d,)
+        for s in up + (self.s_cmp, self.s_d2h):
             s.wait_stream(cur)
         step = math.ceil(B / chunks)
         shared_done = False
         for lo in range(0, B, step):
             hi = min(B, lo + step)
             hin, din = self._views(host_inputs, lo, hi), self._views(self.dev_in, lo, hi)
-            with torch.cuda.stream(self.s_h2d):
-                for k, v in hin.items():
-                    pairs = zip(din[k], v) if isinstance(v, list) else [(din[k], v)]
-                    for dt, ht in pairs:
-                        if self.shared and k in ("ks", "kl") and shared_done:
-                            continue
+            # uploads alternate between the copy streams: the per-copy set-up of one overlaps the transfer of the other
+            n_copy, ev_ups = 0, []
+            for k, v in hin.items():
+                pairs = zip(din[k], v) if isinstance(v, list) else [(din[k], v)]
+                for dt, ht in pairs:
+                    if self.shared and k in ("ks", "kl") and shared_done:
+                        continue
+                    with torch.cuda.stream(up[n_copy % len(up)]):
                         dt.copy_(ht, non_blocking=True)
-                shared_done = True
-                ev_up = torch.cuda.Event()
-                ev_up.record(self.s_h2d)
+                    n_copy += 1
+            shared_done = True
+            for s in up:
+                ev = torch.cuda.Event()
+                ev.record(s)
+                ev_ups.append(ev)
             dout = self._views(self.out, lo, hi)
             with torch.cuda.stream(self.s_cmp):
-                self.s_cmp.wait_event(ev_up)
+                for ev in ev_ups:
+                    self.s_cmp.wait_event(ev)
                 self._launch(din, dout, hi - lo)
                 ev_c = torch.cuda.Event()
                 ev_c.record(self.s_cmp)
@@ -224,6 +232,6 @@ class M1Engine:
                     pairs = zip(hout[k], v) if isinstance(v, list) else [(hout[k], v)]
                     for ht, dt in pairs:
                         ht.copy_(dt, non_blocking=True)
-        for s in (self.s_h2d, self.s_cmp, self.s_d2h):
+        for s in up + (self.s_cmp, self.s_d2h):
             cur.wait_stream(s)
         return self.host_out
