@@ -8,7 +8,7 @@
 //     planes of odd size start 0 or 8 bytes past a 16-byte boundary, so the copy fetches the enclosing 16-byte-aligned window (it
 //     stays inside the tensor: C % 4 == 0 makes the tensor's own ends aligned) and the phases index from the offset.  The NEXT
 //     group's copies are issued as soon as phase R has consumed the landing buffer, so they fly during the column stage;
-//   * phase R (row FFTs) -> column stage (direct complex correlation per frequency column, a dense FFMA loop) -> phase O
+//   * phase R (row FFTs) -> column stage (direct complex correlation per frequency column, a dense FFMA2 loop) -> phase O
 //     (inverse row FFTs), separated by __syncthreads().  An FFT task = one half of a 64-point FFT, register-resident; R and O
 //     share ONE copy of the half-FFT code (the phase only selects the load / store code around it) -- a fully specialised
 //     straight-line kernel (one FFT body per phase, 130 KB of SASS) spent half of its issue slots waiting for instruction fetch;

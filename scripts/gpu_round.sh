@@ -15,6 +15,8 @@ timeout 400 ncu --set full --clock-control none --import-source on -k regex:xcor
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:xcorr -c 2 -o gpurun_out/prof_xcorr_256_direct -f \
     python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --xcorr-algo direct > gpurun_out/prof_xcorr_direct.log 2>&1
 timeout 300 python bench.py --no-cpu --no-e2e --xcorr-algo direct > gpurun_out/bench_direct.json 2>> gpurun_out/bench.err
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:xcorr -c 2 -o gpurun_out/prof_xcorr_native -f \
+    python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --workload 127/255 --batch 512 > gpurun_out/prof_xcorr_native.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_gemm -c 1 -s 2 -o gpurun_out/prof_conv_gemm -f \
     python scripts/tune/conv_one.py > gpurun_out/prof_conv.log 2>&1
 timeout 300 python -m hdn_b200.runner --sequences 2 --frames 40 > gpurun_out/runner.json 2> gpurun_out/runner.err
