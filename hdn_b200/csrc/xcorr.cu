@@ -89,14 +89,16 @@ __device__ __forceinline__ void compute_group(const float *__restrict__ sx, cons
     constexpr int ROWS = Cfg::G * Cfg::HO;
     if constexpr (Cfg::RP) {
         constexpr int NP = (Cfg::HO + 1) / 2;  // row pairs per plane
-        // PPW == 2: a warp owns two whole planes (lane = plane-in-warp * NP + pair); PPW == 0: dense thread = (plane, pair) numbering
+        // PPW == 2: a warp owns two whole planes (lane = plane-in-warp * NP + pair).
+        // PPW == 0: thread = (pair, plane) with the PLANE in the lane: consecutive lanes are one plane pitch apart, and the pitch of every
+        //           network shape is odd (169 = 9 mod 32), so the 32 lanes of a load hit 32 different banks whatever the row
         int p, j;
         bool active;
         if (Cfg::PPW == 2) {
             const int lane = tid & 31, pl = lane / NP;
             p = (tid >> 5) * 2 + pl; j = lane - pl * NP; active = pl < 2;
         } else {
-            p = tid / NP; j = tid - p * NP; active = tid < Cfg::G * NP;
+            j = tid / Cfg::G; p = tid - j * Cfg::G; active = tid < Cfg::G * NP;
         }
         if (active) {
             const int i = 2 * j;
@@ -549,7 +551,7 @@ using CfgNative = XCfg<5, 5, 29, 29, false, 8, 256, 2, 1, false, 2, 1>;  // a wa
 #else
 using CfgNative = XCfg<5, 5, 29, 29, false, 8, 224, 2, 1, false, 2>;
 #endif
-// lp branch, 127 crops: FMA-bound (28 flop/B).  Row pairs + FFMA2 in the dense numbering (two planes per warp, 26 of 32 lanes, measured slower)
+// lp branch, 127 crops: FMA-bound (28 flop/B).  Row pairs + FFMA2; a warp = one row pair of 32 planes (conflict-free, all lanes busy)
 #ifndef HDN_NATIVE_LP_SCALAR
 using CfgNativeLp = XCfg<13, 13, 13, 13, true, 32, 224, 1, 1, false, 3, 0, true>;  // 32 planes x 7 row pairs; single-buffered, 3 CTAs/SM
 #else
