@@ -314,7 +314,7 @@ def main():
     k1_s = kern_avg["k1"] * 1e-3
     fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
     achieved = k1_bytes / k1_s / 1e9
-    roofline = {"kernel": "%s (K1, 6 problems/launch)" % ("xcorr_fft_kernel: 64x64 FFT correlation" if k1_fft else "xcorr_staged_kernel: direct sum"),
+    roofline = {"kernel": "%s (K1, 6 problems/launch)" % ("xcorr_fft_kernel: transform-domain correlation (row FFTs + per-frequency column correlation)" if k1_fft else "xcorr_staged_kernel: direct sum"),
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic_from_profiles(a.workload, B, k1_fft),
                 "algorithmic_bytes_per_launch": k1_bytes, "launch_ms": kern_avg["k1"],
