@@ -15,17 +15,16 @@ import os
 import torch
 import torch.nn.functional as F
 
-_TAP_CACHE = {}
-
-
-def _tap_major(weight):
-    """[Cout,Cin,3,3] -> [9,Cout,Cin] contiguous, cached per parameter version (load_state_dict / .cuda() invalidate it)."""
-    key = id(weight)
+def _tap_major(conv):
+    """[Cout,Cin,3,3] -> [9,Cout,Cin] contiguous.  Cached ON THE MODULE (it lives and dies with it; a module-level dict keyed by id()
+    could hand a new model the packed weights of a freed one) and re-derived when the parameter changes (load_state_dict,
+    .cuda(), in-place updates bump data_ptr / _version)."""
+    weight = conv.weight
     ver = (weight.data_ptr(), weight._version, weight.device)
-    hit = _TAP_CACHE.get(key)
+    hit = conv.__dict__.get("_hdn_tap_major")
     if hit is None or hit[0] != ver:
         hit = (ver, weight.detach().permute(2, 3, 0, 1).reshape(9, weight.shape[0], weight.shape[1]).contiguous())
-        _TAP_CACHE[key] = hit
+        conv.__dict__["_hdn_tap_major"] = hit
     return hit[1]
 
 
@@ -38,7 +37,7 @@ def wants_shifted_gemm(conv, x):
 def dilated_conv3x3(x, conv):
     """conv(x) for a stride-1 3x3 convolution with padding == dilation, as 9 shifted GEMMs."""
     d = conv.dilation[0]
-    wt = _tap_major(conv.weight)
+    wt = _tap_major(conv)
     B, Cin, H, W = x.shape
     Wp = W + 2 * d
     xp = F.pad(x, (d, d, d, d)).reshape(B, Cin, -1)
@@ -55,21 +54,18 @@ def dilated_conv3x3(x, conv):
     return out.view(B, -1, H, Wp)[:, :, :, :W]
 
 
-_FOLD_CACHE = {}
-
-
 def _folded(conv, bn):
-    """(tensor-core packed weight, scale, shift) of conv -> eval-mode BatchNorm, cached per parameter version."""
-    key = (id(conv), id(bn))
-    ver = (conv.weight.data_ptr(), conv.weight._version, bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
-           bn.running_mean.data_ptr())
-    hit = _FOLD_CACHE.get(key)
+    """(tensor-core packed weight, scale, shift) of conv -> eval-mode BatchNorm.  Stored on the conv module itself (see _tap_major)
+    together with the identity and version of every tensor it was derived from."""
+    ver = (id(bn), conv.weight.data_ptr(), conv.weight._version, bn.weight.data_ptr(), bn.weight._version, bn.bias._version,
+           bn.running_mean._version, bn.running_var._version, bn.running_mean.data_ptr(), bn.running_var.data_ptr(), float(bn.eps))
+    hit = conv.__dict__.get("_hdn_folded")
     if hit is None or hit[0] != ver:
         from hdn_b200 import ops
         scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).detach().float().contiguous()
         shift = (bn.bias - bn.running_mean * scale).detach().float().contiguous()
         hit = (ver, ops.pack_conv_weight(conv.weight), scale, shift)
-        _FOLD_CACHE[key] = hit
+        conv.__dict__["_hdn_folded"] = hit
     return hit[1:]
 
 

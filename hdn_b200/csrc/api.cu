@@ -5,14 +5,14 @@ namespace hdn {
 int64_t g_launches = 0;
 
 int sm_count() {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = 148;  // B200
-        cached = n;
-    }
-    return cached;
+    static int cached[64] = {0};  // per device: a process may drive several GPUs
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev >= 0 && dev < 64 && cached[dev]) return cached[dev];
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;  // B200
+    if (dev >= 0 && dev < 64) cached[dev] = n;
+    return n;
 }
 }  // namespace hdn
 

@@ -14,7 +14,24 @@ inline int launch_status() {
     return e == cudaSuccess ? HDN_OK : (int)e;
 }
 
-int sm_count();  // api.cu (cached per process)
+int sm_count();  // api.cu: SM count of the CURRENT device (cached per device)
+
+// One-time per-DEVICE configuration of a kernel (cudaFuncSetAttribute applies to the current device only, so a process that
+// drives several GPUs must opt in to > 48 KB of dynamic shared memory on each of them).  Benign race: the attribute set is idempotent.
+struct DeviceOnce {
+    unsigned long long done = 0;  // bit d = device d configured (devices >= 64 are simply re-configured every call)
+    template <class F>
+    int run(F &&configure) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return HDN_ERR_DEVICE;
+        const unsigned long long bit = dev < 64 ? 1ull << dev : 0ull;
+        if (bit && (__atomic_load_n(&done, __ATOMIC_ACQUIRE) & bit)) return HDN_OK;
+        const cudaError_t e = configure();
+        if (e != cudaSuccess) return (int)e;
+        if (bit) __atomic_fetch_or(&done, bit, __ATOMIC_RELEASE);
+        return HDN_OK;
+    }
+};
 
 // Up to HDN_MAX_PROBLEMS same-shape correlation problems of one launch (device pointers, passed by value).
 struct XProblems {

@@ -291,12 +291,9 @@ template <int BN, int STAGES, int RAW>
 static int launch_conv_gemm(const ConvGemmArgs &a, int B, cudaStream_t st) {
     constexpr size_t SMEM = (size_t)STAGES * (2 * CG_BM * CG_BK * 4 + 2 * CG_BK * BN * 4) + (size_t)RAW * (CG_BK * BN * 4) + 1024;
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_tf32x3_kernel<BN, STAGES, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
-        if (e != cudaSuccess) return (int)e;
-        configured = true;
-    }
+    static DeviceOnce once;
+    if (int e = once.run([] { return cudaFuncSetAttribute(conv_gemm_tf32x3_kernel<BN, STAGES, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM); }))
+        return e;
     dim3 grid((a.Ho * a.Wo + BN - 1) / BN, a.Cout / CG_BM, B);
     conv_gemm_tf32x3_kernel<BN, STAGES, RAW><<<grid, CG_THREADS + 64, SMEM, st>>>(a);
     count_launch();

@@ -19,7 +19,14 @@ struct Best {
     float s;
 };
 
-__device__ __forceinline__ Best better(const Best &a, const Best &b) { return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a; }
+// np.argmax semantics (the reference's arg-max, hdn_tracker_proj_e2e.py:174): the FIRST maximum, and a NaN counts as the maximum
+// (NumPy propagates it: np.argmax([1, nan, 3]) == 1), so a frame with non-finite scores yields the index NumPy would, never an
+// out-of-range one.
+__device__ __forceinline__ Best better(const Best &a, const Best &b) {
+    const bool an = a.v != a.v, bn = b.v != b.v;
+    if (an || bn) return (an && bn) ? (b.i < a.i ? b : a) : (bn ? b : a);
+    return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a;
+}
 
 __global__ void __launch_bounds__(256)
     score_argmax_kernel(const float *__restrict__ cls, const float *__restrict__ loc, const double *__restrict__ window, double w_infl,
@@ -55,10 +62,10 @@ __global__ void __launch_bounds__(256)
     if (threadIdx.x == 0) {
         Best r = sb[0];
         for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = better(r, sb[w]);
-        idx[b] = r.i;
+        idx[b] = min(max(r.i, 0), n - 1);
         pscore[b] = r.v;
         score[b] = r.s;
-        s_idx = r.i;
+        s_idx = min(max(r.i, 0), n - 1);  // defensive: the gather below must stay inside loc whatever the scores were
     }
     __syncthreads();
     for (int l = threadIdx.x; l < L; l += blockDim.x) gathered[b * L + l] = __ldg(loc + ((long long)b * L + l) * n + s_idx);

@@ -17,6 +17,8 @@
 //   * Accumulation order is fixed (u outer, v inner, split-K halves combined in order) -> results
 //     are run-to-run deterministic.
 //   * Shapes outside the table fall back to a plain one-thread-per-output kernel (still on device).
+#include <cstdio>
+#include <cstdlib>
 #include <type_traits>
 #include "common.cuh"
 
@@ -522,12 +524,9 @@ struct KernelOf<Cfg, std::void_t<decltype(Cfg::XP)>> {
 
 template <class Cfg>
 static int launch_staged(const XProblems &P, int n, int B, int C, long long kbs, cudaStream_t st) {
-    static bool configured = false;  // benign race: idempotent attribute set
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(KernelOf<Cfg>::fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
-        if (e != cudaSuccess) return (int)e;
-        configured = true;
-    }
+    static DeviceOnce once;
+    if (int e = once.run([] { return cudaFuncSetAttribute(KernelOf<Cfg>::fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM); }))
+        return e;
     const int gpp = (int)(((long long)B * C) / Cfg::G);
     const int total = gpp * n;
     const int slots = sm_count() * Cfg::CTAS;
@@ -562,13 +561,15 @@ using Cfg256 = VCfg<29, 29, 61, 61, false, 4, 256, 2, 68, 36, true>;    // 256/5
 using Cfg256Lp = VCfg<29, 29, 29, 29, true, 8, 256, 1, 36, 36, false>;  // lp branch, INSTANCE_SIZE=512
 using CfgWin15 = XCfg<15, 15, 39, 39, false, 8, 224, 2, 1, false>;     // 15x15 window sweep
 
-static int g_xcorr_algo = HDN_XCORR_AUTO;  // hdn_xcorr_set_algo
+static thread_local int g_xcorr_algo = HDN_XCORR_AUTO;  // hdn_xcorr_set_algo: per calling thread, so concurrent callers cannot flip each other's choice
 
 // AUTO: the transform-domain kernel wherever one exists -- it measured faster than the direct sum on a B200 for all three shapes
 // (61x61 (*) 29x29: 2.6x, 29x29 circular (*) 29x29: 2.3x, 39x39 (*) 15x15: 1.2x)
 static bool fft_selected(int C, int Hx, int Wx, int Hk, int Wk, int circular) {
     return g_xcorr_algo != HDN_XCORR_DIRECT && xcorr_fft_applicable(C, Hx, Wx, Hk, Wk, circular);
 }
+
+static long long g_generic_launches = 0;  // hdn_xcorr_generic_launches
 
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -598,6 +599,13 @@ static int xcorr_dispatch(const XProblems &P, int n, int B, int C, int Hx, int W
     HDN_TRY(Cfg256Lp)
     HDN_TRY(CfgWin15)
 #undef HDN_TRY
+    // No tiled kernel for this shape / alignment: one thread per output, straight from global memory.  Correct but slow
+    // (no staging, no register tiling) -- say so once per process so that a mis-sized crop does not pass silently.
+    static int warned = 0;
+    __atomic_fetch_add(&g_generic_launches, 1ll, __ATOMIC_RELAXED);
+    if (!__atomic_exchange_n(&warned, 1, __ATOMIC_RELAXED) && !getenv("HDN_B200_QUIET"))
+        fprintf(stderr, "hdn_b200: xcorr %dx%d (*) %dx%d%s, C=%d%s has no tiled kernel: running the generic one-thread-per-output kernel\n", Hx, Wx, Hk,
+                Wk, circular ? " circular" : "", C, fast ? "" : " (unaligned pointers or strided template)");
     const int ph = circular ? Hx / 2 : 0, pw = circular ? Wx / 2 : 0;
     const int Ho = Hx + 2 * ph - Hk + 1, Wo = Wx + 2 * pw - Wk + 1;
     const long long total = (long long)n * B * C * Ho * Wo;
@@ -646,8 +654,12 @@ extern "C" int hdn_xcorr_set_algo(int algo) {
 }
 
 extern "C" int hdn_xcorr_uses_fft(int C, int Hx, int Wx, int Hk, int Wk, int circular, int64_t k_batch_stride) {
-    return (staged_applicable(C, Hx, Wx, Hk, Wk, circular, (long long)k_batch_stride) && fft_selected(C, Hx, Wx, Hk, Wk, circular)) ? 1 : 0;
+    // mirrors xcorr_dispatch: dense or shared template (and 16-byte aligned pointers, which the caller knows) + a transform-domain shape
+    const bool kbs_ok = k_batch_stride == 0 || k_batch_stride == (int64_t)C * Hk * Wk;
+    return (kbs_ok && fft_selected(C, Hx, Wx, Hk, Wk, circular)) ? 1 : 0;
 }
+
+extern "C" int64_t hdn_xcorr_generic_launches(void) { return __atomic_load_n(&g_generic_launches, __ATOMIC_RELAXED); }
 
 extern "C" int hdn_xcorr_is_staged(int C, int Hx, int Wx, int Hk, int Wk, int circular, int64_t k_batch_stride) {
     return staged_applicable(C, Hx, Wx, Hk, Wk, circular, (long long)k_batch_stride) ? 1 : 0;

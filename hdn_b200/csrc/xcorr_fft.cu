@@ -96,12 +96,9 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::CTAS)
 
 template <class Cfg>
 static int launch_fft(const XProblems &P, int n, int B, int C, long long kbs, cudaStream_t st) {
-    static bool configured = false;  // benign race: idempotent attribute set
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(xcorr_fft_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
-        if (e != cudaSuccess) return (int)e;
-        configured = true;
-    }
+    static DeviceOnce once;
+    if (int e = once.run([] { return cudaFuncSetAttribute(xcorr_fft_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM); }))
+        return e;
     const int gpp = (int)(((long long)B * C) / Cfg::G);
     const int total = gpp * n;
     const int slots = sm_count() * Cfg::CTAS;

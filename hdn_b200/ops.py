@@ -31,6 +31,31 @@ def _ptr(t):
     return _vp(t.data_ptr())
 
 
+def _out(out, shape, like, name="out"):
+    """A caller-supplied result buffer goes to the kernel as a raw pointer: insist on exactly what the kernel will write."""
+    if out is None:
+        return torch.empty(shape, device=like.device, dtype=torch.float32)
+    if not isinstance(out, torch.Tensor) or tuple(out.shape) != tuple(shape) or out.dtype != torch.float32 or out.device != like.device \
+            or not out.is_contiguous():
+        raise ValueError("%s must be a contiguous float32 tensor of shape %s on %s" % (name, tuple(shape), like.device))
+    return out
+
+
+class _on_device:
+    """Launch on the device that owns the tensors (the C ABI launches on the calling thread's CURRENT device)."""
+
+    def __init__(self, t):
+        self.ctx = torch.cuda.device(t.device) if t.device.index is not None and t.device.index != torch.cuda.current_device() else None
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
+
+
 def xcorr_out_hw(Hx, Wx, Hk, Wk, circular):
     ph, pw = (Hx // 2, Wx // 2) if circular else (0, 0)
     return Hx + 2 * ph - Hk + 1, Wx + 2 * pw - Wk + 1
@@ -47,10 +72,12 @@ def _xcorr(x, kernel, circular, out=None):
     Ho, Wo = xcorr_out_hw(Hx, Wx, Hk, Wk, circular)
     if Ho < 1 or Wo < 1:
         raise RuntimeError("xcorr: kernel %dx%d larger than (padded) input %dx%d" % (Hk, Wk, Hx, Wx))
-    if out is None:
-        out = torch.empty((B, C, Ho, Wo), device=x.device, dtype=torch.float32)
+    if kernel.device != x.device:
+        raise RuntimeError("xcorr: x is on %s but kernel on %s" % (x.device, kernel.device))
+    out = _out(out, (B, C, Ho, Wo), x)
     kbs = 0 if (Bk == 1 and B > 1) else C * Hk * Wk
-    st = _lib.lib().hdn_xcorr_dw_f32(_ptr(x), _ptr(kernel), _ptr(out), B, C, Hx, Wx, Hk, Wk, int(circular), kbs, _stream())
+    with _on_device(x):
+        st = _lib.lib().hdn_xcorr_dw_f32(_ptr(x), _ptr(kernel), _ptr(out), B, C, Hx, Wx, Hk, Wk, int(circular), kbs, _stream())
     _lib.check(st, "hdn_xcorr_dw_f32")
     return out
 
@@ -86,12 +113,12 @@ def xcorr_depthwise_multi(xs, kernels, circular=False, outs=None):
         if tuple(x.shape) != (B, C, Hx, Wx) or tuple(k.shape) != (Bk, C, Hk, Wk):
             raise RuntimeError("xcorr_depthwise_multi: all problems must share one shape")
     Ho, Wo = xcorr_out_hw(Hx, Wx, Hk, Wk, circular)
-    if outs is None:
-        outs = [torch.empty((B, C, Ho, Wo), device=xs[0].device, dtype=torch.float32) for _ in range(n)]
+    outs = [_out(None if outs is None else outs[i], (B, C, Ho, Wo), xs[0], "outs[%d]" % i) for i in range(n)]
     arr = _vp * n
     kbs = 0 if (Bk == 1 and B > 1) else C * Hk * Wk
-    st = _lib.lib().hdn_xcorr_dw_multi_f32(n, arr(*[x.data_ptr() for x in xs]), arr(*[k.data_ptr() for k in kernels]),
-                                           arr(*[o.data_ptr() for o in outs]), B, C, Hx, Wx, Hk, Wk, int(circular), kbs, _stream())
+    with _on_device(xs[0]):
+        st = _lib.lib().hdn_xcorr_dw_multi_f32(n, arr(*[x.data_ptr() for x in xs]), arr(*[k.data_ptr() for k in kernels]),
+                                               arr(*[o.data_ptr() for o in outs]), B, C, Hx, Wx, Hk, Wk, int(circular), kbs, _stream())
     _lib.check(st, "hdn_xcorr_dw_multi_f32")
     return outs
 
@@ -105,8 +132,7 @@ def logpolar_sample(x, polar=None, rot_delta=0.0, out_size=None, out=None):
         polar = _dev(polar, "polar")
         if tuple(polar.shape) != (B, 2):
             raise RuntimeError("polar must be [B,2]")
-    if out is None:
-        out = torch.empty((B, Ch, S, S), device=x.device, dtype=torch.float32)
+    out = _out(out, (B, Ch, S, S), x)
     st = _lib.lib().hdn_logpolar_f32(_ptr(x), _ptr(polar) if polar is not None else None, float(rot_delta), _ptr(out), B, Ch, H, W, S,
                                      _stream())
     _lib.check(st, "hdn_logpolar_f32")
@@ -165,13 +191,18 @@ _M_CACHE = {}
 
 
 def _m9_cached(t):
-    # M / M^-1 are per-model constants; cache by storage so the D2H read happens once, not per frame.
+    """M / M^-1 are per-model constants: read them from the device once per tensor OBJECT.  The entry holds a weak reference to
+    the tensor it was read from -- a new tensor that merely reuses a freed address (the reference builds M afresh every call)
+    misses and is read again, so a stale matrix can never be returned."""
+    import weakref
     key = (t.data_ptr(), t._version, tuple(t.shape), str(t.device))
-    v = _M_CACHE.get(key)
-    if v is None:
-        if len(_M_CACHE) > 64:
-            _M_CACHE.clear()
-        v = _M_CACHE[key] = _m9(t)
+    hit = _M_CACHE.get(key)
+    if hit is not None and hit[0]() is t:
+        return hit[1]
+    if len(_M_CACHE) > 64:
+        _M_CACHE.clear()
+    v = _m9(t)
+    _M_CACHE[key] = (weakref.ref(t), v)
     return v
 
 
@@ -181,8 +212,7 @@ def homo_warp(I1, H_mat, M=None, M_inv=None, out=None):
     B, Ch, H, W = I1.shape
     if H_mat.numel() != B * 9:
         raise RuntimeError("H_mat must hold one 3x3 per batch item")
-    if out is None:
-        out = torch.empty_like(I1)
+    out = _out(out, tuple(I1.shape), I1)
     mp = (ctypes.c_float * 9)(*M) if M is not None and not isinstance(M, ctypes.Array) else M
     mip = (ctypes.c_float * 9)(*M_inv) if M_inv is not None and not isinstance(M_inv, ctypes.Array) else M_inv
     st = _lib.lib().hdn_homo_warp_f32(_ptr(I1), _ptr(H_mat), mp, mip, _ptr(out), B, Ch, H, W, _stream())
@@ -253,6 +283,8 @@ def score_argmax_packed(cls, loc, window=None, win_influence=0.0):
     L = loc.shape[1]
     if window is not None:
         window = _dev(window, "window", torch.float64)
+        if window.numel() != N * N:
+            raise RuntimeError("window must have N*N entries")
     o_ps, o_sc, o_g, total = 8 * B, 16 * B, 20 * B, 20 * B + 4 * B * L
     buf = torch.empty(total + (-total) % 8, device=cls.device, dtype=torch.uint8)
     base = buf.data_ptr()
@@ -284,8 +316,7 @@ def conv_gemm(x, wpk, scale=None, shift=None, residual=None, ksize=1, dilation=1
     if wpk.numel() != 2 * Cout * ksize * ksize * Cin:
         raise RuntimeError("conv_gemm: packed weight of %d floats does not match Cin=%d, ksize=%d" % (wpk.numel(), Cin, ksize))
     shrink = 2 * dilation if (valid and ksize == 3) else 0
-    if out is None:
-        out = torch.empty((B, Cout, H - shrink, W - shrink), device=x.device, dtype=torch.float32)
+    out = _out(out, (B, Cout, H - shrink, W - shrink), x)
     opt = lambda t, n: _ptr(_dev(t, n)) if t is not None else None  # noqa: E731
     if residual is not None and tuple(residual.shape) != tuple(out.shape):
         raise RuntimeError("conv_gemm: residual shape mismatch")

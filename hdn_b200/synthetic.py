@@ -36,9 +36,11 @@ def texture(seed, h, w):
     return np.clip(img * 255.0, 0, 255).astype(np.uint8)
 
 
-def sequence(seed, n_frames, size=(360, 480), obj=(120, 160)):
+def sequence(seed, n_frames, size=(360, 480), obj=(120, 160), events=None):
     """A planar object on a background, moved by a smooth random homography walk.
-    -> frames [n] uint8 BGR, gt polygons [n,8] (x1,y1,..,x4,y4 TL,TR,BR,BL of the object)."""
+    -> frames [n] uint8 BGR, gt polygons [n,8] (x1,y1,..,x4,y4 TL,TR,BR,BL of the object).
+    events: {frame index: 'occlude' | 'invert' | 'flat'} -- that frame shows an unrelated texture / the photometric negative /
+    a constant colour instead (the frames that trip the tracker's pscore / lp-score / homo_score gates)."""
     rng = np.random.default_rng(seed)
     H_img, W_img = size
     oh, ow = obj
@@ -59,6 +61,15 @@ def sequence(seed, n_frames, size=(360, 480), obj=(120, 160)):
         warped = cv2.warpPerspective(fg, Hm, (W_img, H_img))
         mask = cv2.warpPerspective(np.full((oh, ow), 255, np.uint8), Hm, (W_img, H_img))
         frame[mask > 127] = warped[mask > 127]
+        kind = (events or {}).get(t)
+        if kind == "occlude":
+            frame = texture(seed + 1000 + t, H_img, W_img)
+        elif kind == "invert":
+            frame = 255 - frame
+        elif kind == "flat":
+            frame = np.full_like(frame, 128)
+        elif kind is not None:
+            raise ValueError("unknown event %r" % (kind,))
         frames.append(frame)
         polys.append(cur.reshape(-1).copy())
     return frames, np.asarray(polys, np.float32)
@@ -82,9 +93,19 @@ def _randn(name, shape):
     return torch.randn(tuple(shape), generator=_gen(name))
 
 
-def fill_weights(model, scales=None):
-    """In-place deterministic initialisation of every parameter and buffer of `model` (eval-mode fixture)."""
-    scales = dict(SCALES, **(scales or {}))
+# Second calibration ("gates" variant): the classification heads respond MONOTONICALLY to the correlation strength (final 1x1
+# weights +1 on the foreground row, -1 on the background row, plus a bias: logit ~ the norm of the correlation vector), so the log-polar peak sits at the
+# auto-correlation maximum with a confident score, and a frame whose content does not match the template drops below the
+# tracker's gates (pscore < 0.05, lp score < 0.25) while a photometric mismatch pushes homo_score past 2.5.  Values are
+# calibrated against the reference by `python oracle/gen_golden_model.py --calibrate-gates` (printed there).
+GATES = {"head_cls": 1e-8, "head_cls_bias": 13.0, "head_loc": 1.297e-06, "head_lp_cls": 8.6e-9, "head_lp_cls_bias": 45.5, "head_lp_loc": 3e-9,
+         "head_lp_loc_bias0": -1.0, "fc": 1.351, "share_gain": 19.93}
+
+
+def fill_weights(model, scales=None, variant=None):
+    """In-place deterministic initialisation of every parameter and buffer of `model` (eval-mode fixture).
+    variant='gates': the second calibration described above (scales default to GATES)."""
+    scales = dict(GATES if variant == "gates" else SCALES, **(scales or {}))
     with torch.no_grad():
         for mname, m in model.named_modules():
             if isinstance(m, nn.Conv2d):
@@ -111,8 +132,23 @@ def fill_weights(model, scales=None):
             for prefix, tag in (("head.", "head"), ("head_lp.", "head_lp")):
                 if key.startswith(prefix) and ".head.3." in key:
                     branch = "cls" if ".cls." in key else "loc"
-                    t.mul_(scales["%s_%s" % (tag, branch)])
+                    if variant == "gates" and branch == "cls":
+                        if key.endswith("weight"):  # row 1 = foreground: +1, row 0 = background: -1
+                            t.fill_(1.0)
+                            t[0].fill_(-1.0)
+                        else:  # bias: the background logit carries the offset
+                            t.zero_()
+                            t[0] = scales["%s_cls_bias" % tag]
+                    if variant == "gates" and tag == "head_lp" and branch == "loc" and key.endswith("bias"):
+                        # constant log-radius offset: cancels the one-cell bias of the untrained log-polar peak (scale stays near 1)
+                        level = int(key.split(".box")[1][0]) - 2
+                        t.zero_()
+                        t[0] = scales["head_lp_loc_bias0"] / float(sd["head_lp.loc_scale"][level])
+                        continue
+                    t.mul_(scales["%s_%s" % (tag, branch)] if not (variant == "gates" and branch == "cls" and key.endswith("bias")) else 1.0)
             if key.startswith("hm_net.fc."):
                 t.mul_(scales["fc"])
+            if variant == "gates" and key in ("hm_net.ShareFeature.ShareFeature.7.weight", "hm_net.ShareFeature.ShareFeature.7.bias"):
+                t.mul_(scales["share_gain"])  # last BatchNorm of the 1->4->8->1 feature extractor: sets the scale of homo_score
     model.eval()
     return model

@@ -12,10 +12,15 @@
  *   - All tensor pointers are DEVICE pointers to contiguous NCHW fp32 unless
  *     the parameter name ends in _host.  The caller owns every buffer.
  *   - Every launcher is asynchronous on the caller's stream (a cudaStream_t
- *     passed as void*; NULL = legacy default stream) and re-entrant.
+ *     passed as void*; NULL = legacy default stream) and re-entrant: launches go
+ *     to the CURRENT device of the calling thread; the only library state is
+ *     per-device kernel configuration and the per-thread algorithm choice of
+ *     hdn_xcorr_set_algo.
  *   - Return value: 0 on success, a negative hdn_status for a rejected
  *     argument (nothing was launched), or a positive cudaError_t if the launch
- *     itself failed.  No function throws, exits or prints.
+ *     itself failed.  No function throws or exits.  The only message ever
+ *     printed (once per process, to stderr, silenced by HDN_B200_QUIET) says
+ *     that a correlation shape has no tiled kernel and runs the slow generic one.
  */
 #ifndef HDN_B200_H
 #define HDN_B200_H
@@ -66,13 +71,17 @@ int hdn_xcorr_dw_multi_f32(int n, const float *const *x_host, const float *const
 /* Algorithm of K1/K2 for the shapes that have both kernels (29x29 and 15x15 templates, where the direct sum is FMA-bound at
  * 30-140 flop/B): HDN_XCORR_DIRECT = the direct register-tiled sum; HDN_XCORR_FFT / HDN_XCORR_AUTO (default) = the transform-domain
  * kernel (row FFTs + per-frequency column correlation + inverse row FFTs, xcorr_fft.cu), faster on a B200 for all of them.
- * Process-wide; both give the reference's result to ~3e-7 of max|out|.  hdn_xcorr_uses_fft: 1 if that shape now takes the FFT kernel. */
+ * Per calling thread; both give the reference's result to ~3e-7 of max|out|.  hdn_xcorr_uses_fft: 1 if that shape (dense or shared
+ * template, 16-byte aligned pointers) now takes the FFT kernel -- the same decision hdn_xcorr_dw*_f32 makes. */
 enum hdn_xcorr_algo { HDN_XCORR_AUTO = 0, HDN_XCORR_DIRECT = 1, HDN_XCORR_FFT = 2 };
 int hdn_xcorr_set_algo(int algo);
 int hdn_xcorr_uses_fft(int C, int Hx, int Wx, int Hk, int Wk, int circular, int64_t k_batch_stride);
 
 /* 1 if (shape, 16-byte aligned pointers) takes the TMA-staged kernel, 0 if it takes the generic one-thread-per-output kernel. */
 int hdn_xcorr_is_staged(int C, int Hx, int Wx, int Hk, int Wk, int circular, int64_t k_batch_stride);
+/* How many correlation launches of this process fell to the generic kernel (shape outside the tiled table, unaligned pointers or a
+ * strided template): correct but slow; the first one is also reported on stderr. */
+int64_t hdn_xcorr_generic_launches(void);
 
 /* K3.  Replaces hdn/models/logpolar.py:50-134 STN_Polar.forward: analytic log-polar
  * grid (rows = angle, cols = log-radius) + bilinear border sampling, align_corners=False.

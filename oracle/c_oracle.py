@@ -28,7 +28,8 @@ def build(force=False):
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_SO):
+        src = os.path.join(_HERE, "hdn_oracle.c")
+        if not os.path.exists(_SO) or (os.path.exists(src) and os.path.getmtime(_SO) < os.path.getmtime(src)):
             build()
         L = ctypes.CDLL(_SO)
         ci, cll = ctypes.c_int, ctypes.c_longlong

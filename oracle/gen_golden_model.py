@@ -50,7 +50,7 @@ class fixture:  # same names the rest of this script uses
 t = torch.from_numpy
 
 
-def build_reference_model(instance=255, exemplar=127, scales=None):
+def build_reference_model(instance=255, exemplar=127, scales=None, variant=None):
     from hdn.core.config import cfg
     cfg.merge_from_file(YAML)
     cfg.TRACK.INSTANCE_SIZE, cfg.TRACK.EXEMPLAR_SIZE = instance, exemplar
@@ -58,8 +58,11 @@ def build_reference_model(instance=255, exemplar=127, scales=None):
     from hdn.models.model_builder_e2e_unconstrained_v2 import ModelBuilder
     torch.manual_seed(0)
     model = ModelBuilder()
-    fixture.fill(model, scales)
+    fixture.fill(model, scales, variant)
     return model, cfg
+
+
+FEATURE_STRIDE = {255: 3, 512: 13}  # keeps the committed fixtures small (zf / zf_lp / x_lp samples, ~0.4 MB per golden)
 
 
 def homo_inputs(seed, B=1):
@@ -76,15 +79,20 @@ def run_model(model, instance, exemplar, seed):
     out = {}
     with torch.no_grad():
         model.template(t(z))
+        stride = FEATURE_STRIDE[instance]  # element-wise samples of the neck features: every stride-th value of the flattened map
         for i, f in enumerate(model.zf):
             out["zf%d_stats" % i] = np.asarray([f.mean().item(), f.std().item(), f.abs().max().item()], np.float32)
+            out["zf%d_sample" % i] = f.reshape(-1)[::stride].numpy().copy()
         for i, f in enumerate(model.zf_lp):
             out["zf_lp%d_stats" % i] = np.asarray([f.mean().item(), f.std().item(), f.abs().max().item()], np.float32)
+            out["zf_lp%d_sample" % i] = f.reshape(-1)[::stride].numpy().copy()
+        out["feature_stride"] = np.int32(stride)
         r = model.track_new(t(x))
         out["cls"], out["loc_c"] = r["cls"].numpy(), r["loc_c"].numpy()
         r = model.track_new_lp(t(x), [0, 0])
         out["cls_lp"], out["loc_lp"] = r["cls_lp"].numpy(), r["loc_lp"].numpy()
         out["x_lp_stats"] = np.asarray([r["x_lp"].mean().item(), r["x_lp"].std().item()], np.float32)
+        out["x_lp_sample"] = r["x_lp"].reshape(-1)[::stride].numpy().copy()
         data = {"org_imgs": t(pair), "input_tensors": t(pair), "h4p": t(h4p),
                 "patch_indices": t(np.tile(np.arange(127 * 127, dtype=np.float32), (1, 1)))}
         H, s_homo, s_simi = model.track_proj(data, None)
@@ -149,6 +157,111 @@ def gen_tracker(seed=7, n_frames=8):
             print("frame %d best_score %.4f polygon %s" % (idx, o["best_score"], np.round(o["polygon"].reshape(-1), 1)))
     np.savez_compressed(os.path.join(OUT, "tracker_seq%d.npz" % seed), seed=np.int64(seed), n_frames=np.int32(n_frames), gt=polys,
                         **{k: np.asarray(v) for k, v in rec.items()})
+
+
+GATE_EVENTS = {6: "occlude", 12: "invert", 18: "flat", 24: "occlude", 27: "invert"}
+
+
+def gen_tracker_gates(seed=13, n_frames=31, scales=None):
+    """Second tracker golden ('gates' weight calibration, hdn_b200/synthetic.py GATES): every frame is ONE independent step of
+    hdnTrackerHomo.track_new from a known state -- H_total is set to the ground-truth homography of the previous frame (what a
+    perfect tracker would hold), so the steps stay realistic although the weights are untrained, and a last-bit difference cannot
+    amplify over frames.  The log-polar head is confident on ordinary frames (non-zero rotation, scale != 1 -> decode_logpolar,
+    H_sim, the rotated / re-scaled stage-3 crop) and the event frames trip `lp score < 0.25` and `homo_score > 2.5`
+    (hdn_tracker_proj_e2e.py:203,261).  `pscore < 0.05` (:176) cannot fire with the shipped WINDOW_INFLUENCE: the Hanning term
+    alone is 0.163 at the map centre."""
+    import cv2
+    model, cfg = build_reference_model(scales=scales, variant="gates")
+    from hdn.tracker.tracker_builder import build_tracker
+    from hdn.utils.bbox import get_min_max_bbox, get_w_h_from_poly
+    torch.set_num_threads(8)
+    tracker = build_tracker(model)
+    frames, polys = synth.sequence(seed, n_frames, events=GATE_EVENTS)
+    log = {}
+    ref_new, ref_lp, ref_proj = model.track_new, model.track_new_lp, model.track_proj
+
+    def spy_new(x):
+        r = ref_new(x)
+        sc = tracker._convert_score(r["cls"])
+        ps = sc * (1 - cfg.TRACK.WINDOW_INFLUENCE) + tracker.window * cfg.TRACK.WINDOW_INFLUENCE
+        log.update(idx=int(np.argmax(ps)), pscore=float(ps.max()))
+        return r
+
+    def spy_lp(x, d):
+        r = ref_lp(x, d)
+        sc = tracker._convert_score(r["cls_lp"])
+        log.update(idx_lp=int(np.argmax(sc)), lp_score=float(sc.max()))
+        return r
+
+    def spy_proj(d, m):
+        r = ref_proj(d, m)
+        log.update(homo_score=float(r[1]))
+        return r
+
+    model.track_new, model.track_new_lp, model.track_proj = spy_new, spy_lp, spy_proj
+    keys = ("polygon", "best_score", "H_pre", "H_total", "idx", "pscore", "idx_lp", "lp_score", "homo_score", "rot_delta", "scale_delta")
+    rec = {k: [] for k in keys}
+    init_pts = polys[0].reshape(4, 2).astype(np.float32)
+    with torch.no_grad():
+        gt = polys[0]
+        cx, cy, w, h = get_min_max_bbox(np.array(gt))
+        tracker.init(frames[0], [cx - (w - 1) / 2, cy - (h - 1) / 2, w, h], get_w_h_from_poly(np.array(gt)), gt, np.array([gt[:2]]))
+        for idx in range(1, n_frames):
+            H_pre = cv2.getPerspectiveTransform(init_pts, polys[idx - 1].reshape(4, 2).astype(np.float32))
+            tracker.H_total = H_pre.copy()
+            rot0, scale0 = tracker.rot, tracker.scale
+            o = tracker.track_new(idx, frames[idx], None, None, None)
+            rec["polygon"].append(np.asarray(o["polygon"], np.float64))
+            rec["best_score"].append(float(o["best_score"]))
+            rec["H_pre"].append(H_pre)
+            rec["H_total"].append(np.asarray(tracker.H_total, np.float64))
+            rec["rot_delta"].append(float(tracker.rot - rot0))
+            rec["scale_delta"].append(float(tracker.scale / scale0))
+            for k in ("idx", "pscore", "idx_lp", "lp_score", "homo_score"):
+                rec[k].append(log[k])
+            print("frame %2d %-8s idx %3d pscore %.4f | lp idx %3d score %.4f rot %+.4f scale %.4f | homo %.3f" % (
+                idx, GATE_EVENTS.get(idx, ""), log["idx"], log["pscore"], log["idx_lp"], log["lp_score"], rec["rot_delta"][-1], rec["scale_delta"][-1],
+                log["homo_score"]), flush=True)
+    lp, hs = np.asarray(rec["lp_score"]), np.asarray(rec["homo_score"])
+    print("lp gate fires on %d / %d frames, homo gate on %d, non-identity similarity on %d" % (
+        (lp < 0.25).sum(), len(lp), (hs > 2.5).sum(), (np.asarray(rec["rot_delta"]) != 0).sum()))
+    np.savez_compressed(os.path.join(OUT, "tracker_gates%d.npz" % seed), seed=np.int64(seed), n_frames=np.int32(n_frames), gt=polys,
+                        events=np.asarray(sorted(GATE_EVENTS.items()), dtype="U16"), **{k: np.asarray(v) for k, v in rec.items()})
+
+
+def gen_tracker_sim(seed=13, n_frames=7):
+    """Similarity-only tracker (cfg.TRACK.TYPE = 'hdnTracker', hdn/tracker/hdn_tracker.py:110-301): init + free-running
+    track_new (translation, scale / rotation, per-frame `update_template` from the rotated first frame), once with the default
+    weight calibration (lp gate fires: identity similarity) and once with the 'gates' one (confident log-polar head: the box
+    is re-scaled and rotated every frame; the tracker clamps the size to the frame, so the run stays bounded)."""
+    from hdn.utils.bbox import get_min_max_bbox, get_w_h_from_poly
+    torch.set_num_threads(8)
+    frames, polys = synth.sequence(seed, n_frames)
+    out = {"seed": np.int64(seed), "n_frames": np.int32(n_frames), "gt": polys}
+    for tag, variant in (("v0", None), ("v1", "gates")):
+        model, cfg = build_reference_model(variant=variant)
+        cfg.TRACK.TYPE = "hdnTracker"
+        from hdn.tracker.tracker_builder import build_tracker
+        tracker = build_tracker(model)
+        assert type(tracker).__name__ == "hdnTracker"
+        rec = {k: [] for k in ("polygon", "bbox", "best_score", "rot", "center_pos", "size")}
+        with torch.no_grad():
+            gt = polys[0]
+            cx, cy, w, h = get_min_max_bbox(np.array(gt))
+            tracker.init(frames[0], [cx - (w - 1) / 2, cy - (h - 1) / 2, w, h], get_w_h_from_poly(np.array(gt)), np.array([gt[:2]]))
+            for idx in range(1, n_frames):
+                o = tracker.track_new(idx, frames[idx], None, None)
+                rec["polygon"].append(np.asarray(o["polygon"], np.float64))
+                rec["bbox"].append(np.asarray(o["bbox"], np.float64))
+                rec["best_score"].append(float(o["best_score"]))
+                rec["rot"].append(float(o["rot"]))
+                rec["center_pos"].append(np.asarray(tracker.center_pos, np.float64))
+                rec["size"].append(np.asarray(tracker.size, np.float64))
+                print("%s frame %d best_score %.4f rot %+.4f size %s centre %s" % (tag, idx, o["best_score"], o["rot"], np.round(tracker.size, 2),
+                                                                                 np.round(tracker.center_pos, 2)), flush=True)
+        out.update({"%s_%s" % (tag, k): np.asarray(v) for k, v in rec.items()})
+        cfg.TRACK.TYPE = "hdnTrackerHomoProje2e"
+    np.savez_compressed(os.path.join(OUT, "tracker_sim%d.npz" % seed), **out)
 
 
 def gen_host():
@@ -220,7 +333,7 @@ if __name__ == "__main__":
     if "--calibrate" in args:
         calibrate()
         sys.exit(0)
-    which = args or ["keys", "native", "256", "tracker", "host"]
+    which = args or ["keys", "native", "256", "tracker", "gates", "sim", "host"]
     if "keys" in which:
         gen_keys()
     if "native" in which:
@@ -229,5 +342,9 @@ if __name__ == "__main__":
         gen_model("256_512", 512, 256, 2000)
     if "tracker" in which:
         gen_tracker()
+    if "gates" in which:
+        gen_tracker_gates()
+    if "sim" in which:
+        gen_tracker_sim()
     if "host" in which:
         gen_host()

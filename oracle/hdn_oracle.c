@@ -261,7 +261,8 @@ void orc_score_argmax(const float *cls, const float *loc, const double *window, 
             } else {
                 ps = (double)s;
             }
-            if (ps > bestv) { bestv = ps; best = p; bests = s; }
+            /* np.argmax: first maximum; a NaN counts as the maximum and the first NaN wins */
+            if ((ps > bestv && bestv == bestv) || (ps != ps && bestv == bestv)) { bestv = ps; best = p; bests = s; }
         }
         idx[b] = best;
         pscore[b] = bestv;

@@ -18,14 +18,14 @@ pytestmark = pytest.mark.gpu
 YAML = os.path.join(ROOT, "experiments", "tracker_homo_config", "proj_e2e_GOT_unconstrained_v2.yaml")
 
 
-def build_model(instance=255, exemplar=127):
+def build_model(instance=255, exemplar=127, variant=None):
     from hdn.core.config import cfg
     import weights_fixture
     cfg.merge_from_file(YAML)
     cfg.TRACK.INSTANCE_SIZE, cfg.TRACK.EXEMPLAR_SIZE = instance, exemplar
     cfg.CUDA = True
     from hdn.models.model_builder_e2e_unconstrained_v2 import ModelBuilder
-    model = weights_fixture.fill(ModelBuilder()).cuda().eval()
+    model = weights_fixture.fill(ModelBuilder(), variant=variant).cuda().eval()
     return model, cfg
 
 
@@ -43,8 +43,12 @@ def test_model_level_parity(tag):
     z = synth.crop_tensor(seed, (1, 6, ex, ex))
     x = synth.crop_tensor(seed + 1, (1, 3, inst, inst))
     model.template(cuda(z))
+    stride = int(g["feature_stride"])
     for i, f in enumerate(model.zf):
         assert np.allclose([f.mean().item(), f.std().item(), f.abs().max().item()], g["zf%d_stats" % i], rtol=1e-3)
+        assert_close(f.reshape(-1)[::stride].cpu().numpy(), g["zf%d_sample" % i], what="zf[%d] element-wise" % i)
+    for i, f in enumerate(model.zf_lp):
+        assert_close(f.reshape(-1)[::stride].cpu().numpy(), g["zf_lp%d_sample" % i], what="zf_lp[%d] element-wise" % i)
     out = model.track_new(cuda(x))
     assert_close(out["cls"].cpu().numpy(), g["cls"], what="cls")
     assert_close(out["loc_c"].cpu().numpy(), g["loc_c"], what="loc_c")
@@ -52,6 +56,7 @@ def test_model_level_parity(tag):
     assert_close(lp["cls_lp"].cpu().numpy(), g["cls_lp"], what="cls_lp")
     assert_close(lp["loc_lp"].cpu().numpy(), g["loc_lp"], what="loc_lp")
     assert np.allclose([lp["x_lp"].mean().item(), lp["x_lp"].std().item()], g["x_lp_stats"], rtol=1e-4)
+    assert_close(lp["x_lp"].reshape(-1)[::stride].cpu().numpy(), g["x_lp_sample"], what="x_lp element-wise")
     # arg-max indices on the reference maps and on ours must be the same cell (bit-exact requirement)
     N = g["cls"].shape[-1]
     win = np.outer(np.hanning(N), np.hanning(N)).flatten()
@@ -110,6 +115,100 @@ def test_tracker_trajectory_parity():
         assert abs(float(o["best_score"]) - g["best_score"][idx - 1]) < 1e-3
         assert np.allclose(tracker.H_total, g["H_total"][idx - 1], rtol=1e-3, atol=1e-3 * np.abs(g["H_total"][idx - 1]).max())
         assert set(o) == {"bbox_aligned", "best_score", "polygon", "points", "bbox"}
+
+
+def test_tracker_gate_steps_parity():
+    """30 independent steps of hdnTrackerHomo.track_new from known states (H_total = ground-truth homography of the previous
+    frame) with the 'gates' weight calibration: the log-polar head is confident on ordinary frames (non-zero rotation,
+    scale != 1 -> decode_logpolar, H_sim, the rotated / re-scaled stage-3 crop) and the event frames trip `lp score < 0.25`
+    and `homo_score > 2.5` (hdn_tracker_proj_e2e.py:203,261).  Arg-max indices and both gate decisions bit-exact; polygons
+    and H_total within 1e-3.  (`pscore < 0.05` cannot fire with the shipped WINDOW_INFLUENCE: 0.163 * hanning(centre) > 0.05.)"""
+    import synth
+    from hdn.tracker.tracker_builder import build_tracker
+    from hdn.utils.bbox import get_min_max_bbox, get_w_h_from_poly
+    g = load_golden("tracker_gates13")
+    events = {int(k): str(v) for k, v in g["events"]}
+    model, cfg = build_model(variant="gates")
+    tracker = build_tracker(model)
+    frames, polys = synth.sequence(int(g["seed"]), int(g["n_frames"]), events=events)
+    assert np.array_equal(polys, g["gt"])
+    seen = {}
+    s1, s2, s3 = model.track_new_scored, model.track_new_lp_scored, model.track_proj_packed
+
+    def spy1(x, w=None):
+        r = s1(x, w)
+        seen.update(idx=int(r[0][0]), pscore=float(r[1][0]))
+        return r
+
+    def spy2(x, d=[0, 0]):
+        r = s2(x, d)
+        seen.update(idx_lp=int(r[0][0]), lp_score=float(r[2][0]))
+        return r
+
+    def spy3(pair, h4p):
+        r = s3(pair, h4p)
+        seen.update(homo_score=float(r[0][9]))
+        return r
+
+    model.track_new_scored, model.track_new_lp_scored, model.track_proj_packed = spy1, spy2, spy3
+    gt = polys[0]
+    cx, cy, w, h = get_min_max_bbox(np.array(gt))
+    tracker.init(frames[0], [cx - (w - 1) / 2, cy - (h - 1) / 2, w, h], get_w_h_from_poly(np.array(gt)), gt, np.array([gt[:2]]))
+    diag = float(np.hypot(*frames[0].shape[:2]))
+    n_lp_gate = n_homo_gate = n_sim = 0
+    for idx in range(1, len(frames)):
+        i = idx - 1
+        tracker.H_total = g["H_pre"][i].copy()
+        rot0, scale0 = tracker.rot, tracker.scale
+        o = tracker.track_new(idx, frames[idx], None, None, None)
+        assert seen["idx"] == int(g["idx"][i]), "frame %d: stage-1 arg-max %d != %d" % (idx, seen["idx"], int(g["idx"][i]))
+        assert seen["idx_lp"] == int(g["idx_lp"][i]), "frame %d: log-polar arg-max" % idx
+        assert abs(seen["pscore"] - g["pscore"][i]) < 1e-3 and abs(seen["lp_score"] - g["lp_score"][i]) < 1e-3
+        assert (seen["lp_score"] < 0.25) == (g["lp_score"][i] < 0.25), "frame %d: lp gate" % idx
+        assert (seen["homo_score"] > 2.5) == (g["homo_score"][i] > 2.5), "frame %d: homo gate" % idx
+        assert abs(seen["homo_score"] - g["homo_score"][i]) <= 2e-3 * g["homo_score"][i]
+        assert abs((tracker.rot - rot0) - g["rot_delta"][i]) < 1e-4 and abs(tracker.scale / scale0 - g["scale_delta"][i]) < 1e-4 * g["scale_delta"][i]
+        ref_poly = g["polygon"][i]
+        scale = max(diag, float(np.abs(ref_poly).max()))
+        assert np.abs(np.asarray(o["polygon"], np.float64) - ref_poly).max() <= 1e-3 * scale, "frame %d polygon" % idx
+        assert np.allclose(tracker.H_total, g["H_total"][i], rtol=1e-3, atol=1e-3 * np.abs(g["H_total"][i]).max())
+        n_lp_gate += g["lp_score"][i] < 0.25
+        n_homo_gate += g["homo_score"][i] > 2.5
+        n_sim += g["rot_delta"][i] != 0
+    assert n_lp_gate >= 2 and n_homo_gate >= 5 and n_sim >= 20  # the golden really covers the branches
+
+
+@pytest.mark.parametrize("tag,variant", [("v0", None), ("v1", "gates")])
+def test_similarity_tracker_parity(tag, variant):
+    """cfg.TRACK.TYPE = 'hdnTracker' (hdn/tracker/hdn_tracker.py:110-301): init + 6 free-running frames incl. the per-frame
+    `update_template` from the rotated first frame, against the reference tracker's own trajectory; v1 = confident log-polar
+    head (the box is rotated / re-scaled every frame and clamped to the frame size)."""
+    import synth
+    from hdn.tracker.tracker_builder import build_tracker
+    from hdn.utils.bbox import get_min_max_bbox, get_w_h_from_poly
+    g = load_golden("tracker_sim13")
+    model, cfg = build_model(variant=variant)
+    cfg.TRACK.TYPE = "hdnTracker"
+    try:
+        tracker = build_tracker(model)
+        assert type(tracker).__name__ == "hdnTracker"
+        frames, polys = synth.sequence(int(g["seed"]), int(g["n_frames"]))
+        assert np.array_equal(polys, g["gt"])
+        gt = polys[0]
+        cx, cy, w, h = get_min_max_bbox(np.array(gt))
+        tracker.init(frames[0], [cx - (w - 1) / 2, cy - (h - 1) / 2, w, h], get_w_h_from_poly(np.array(gt)), np.array([gt[:2]]))
+        diag = float(np.hypot(*frames[0].shape[:2]))
+        for idx in range(1, len(frames)):
+            o = tracker.track_new(idx, frames[idx], None, None)
+            i = idx - 1
+            assert np.abs(np.asarray(o["polygon"], np.float64) - g[tag + "_polygon"][i]).max() <= 1e-3 * diag, "frame %d polygon" % idx
+            assert np.abs(np.asarray(o["bbox"], np.float64) - g[tag + "_bbox"][i]).max() <= 1e-3 * diag
+            assert abs(float(o["best_score"]) - g[tag + "_best_score"][i]) < 1e-3
+            assert abs(float(o["rot"]) - g[tag + "_rot"][i]) < 1e-4
+            assert np.abs(tracker.size - g[tag + "_size"][i]).max() <= 1e-3 * diag
+            assert set(o) == {"bbox", "bbox_aligned", "best_score", "rot", "polygon"}
+    finally:
+        cfg.TRACK.TYPE = "hdnTrackerHomoProje2e"
 
 
 def test_cuda_graph_stages_equal_eager():

@@ -148,6 +148,38 @@ def test_xcorr_full_size_properties(shape, algo):
         assert float((fn(x, k) - direct).abs().max()) <= 5e-6 * float(direct.abs().max())
 
 
+@pytest.mark.parametrize("shape", [(64, 256, 61, 61, 29, 29, 0), (64, 256, 29, 29, 29, 29, 1), (256, 256, 39, 39, 15, 15, 0)])
+def test_xcorr_full_size_random_slice_vs_oracle(shape, algo):
+    """BASELINE batch sizes against the C oracle itself: two randomly chosen pairs of the batch-64 / batch-256 output are
+    recomputed on the CPU (the oracle finishes a 2-pair slice in seconds) -- not only self-consistency properties."""
+    B, C, Hx, Wx, Hk, Wk, circ = shape
+    fn = ops().xcorr_depthwise_circular if circ else ops().xcorr_depthwise
+    gen = torch.Generator(device=DEV).manual_seed(B + Hx)
+    x = torch.randn((B, C, Hx, Wx), device=DEV, generator=gen) + 0.5
+    k = torch.randn((B, C, Hk, Wk), device=DEV, generator=gen) * 0.1
+    out = fn(x, k)
+    pick = np.random.default_rng(Hx * 7 + Hk).choice(B, 2, replace=False)
+    for b in pick:
+        ref = c_oracle.xcorr_dw(x[b:b + 1].cpu().numpy(), k[b:b + 1].cpu().numpy(), bool(circ))
+        assert_close(out[b:b + 1].cpu().numpy(), ref, what="%s pair %d" % (shape, b))
+        if algo == "fft" and uses_fft(C, Hx, Wx, Hk, Wk, circ):
+            assert np.abs(out[b:b + 1].cpu().numpy() - ref).max() <= 5e-6 * np.abs(ref).max()
+
+
+def test_xcorr_untiled_shape_runs_generic_kernel_and_is_counted():
+    """A crop size outside the tiled table (INSTANCE_SIZE 287 -> 33x33 search features) still gives the reference's result,
+    and the library counts it (hdn_xcorr_generic_launches) instead of degrading silently."""
+    from hdn_b200 import _lib
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((2, 32, 33, 33)).astype(np.float32)
+    k = rng.standard_normal((2, 32, 5, 5)).astype(np.float32)
+    assert _lib.lib().hdn_xcorr_is_staged(32, 33, 33, 5, 5, 0, 32 * 25) == 0
+    n0 = _lib.lib().hdn_xcorr_generic_launches()
+    out = ops().xcorr_depthwise(g2d(x), g2d(k)).cpu().numpy()
+    assert _lib.lib().hdn_xcorr_generic_launches() == n0 + 1
+    assert_close(out, c_oracle.xcorr_dw(x, k, False))
+
+
 # ------------------------------------------------------------------ K3
 @pytest.mark.parametrize("name", golden_names("ops_k3_"))
 def test_logpolar_golden(name):
@@ -288,3 +320,27 @@ def test_score_argmax_vs_oracle_batch512(N, L, windowed):
     assert np.allclose(sc.cpu().numpy(), rsc, rtol=1e-6, atol=1e-7)
     if not windowed:
         assert int(idx[5]) == 0  # first maximum wins a full tie
+
+
+def test_score_argmax_nan_scores_follow_numpy():
+    """Non-finite scores (a NaN frame): np.argmax returns the first NaN; the kernel must do the same and never gather out of range."""
+    rng = np.random.default_rng(9)
+    N, L, B = 25, 2, 4
+    cls = (rng.standard_normal((B, 2, N, N)) * 2).astype(np.float32)
+    loc = rng.standard_normal((B, L, N, N)).astype(np.float32)
+    cls[0] = np.nan                  # every score NaN -> index 0
+    cls[1, 1, 3, 7] = np.nan         # a single NaN -> that cell
+    cls[2, 0, 20, 2] = np.nan
+    cls[2, 1, 4, 4] = np.nan         # two NaNs -> the first in scan order
+    win = np.outer(np.hanning(N), np.hanning(N)).flatten()
+    w = 0.1632532824922313
+    idx, ps, sc, gath = ops().score_argmax(g2d(cls), g2d(loc), g2d(win), w)
+    e = np.exp(cls - cls.max(1, keepdims=True))
+    score = (e[:, 1] / e.sum(1)).reshape(B, -1).astype(np.float32)
+    pscore = score * np.float32(1 - w) + win * w   # hdn_tracker_proj_e2e.py:172-173
+    expect = np.argmax(pscore, 1)
+    assert list(expect[:3]) == [0, 3 * N + 7, 4 * N + 4]
+    assert np.array_equal(idx.cpu().numpy(), expect)
+    assert np.array_equal(gath.cpu().numpy(), np.stack([loc[b].reshape(L, -1)[:, expect[b]] for b in range(B)]))
+    ridx = c_oracle.score_argmax(cls, loc, win, w)[0]
+    assert np.array_equal(ridx, expect)

@@ -129,3 +129,19 @@ def test_score_argmax_lp():
     rot = (pts[:, 1] - gath[:, 2] * st) * (2 * np.pi / E)
     assert np.allclose(scale, g["sim"][:, 0], rtol=1e-5)
     assert np.allclose(rot, g["sim"][:, 2], rtol=1e-5, atol=1e-6)
+
+
+def test_oracle_argmax_nan_semantics_match_numpy():
+    """np.argmax (the reference's arg-max) treats NaN as the maximum and returns the first one; so does the oracle."""
+    rng = np.random.default_rng(9)
+    N, L, B = 13, 4, 3
+    cls = (rng.standard_normal((B, 2, N, N)) * 2).astype(np.float32)
+    loc = rng.standard_normal((B, L, N, N)).astype(np.float32)
+    cls[0] = np.nan
+    cls[1, 1, 3, 7] = np.nan
+    cls[1, 0, 9, 1] = np.nan
+    e = np.exp(cls - cls.max(1, keepdims=True))
+    score = (e[:, 1] / e.sum(1)).reshape(B, -1)
+    idx = c_oracle.score_argmax(cls, loc, None, 0.0)[0]
+    assert np.array_equal(idx, np.argmax(score, 1))
+    assert list(idx[:2]) == [0, 3 * N + 7]
