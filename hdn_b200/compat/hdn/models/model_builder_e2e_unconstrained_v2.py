@@ -170,12 +170,25 @@ class ModelBuilder(nn.Module):
         return static_out
 
     def _stage1_packed(self, x, w):
-        out = self.track_new(x)
-        return ops.score_argmax_packed(out["cls"], out["loc_c"], self._window(out["cls"].shape[-1], x.device), w)
+        xf = self._necked(x, "neck")
+        if self._fusable(self.head, xf, self._k_sim):  # level sum + K6 inside the fused head's last launch: the maps are never stored
+            return self.head.fused(xf, self._k_sim, self._window(self.head.out_size(xf, self._k_sim), x.device), w, want_maps=False)[2]
+        cls, loc_c = self.head(self.zf, xf, self._k_sim)
+        return ops.score_argmax_packed(cls, loc_c, self._window(cls.shape[-1], x.device), w)
 
     def _stage2_packed(self, x):
-        out = self.track_new_lp(x, [0, 0])
-        return ops.score_argmax_packed(out["cls_lp"], out["loc_lp"], None, 0.0)
+        polar = torch.zeros(x.shape[0], 2, device=x.device)
+        x_lp, _ = self.logpolar_instance(x, polar, [0, 0])
+        xf = self._necked(x_lp, "neck_lp")
+        if self._fusable(self.head_lp, xf, self._k_lp):
+            return self.head_lp.fused(xf, self._k_lp, None, 0.0, want_maps=False)[2]
+        cls_lp, loc_lp = self.head_lp(self.zf_lp, xf, self._k_lp)
+        return ops.score_argmax_packed(cls_lp, loc_lp, None, 0.0)
+
+    @staticmethod
+    def _fusable(head, xf, kernels):
+        return (hasattr(head, "fused_eligible") and isinstance(xf, (list, tuple)) and head.fused_eligible(xf) and kernels is not None
+                and len({tuple(k.shape) for k in kernels}) == 1 and xf[0].shape[-1] == xf[0].shape[-2])
 
     def _stage3_packed(self, pair, h4p):
         """-> [B, 11]: H (9), homo score, similarity score PER ITEM.  For B = 1 these are exactly track_proj's returns (the

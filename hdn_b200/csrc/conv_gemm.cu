@@ -87,9 +87,14 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// Up to HDN_MAX_PROBLEMS same-shape convolutions per launch (the 3 levels x {cls, loc} branches of a BAN head share one shape):
+// blockIdx.z = problem * B + image.
 struct ConvGemmArgs {
-    const float *x, *wpk, *scale, *shift, *residual;  // wpk: hdn_conv_pack_weight_f32 output
-    float *out;
+    const float *x[HDN_MAX_PROBLEMS], *wpk[HDN_MAX_PROBLEMS], *scale[HDN_MAX_PROBLEMS], *shift[HDN_MAX_PROBLEMS],
+        *residual[HDN_MAX_PROBLEMS];  // wpk: hdn_conv_pack_weight_f32 output
+    float *out[HDN_MAX_PROBLEMS];
+    const float *w2[HDN_MAX_PROBLEMS];  // PROJECT mode: second 1x1 convolution [L, Cout] row-major (device); out = partial sums
+    int B, L;
     int Cin, Cout, H, W, taps, dil, relu;
     int Ho, Wo, off;  // output extent and the input offset of output pixel (0,0): 'same' -> (H, W, 0); 'valid' 3x3 -> (H-2d, W-2d, d)
 };
@@ -101,8 +106,11 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 // Warp-specialised: warps 0..7 (256 threads) are PRODUCERS (global -> registers -> hi/lo -> shared, TMEM drains, epilogue),
 // warp 8 is the MMA ISSUER.  Stages hand over through mbarriers (full: 256 producer arrivals; free: tcgen05.commit), so
 // staging of block k+1.. never waits for the issue of block k; two TMEM accumulators alternate per 256-deep K chunk.
-template <int BN, int STAGES, int RAW>
-__global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(ConvGemmArgs a) {
+// PROJECT: instead of storing its 128 x BN tile y = ReLU(BN(conv)), the CTA multiplies it by the matching 128-column slice of a
+// second 1x1 convolution w2 [L, Cout] (the `head[3]` layer of DepthwiseXCorr, ban.py:62-66) and stores the L x BN PARTIAL sums
+// (one per 128-channel tile; fixed summation order -> deterministic) -- the 256-channel hidden map never goes to HBM.
+template <int BN, int STAGES, int RAW, bool PROJECT>
+__global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(const __grid_constant__ ConvGemmArgs a) {
     constexpr int A_TILE = CG_BM * CG_BK * 4;  // bytes of one operand tile (hi or lo)
     constexpr int B_TILE = CG_BK * BN * 4;
     constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
@@ -117,7 +125,7 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(Co
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int HW = a.H * a.W, HWo = a.Ho * a.Wo;
-    const int pix0 = blockIdx.x * BN, co0 = blockIdx.y * CG_BM, img = blockIdx.z;
+    const int pix0 = blockIdx.x * BN, co0 = blockIdx.y * CG_BM, prob = blockIdx.z / a.B, img = blockIdx.z - prob * a.B;
     const int Ktot = a.taps * a.Cin;
     const int nkb = Ktot / CG_BK;
     const int nchunks = (nkb + CG_KCB - 1) / CG_KCB;
@@ -172,7 +180,7 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(Co
     } else if (warp == CG_THREADS / 32 + 1) {
         // ============================== weight loader: one 32 KB TMA bulk copy per K block ==============================
         if (elect_one()) {
-            const float *wsrc = a.wpk + (size_t)blockIdx.y * nkb * (2 * A_TILE / 4);
+            const float *wsrc = a.wpk[prob] + (size_t)blockIdx.y * nkb * (2 * A_TILE / 4);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES;
                 if (kb >= STAGES) mbar_wait(&bar_free[s], ((kb / STAGES) - 1) & 1);
@@ -183,7 +191,7 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(Co
         __syncwarp();
     } else {
         // ============================== producers (activations) ==============================
-        const float *xb = a.x + (size_t)img * a.Cin * HW;
+        const float *xb = a.x[prob] + (size_t)img * a.Cin * HW;
         // A: float4 slots f = tid + 256*j, j < 4:      r0 = f&7, kc = (f>>3)&7, rg = f>>6        (row = rg*8 + r0, k = kc*4..+3)
         // B: slots f = tid + 256*j, j < BN/32:          n = f % BN (= tid % BN for every j), kc = f / BN   (k = kc*4..+3)
         //    consecutive lanes -> consecutive pixels: coalesced scalar loads, and one conflict-free 16-byte store per slot.
@@ -269,16 +277,45 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(Co
         // ---- epilogue: remaining chunks -> registers -> BN / residual / ReLU -> global NCHW ----
         while (drained < nchunks) drain(drained++);
         const int co = co0 + row;
-        const float sc = a.scale ? __ldg(a.scale + co) : 1.f, sh = a.shift ? __ldg(a.shift + co) : 0.f;
+        const float *scp = a.scale[prob], *shp = a.shift[prob], *resp = a.residual[prob];
+        const float sc = scp ? __ldg(scp + co) : 1.f, sh = shp ? __ldg(shp + co) : 0.f;
         const size_t obase = ((size_t)img * a.Cout + co) * HWo;
+        if (!PROJECT) {
 #pragma unroll
-        for (int e = 0; e < HALF; ++e) {
-            const int p = pix0 + col_lo + e;
-            if (p < HWo) {
+            for (int e = 0; e < HALF; ++e) {
+                const int p = pix0 + col_lo + e;
+                if (p < HWo) {
+                    float y = fmaf(racc[e], sc, sh);
+                    if (resp) y += __ldg(resp + obase + p);
+                    if (a.relu) y = fmaxf(y, 0.f);
+                    a.out[prob][obase + p] = y;
+                }
+            }
+        } else {
+            // The pipeline stages are dead (the last accumulator was committed after every MMA had read them): stage the tile as
+            // ys[channel][pixel] (pitch BN + 1: lanes = consecutive channels hit consecutive banks) next to the w2 slice.
+            constexpr int YP = BN + 1;
+            float *ys = reinterpret_cast<float *>(smem);
+            float *w2s = ys + CG_BM * YP;  // [L][128]
+#pragma unroll
+            for (int e = 0; e < HALF; ++e) {
                 float y = fmaf(racc[e], sc, sh);
-                if (a.residual) y += __ldg(a.residual + obase + p);
                 if (a.relu) y = fmaxf(y, 0.f);
-                a.out[obase + p] = y;
+                ys[row * YP + col_lo + e] = y;
+            }
+            for (int i = tid; i < a.L * CG_BM; i += CG_THREADS) w2s[i] = __ldg(a.w2[prob] + (size_t)(i / CG_BM) * a.Cout + co0 + (i % CG_BM));
+            asm volatile("bar.sync 1, %0;" ::"n"(CG_THREADS) : "memory");  // the 256 producer threads only
+            const int c = tid % BN, p = pix0 + c;
+            for (int l = tid / BN; l < a.L; l += CG_THREADS / BN) {
+                const float *wr = w2s + l * CG_BM;
+                float s0 = 0.f, s1 = 0.f;  // two chains: channels in fixed order r = 0, 2, 4, ... and 1, 3, 5, ...
+#pragma unroll 8
+                for (int r = 0; r < CG_BM; r += 2) {
+                    s0 = fmaf(wr[r], ys[r * YP + c], s0);
+                    s1 = fmaf(wr[r + 1], ys[(r + 1) * YP + c], s1);
+                }
+                // partial sums of channel tile blockIdx.y:  out[tile][img][l][pixel]
+                if (p < HWo) a.out[prob][(((size_t)blockIdx.y * a.B + img) * a.L + l) * HWo + p] = s0 + s1;
             }
         }
     }
@@ -287,15 +324,16 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(Co
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)(2 * BN)));
 }
 
-template <int BN, int STAGES, int RAW>
-static int launch_conv_gemm(const ConvGemmArgs &a, int B, cudaStream_t st) {
+template <int BN, int STAGES, int RAW, bool PROJECT = false>
+static int launch_conv_gemm(const ConvGemmArgs &a, int nprob, cudaStream_t st) {
     constexpr size_t SMEM = (size_t)STAGES * (2 * CG_BM * CG_BK * 4 + 2 * CG_BK * BN * 4) + (size_t)RAW * (CG_BK * BN * 4) + 1024;
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
+    static_assert(!PROJECT || (size_t)(CG_BM * (BN + 1) + 8 * CG_BM) * 4 <= SMEM, "projection staging must fit the pipeline's shared memory");
     static DeviceOnce once;
-    if (int e = once.run([] { return cudaFuncSetAttribute(conv_gemm_tf32x3_kernel<BN, STAGES, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM); }))
+    if (int e = once.run([] { return cudaFuncSetAttribute(conv_gemm_tf32x3_kernel<BN, STAGES, RAW, PROJECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM); }))
         return e;
-    dim3 grid((a.Ho * a.Wo + BN - 1) / BN, a.Cout / CG_BM, B);
-    conv_gemm_tf32x3_kernel<BN, STAGES, RAW><<<grid, CG_THREADS + 64, SMEM, st>>>(a);
+    dim3 grid((a.Ho * a.Wo + BN - 1) / BN, a.Cout / CG_BM, a.B * nprob);
+    conv_gemm_tf32x3_kernel<BN, STAGES, RAW, PROJECT><<<grid, CG_THREADS + 64, SMEM, st>>>(a);
     count_launch();
     return launch_status();
 }
@@ -334,16 +372,57 @@ extern "C" int hdn_conv_gemm_supported(int Cin, int Cout, int ksize, int dilatio
     return (Cin >= 32 && Cin % 32 == 0 && Cout % CG_BM == 0 && (ksize == 1 || ksize == 3) && dilation >= 1) ? 1 : 0;
 }
 
+static int conv_gemm_multi(int n, const float *const *x, const float *const *wpk, const float *const *scale, const float *const *shift,
+                           const float *const *residual, const float *const *w2, float *const *out, int B, int Cin, int Cout, int H, int W,
+                           int ksize, int dilation, int valid, int relu, int L, cudaStream_t st) {
+    if (!x || !wpk || !out) return HDN_ERR_NULL;
+    if (n < 1 || n > HDN_MAX_PROBLEMS) return HDN_ERR_UNSUPPORTED;
+    if (B < 1 || H < 1 || W < 1 || (long long)B * n > 65535) return HDN_ERR_SHAPE;
+    if (!hdn_conv_gemm_supported(Cin, Cout, ksize, dilation)) return HDN_ERR_UNSUPPORTED;
+    const int shrink = (valid && ksize == 3) ? 2 * dilation : 0;
+    if (H - shrink < 1 || W - shrink < 1) return HDN_ERR_SHAPE;
+    ConvGemmArgs a{};
+    for (int i = 0; i < n; ++i) {
+        if (!x[i] || !wpk[i] || !out[i] || (w2 && !w2[i])) return HDN_ERR_NULL;
+        if (reinterpret_cast<uintptr_t>(wpk[i]) & 15u) return HDN_ERR_ALIGN;
+        a.x[i] = x[i];
+        a.wpk[i] = wpk[i];
+        a.scale[i] = scale ? scale[i] : nullptr;
+        a.shift[i] = shift ? shift[i] : nullptr;
+        a.residual[i] = residual ? residual[i] : nullptr;
+        a.w2[i] = w2 ? w2[i] : nullptr;
+        a.out[i] = out[i];
+    }
+    a.B = B; a.L = L;
+    a.Cin = Cin; a.Cout = Cout; a.H = H; a.W = W; a.taps = ksize * ksize; a.dil = dilation; a.relu = relu;
+    a.Ho = H - shrink; a.Wo = W - shrink; a.off = shrink / 2;
+    if (w2) {  // fused second 1x1: narrow pixel tiles (the projection's staging pitch), L <= 8
+        if (L < 1 || L > 8) return HDN_ERR_UNSUPPORTED;
+        return launch_conv_gemm<64, 3, 5, true>(a, n, st);
+    }
+    const long long tiles128 = (long long)((a.Ho * a.Wo + 127) / 128) * (Cout / CG_BM) * B * n;
+    // small problems (tracking batch sizes): narrower pixel tiles put more CTAs on the 148 SMs
+    return tiles128 >= 2 * sm_count() ? launch_conv_gemm<128, 2, 4>(a, n, st) : launch_conv_gemm<64, 3, 5>(a, n, st);
+}
+
 extern "C" int hdn_conv_gemm_f32(const float *x, const float *wpk, const float *scale, const float *shift, const float *residual, float *out,
                                  int B, int Cin, int Cout, int H, int W, int ksize, int dilation, int valid, int relu, hdn_stream_t stream) {
     if (!x || !wpk || !out) return HDN_ERR_NULL;
-    if (B < 1 || H < 1 || W < 1 || B > 65535) return HDN_ERR_SHAPE;
-    if (!hdn_conv_gemm_supported(Cin, Cout, ksize, dilation)) return HDN_ERR_UNSUPPORTED;
-    if (reinterpret_cast<uintptr_t>(wpk) & 15u) return HDN_ERR_ALIGN;
-    const int shrink = (valid && ksize == 3) ? 2 * dilation : 0;
-    if (H - shrink < 1 || W - shrink < 1) return HDN_ERR_SHAPE;
-    ConvGemmArgs a{x, wpk, scale, shift, residual, out, Cin, Cout, H, W, ksize * ksize, dilation, relu, H - shrink, W - shrink, shrink / 2};
-    const long long tiles128 = (long long)((a.Ho * a.Wo + 127) / 128) * (Cout / CG_BM) * B;
-    // small problems (tracking batch sizes): narrower pixel tiles put more CTAs on the 148 SMs
-    return tiles128 >= 2 * sm_count() ? launch_conv_gemm<128, 2, 4>(a, B, (cudaStream_t)stream) : launch_conv_gemm<64, 3, 5>(a, B, (cudaStream_t)stream);
+    return conv_gemm_multi(1, &x, &wpk, &scale, &shift, &residual, nullptr, &out, B, Cin, Cout, H, W, ksize, dilation, valid, relu, 0,
+                           (cudaStream_t)stream);
+}
+
+extern "C" int hdn_conv_gemm_multi_f32(int n, const float *const *x_host, const float *const *wpk_host, const float *const *scale_host,
+                                       const float *const *shift_host, float *const *out_host, int B, int Cin, int Cout, int H, int W, int ksize,
+                                       int dilation, int valid, int relu, hdn_stream_t stream) {
+    return conv_gemm_multi(n, x_host, wpk_host, scale_host, shift_host, nullptr, nullptr, out_host, B, Cin, Cout, H, W, ksize, dilation, valid, relu,
+                           0, (cudaStream_t)stream);
+}
+
+extern "C" int hdn_head_project_multi_f32(int n, const float *const *x_host, const float *const *wpk_host, const float *const *scale_host,
+                                          const float *const *shift_host, const float *const *w2_host, float *const *part_host, int B, int C,
+                                          int H, int W, int L, hdn_stream_t stream) {
+    if (!w2_host) return HDN_ERR_NULL;
+    return conv_gemm_multi(n, x_host, wpk_host, scale_host, shift_host, nullptr, w2_host, part_host, B, C, C, H, W, 1, 1, 0, 1, L,
+                           (cudaStream_t)stream);
 }

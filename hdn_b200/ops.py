@@ -326,6 +326,78 @@ def conv_gemm(x, wpk, scale=None, shift=None, residual=None, ksize=1, dilation=1
     return out
 
 
+def _ptr_array(tensors):
+    return (_vp * len(tensors))(*[t.data_ptr() if t is not None else None for t in tensors])
+
+
+def conv_gemm_multi(xs, wpks, scales, shifts, ksize=3, dilation=1, relu=True, valid=True, outs=None):
+    """n <= 8 same-shape convolutions (+ folded BatchNorm, ReLU) in ONE launch: the `conv_search` layers of the 3 levels x {cls, loc}
+    branches of MultiBAN / MultiCircBAN (hdn/models/head/ban.py:56-61).  xs[i] [B,Cin,H,W]; wpks[i] = pack_conv_weight(weight_i)."""
+    n = len(xs)
+    xs = [_dev(x, "x") for x in xs]
+    B, Cin, H, W = xs[0].shape
+    if any(tuple(x.shape) != (B, Cin, H, W) for x in xs):
+        raise RuntimeError("conv_gemm_multi: all problems must share one shape")
+    Cout = wpks[0].numel() // (2 * ksize * ksize * Cin)
+    shrink = 2 * dilation if (valid and ksize == 3) else 0
+    outs = [_out(None if outs is None else outs[i], (B, Cout, H - shrink, W - shrink), xs[0], "outs[%d]" % i) for i in range(n)]
+    with _on_device(xs[0]):
+        st = _lib.lib().hdn_conv_gemm_multi_f32(n, _ptr_array(xs), _ptr_array(wpks), _ptr_array(scales), _ptr_array(shifts), _ptr_array(outs), B, Cin,
+                                                Cout, H, W, ksize, dilation, int(bool(valid)), int(bool(relu)), _stream())
+    _lib.check(st, "hdn_conv_gemm_multi_f32")
+    return outs
+
+
+def head_project_multi(feats, wpks, scales, shifts, w2s, parts=None):
+    """Fused tail of DepthwiseXCorr for n branches in one launch: 1x1 (C->C) + BatchNorm + ReLU + 1x1 (C->L) on the correlation
+    features; the hidden map stays on chip.  w2s[i] [L,C].  -> parts[i] [C/128, B, L, H*W] partial sums (no bias; see head_score)."""
+    n = len(feats)
+    feats = [_dev(f, "feature") for f in feats]
+    B, C, H, W = feats[0].shape
+    L = w2s[0].shape[0]
+    if any(tuple(f.shape) != (B, C, H, W) for f in feats) or any(tuple(w.shape) != (L, C) for w in w2s):
+        raise RuntimeError("head_project_multi: all branches must share one shape")
+    w2s = [_dev(w, "w2") for w in w2s]
+    parts = [_out(None if parts is None else parts[i], (C // 128, B, L, H * W), feats[0], "parts[%d]" % i) for i in range(n)]
+    with _on_device(feats[0]):
+        st = _lib.lib().hdn_head_project_multi_f32(n, _ptr_array(feats), _ptr_array(wpks), _ptr_array(scales), _ptr_array(shifts), _ptr_array(w2s),
+                                                   _ptr_array(parts), B, C, H, W, L, _stream())
+    _lib.check(st, "hdn_head_project_multi_f32")
+    return parts
+
+
+def head_score(cls_parts, loc_parts, cls_bias, loc_bias, cls_w, loc_scale, loc_w, N, window=None, win_influence=0.0, want_maps=True,
+               maps=None, packed=None):
+    """End of MultiBAN.forward (ban.py:102-127) + K6 in one launch.  cls_parts[l] [ntile,B,2,N*N], loc_parts[l] [ntile,B,L,N*N] from
+    head_project_multi; cls_bias[l] [2], loc_bias[l] [L] device tensors; cls_w / loc_scale / loc_w: python floats per level.
+    -> (cls [B,2,N,N] | None, loc [B,L,N,N] | None, packed uint8 buffer in score_argmax_packed's layout)."""
+    nlev = len(cls_parts)
+    ntile, B, two, n = cls_parts[0].shape
+    L = loc_parts[0].shape[2]
+    if two != 2 or n != N * N:
+        raise RuntimeError("head_score: cls parts must be [ntile,B,2,N*N]")
+    dev = cls_parts[0].device
+    if window is not None:
+        window = _dev(window, "window", torch.float64)
+        if window.numel() != N * N:
+            raise RuntimeError("window must have N*N entries")
+    if want_maps:
+        cls, loc = maps if maps is not None else (torch.empty((B, 2, N, N), device=dev), torch.empty((B, L, N, N), device=dev))
+    else:
+        cls = loc = None
+    o_ps, o_sc, o_g, total = 8 * B, 16 * B, 20 * B, 20 * B + 4 * B * L
+    buf = packed if packed is not None else torch.empty(total + (-total) % 8, device=dev, dtype=torch.uint8)
+    base = buf.data_ptr()
+    fl = ctypes.c_float * nlev
+    with _on_device(cls_parts[0]):
+        st = _lib.lib().hdn_head_score_f32(nlev, ntile, _ptr_array(cls_parts), _ptr_array(loc_parts), _ptr_array(cls_bias), _ptr_array(loc_bias),
+                                           fl(*cls_w), fl(*loc_scale), fl(*loc_w), _ptr(cls) if cls is not None else None,
+                                           _ptr(loc) if loc is not None else None, _ptr(window) if window is not None else None,
+                                           float(win_influence), _vp(base), _vp(base + o_ps), _vp(base + o_sc), _vp(base + o_g), B, L, N, _stream())
+    _lib.check(st, "hdn_head_score_f32")
+    return cls, loc, buf
+
+
 def conv_gemm_supported(Cin, Cout, ksize, dilation=1):
     return bool(_lib.lib().hdn_conv_gemm_supported(Cin, Cout, ksize, dilation))
 

@@ -131,6 +131,34 @@ int hdn_conv_pack_weight_f32(const float *wt, float *packed, int Cout, int Ktot,
 int hdn_conv_gemm_f32(const float *x, const float *wpk, const float *scale, const float *shift, const float *residual, float *out, int B,
                       int Cin, int Cout, int H, int W, int ksize, int dilation, int valid, int relu, hdn_stream_t stream);
 
+/* n <= HDN_MAX_PROBLEMS convolutions of one shape in ONE launch (blockIdx.z = problem x image): the 3 levels x {cls, loc}
+ * `conv_search` / `conv_kernel` layers of MultiBAN / MultiCircBAN (hdn/models/head/ban.py:56-61, ban_lp.py:19-24), each
+ * 3x3 + BatchNorm + ReLU on a neck feature map.  *_host: HOST arrays of n device pointers (scale_host / shift_host may be NULL). */
+int hdn_conv_gemm_multi_f32(int n, const float *const *x_host, const float *const *wpk_host, const float *const *scale_host,
+                            const float *const *shift_host, float *const *out_host, int B, int Cin, int Cout, int H, int W, int ksize,
+                            int dilation, int valid, int relu, hdn_stream_t stream);
+
+/* Fused tail of DepthwiseXCorr (hdn/models/head/ban.py:62-66, :77): head = 1x1 (C->C, no bias) + BatchNorm + ReLU + 1x1 (C->L, bias)
+ * applied to the correlation features, for n <= HDN_MAX_PROBLEMS branches in one launch.  The hidden C-channel map stays on chip:
+ * each CTA multiplies its 128-channel x 64-pixel tile by the matching slice of the second convolution and stores PARTIAL sums.
+ *   x_host[i]   [B,C,H,W] correlation features of branch i        wpk_host[i] packed first 1x1 (hdn_conv_pack_weight_f32)
+ *   scale/shift [C] folded BatchNorm                               w2_host[i]  [L,C] second 1x1 weight (row-major, device)
+ *   part_host[i] [C/128, B, L, H*W] partial sums (bias NOT added): hdn_head_score_f32 finishes them. */
+int hdn_head_project_multi_f32(int n, const float *const *x_host, const float *const *wpk_host, const float *const *scale_host,
+                               const float *const *shift_host, const float *const *w2_host, float *const *part_host, int B, int C, int H,
+                               int W, int L, hdn_stream_t stream);
+
+/* End of MultiBAN.forward (ban.py:102-127) fused with K6: per level l the partial sums are added (fixed order) + bias,
+ * loc is scaled by loc_scale[l], the levels are combined with cls_w / loc_w (= softmax(cls_weight), softmax(loc_weight), HOST
+ * floats), then hdn_score_argmax_f32's epilogue runs on the combined maps.
+ *   cls_parts_host[l] [ntile,B,2,N*N], loc_parts_host[l] [ntile,B,L,N*N], cls_bias_host[l] [2], loc_bias_host[l] [L]  (device)
+ *   cls_out [B,2,N,N] / loc_out [B,L,N,N]: the combined maps `track_new` returns; NULL = not stored. */
+int hdn_head_score_f32(int nlev, int ntile, const float *const *cls_parts_host, const float *const *loc_parts_host,
+                       const float *const *cls_bias_host, const float *const *loc_bias_host, const float *cls_w_host,
+                       const float *loc_scale_host, const float *loc_w_host, float *cls_out, float *loc_out, const double *window,
+                       double win_influence, int64_t *idx, double *pscore, float *score, float *gathered, int B, int L, int N,
+                       hdn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -142,3 +142,44 @@ def m1_chain(feats, threads=None):
     out["H"] = Hm
     out["warp"] = homo_warp(feats["gray"], Hm, feats["M"], feats["Minv"])
     return out
+
+
+# ---- the BAN heads from neck features: what hdn_b200.head_engine.HeadEngine fuses ------------------------------
+def _conv_bn_relu(x, w, scale, shift):
+    """nn.Conv2d(bias=False) -> eval-mode BatchNorm2d (folded to scale / shift) -> ReLU   (ban.py:56-61)"""
+    return F.relu(F.conv2d(x, w) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+
+
+def ban_head(w, z_fs, x_fs, circular, kernels=None):
+    """MultiBAN.forward / MultiCircBAN.forward (hdn/models/head/ban.py:73-78, 102-127; ban_lp.py:33-40, 65-92) on the torch calls
+    the reference makes.  w: HeadWeights.raw (per branch cls2, loc2, cls3, loc3, cls4, loc4).  kernels: pre-computed template side
+    (None = recompute `conv_kernel(z_f)` like the reference does on every frame, ban.py:74).  -> (cls, loc)"""
+    corr = xcorr_depthwise_circular if circular else xcorr_depthwise
+    outs = []
+    for i in range(6):
+        k = kernels[i] if kernels is not None else _conv_bn_relu(z_fs[i // 2], w["kernel_w"][i], w["kernel_scale"][i], w["kernel_shift"][i])
+        s = _conv_bn_relu(x_fs[i // 2], w["search_w"][i], w["search_scale"][i], w["search_shift"][i])
+        h = _conv_bn_relu(corr(s, k), w["hidden_w"][i], w["hidden_scale"][i], w["hidden_shift"][i])
+        outs.append(F.conv2d(h, w["w2"][i].view(w["w2"][i].shape[0], -1, 1, 1), w["b2"][i]))
+    cls = sum(outs[2 * l] * w["cls_w"][l] for l in range(3))
+    loc = sum(outs[2 * l + 1] * w["loc_scale"][l] * w["loc_w"][l] for l in range(3))
+    return cls, loc
+
+
+def template_kernels(w, z_fs):
+    return [_conv_bn_relu(z_fs[i // 2], w["kernel_w"][i], w["kernel_scale"][i], w["kernel_shift"][i]) for i in range(6)]
+
+
+def fused_chain(feats, w_sim, w_lp, window, win_influence, kernels=None):
+    """One pass of the chain HeadEngine runs, on CPU tensors: both BAN heads from neck features, K6 epilogues, K3, K5 + K4.
+    kernels: (k_sim, k_lp) hoisted template kernels or None (reference behaviour: recomputed per call)."""
+    out = {}
+    out["cls"], out["loc"] = ban_head(w_sim, feats["zf"], feats["xf"], False, kernels[0] if kernels else None)
+    out["cls_lp"], out["loc_lp"] = ban_head(w_lp, feats["zf_lp"], feats["xf_lp"], True, kernels[1] if kernels else None)
+    out["idx"], out["pscore"], out["score"], out["center"] = score_argmax(out["cls"], out["loc"], window, win_influence)
+    out["idx_lp"], out["pscore_lp"], out["score_lp"], out["sim_lp"] = score_argmax(out["cls_lp"], out["loc_lp"], None, 0.0)
+    out["x_lp"] = logpolar(feats["img"], None, 0.0, feats["S"])
+    Hm = dlt_solve(feats["src"], feats["off"]).squeeze(1)
+    out["H"] = Hm
+    out["warp"] = homo_warp(feats["gray"], Hm, feats["M"], feats["Minv"])
+    return out

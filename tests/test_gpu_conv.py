@@ -75,3 +75,109 @@ def test_fused_block_equals_module_path():
         fused = convs.conv_bn_act(conv, bn, x, residual=r, relu=True)
         plain = torch.relu(bn(conv(x)) + r)
     assert torch.allclose(fused, plain, rtol=1e-4, atol=1e-5 * float(plain.abs().max()))
+
+
+def test_conv_gemm_multi_equals_single_launches():
+    """6 same-shape problems in one launch (blockIdx.z = problem x image) == 6 single launches, bit for bit."""
+    from hdn_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    xs = [torch.randn(2, 256, 17, 17, device="cuda", generator=g) for _ in range(3)]
+    ws = [torch.randn(256, 256, 3, 3, device="cuda", generator=g) * 0.03 for _ in range(6)]
+    sc = [1 + 0.1 * torch.randn(256, device="cuda", generator=g) for _ in range(6)]
+    sh = [0.1 * torch.randn(256, device="cuda", generator=g) for _ in range(6)]
+    packs = [ops.pack_conv_weight(w) for w in ws]
+    multi = ops.conv_gemm_multi([xs[i // 2] for i in range(6)], packs, sc, sh, ksize=3, relu=True, valid=True)
+    for i in range(6):
+        single = ops.conv_gemm(xs[i // 2], packs[i], sc[i], sh[i], ksize=3, relu=True, valid=True)
+        assert tuple(single.shape) == (2, 256, 15, 15) and torch.equal(single, multi[i])
+
+
+@pytest.mark.parametrize("B,N,L", [(1, 25, 2), (3, 33, 2), (2, 13, 4), (2, 29, 4)])
+def test_fused_head_tail_equals_reference_ops(B, N, L):
+    """hdn_head_project_multi_f32 + hdn_head_score_f32 == the reference's tail of MultiBAN.forward (ban.py:62-66, 102-127):
+    per level 1x1 + BN + ReLU + 1x1 (+bias), loc * loc_scale, softmax-weighted level sums, then softmax / window / arg-max."""
+    from hdn_b200 import ops
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(B * 100 + N + L)
+    C, nlev = 256, 3
+    rnd = lambda *s: torch.randn(*s, device="cuda", generator=g)  # noqa: E731
+    feats = [rnd(B, C, N, N) for _ in range(2 * nlev)]                     # cls2, loc2, cls3, loc3, ...
+    w1 = [rnd(C, C, 1, 1) * (2.0 / C) ** 0.5 for _ in range(2 * nlev)]
+    sc = [1 + 0.1 * rnd(C) for _ in range(2 * nlev)]
+    sh = [0.1 * rnd(C) for _ in range(2 * nlev)]
+    w2 = [rnd(2 if i % 2 == 0 else L, C) * 0.1 for i in range(2 * nlev)]
+    b2 = [rnd(2 if i % 2 == 0 else L) * 0.1 for i in range(2 * nlev)]
+    cls_w = torch.softmax(rnd(nlev), 0).tolist()
+    loc_w = torch.softmax(rnd(nlev), 0).tolist()
+    loc_scale = (1 + 0.2 * rnd(nlev)).tolist()
+    packs = [ops.pack_conv_weight(w) for w in w1]
+    cls_parts = ops.head_project_multi(feats[0::2], packs[0::2], sc[0::2], sh[0::2], w2[0::2])
+    loc_parts = ops.head_project_multi(feats[1::2], packs[1::2], sc[1::2], sh[1::2], w2[1::2])
+    assert tuple(cls_parts[0].shape) == (2, B, 2, N * N) and tuple(loc_parts[0].shape) == (2, B, L, N * N)
+    win = torch.from_numpy(np.outer(np.hanning(N), np.hanning(N)).flatten()).cuda()
+    w_infl = 0.1632532824922313
+    cls, loc, buf = ops.head_score(cls_parts, loc_parts, b2[0::2], b2[1::2], cls_w, loc_scale, loc_w, N, win, w_infl)
+    idx, ps, scr, gath = ops.unpack_scores(buf.cpu().numpy(), B, L)
+
+    def level(i, dt):
+        h = F.relu(F.conv2d(feats[i].to(dt), w1[i].to(dt)) * sc[i].to(dt).view(1, -1, 1, 1) + sh[i].to(dt).view(1, -1, 1, 1))
+        return F.conv2d(h, w2[i].to(dt).view(-1, C, 1, 1), b2[i].to(dt))
+
+    def combined(dt):
+        c = sum(level(2 * l, dt) * cls_w[l] for l in range(nlev))
+        o = sum(level(2 * l + 1, dt) * loc_scale[l] * loc_w[l] for l in range(nlev))
+        return c, o
+
+    c64, o64 = combined(torch.float64)
+    c32, o32 = combined(torch.float32)
+    for got, want, lib in ((cls, c64, c32), (loc, o64, o32)):
+        den = float(want.abs().max())
+        err = float((got.double() - want).abs().max()) / den
+        err_lib = float((lib.double() - want).abs().max()) / den
+        assert err < 1e-5 and err < 8 * max(err_lib, 3e-7), (err, err_lib)
+    # the fused K6 on the combined maps == the stand-alone K6 kernel on the same maps (bit for bit)
+    idx2, ps2, sc2, g2 = ops.score_argmax(cls, loc, win, w_infl)
+    assert np.array_equal(idx, idx2.cpu().numpy()) and np.array_equal(ps, ps2.cpu().numpy()) and np.array_equal(scr, sc2.cpu().numpy())
+    assert np.array_equal(gath, g2.cpu().numpy())
+    # maps not requested: same scores
+    _, _, buf2 = ops.head_score(cls_parts, loc_parts, b2[0::2], b2[1::2], cls_w, loc_scale, loc_w, N, win, w_infl, want_maps=False)
+    assert torch.equal(buf, buf2)
+
+
+@pytest.mark.parametrize("workload,B,chunk,shared", [("127/255", 5, 2, False), ("127/255", 3, 4, True), ("256/512", 2, 1, False)])
+def test_head_engine_equals_cpu_port(workload, B, chunk, shared):
+    """The fused chain from neck features (HeadEngine: conv_search -> correlation -> 1x1 tail -> level sum + K6, K3, K5 + K4),
+    device-resident and through the pinned-host pipeline, against the CPU port of the reference's own torch calls
+    (oracle/torch_port.fused_chain).  Maps within 1e-3; arg-max indices bit-exact."""
+    from hdn_b200 import head_engine as he
+    from hdn_b200.engine import WIN_INFL
+    from oracle import c_oracle, torch_port as tp
+    dev = torch.device("cuda")
+    host = he.make_inputs(workload, B, seed=5, shared_template=shared)
+    eng = he.HeadEngine(workload, B, dev, chunk=chunk)
+    up = lambda v: [t.to(dev) for t in v] if isinstance(v, list) else v.to(dev)  # noqa: E731
+    eng.set_template(up(host["zf"]), up(host["zf_lp"]))
+    eng.bind({k: up(host[k]) for k in he.FRAME_KEYS})
+    out = {k: v.cpu() for k, v in eng.run().items()}
+    w_sim, w_lp = ({k: ([t.cpu() for t in v] if isinstance(v, list) and isinstance(v[0], torch.Tensor) else v) for k, v in w.raw.items()}
+                   for w in (eng.w_sim, eng.w_lp))
+    M, Mi = c_oracle.default_M(127, 127)
+    feats = dict(host, S=he.NECK[workload]["S"], M=torch.from_numpy(M), Minv=torch.from_numpy(Mi))
+    win = np.outer(np.hanning(eng.N), np.hanning(eng.N)).flatten()
+    ref = tp.fused_chain(feats, w_sim, w_lp, win, WIN_INFL)
+    for k in ("cls", "loc", "cls_lp", "loc_lp", "x_lp"):
+        r = ref[k].numpy()
+        atol = 1e-4 * np.abs(r).max()
+        assert np.all(np.abs(out[k].numpy() - r) <= atol + 1e-3 * np.abs(r)), k
+    assert np.array_equal(out["idx"].numpy(), ref["idx"]) and np.array_equal(out["idx_lp"].numpy(), ref["idx_lp"])
+    assert np.allclose(out["center"].numpy(), ref["center"], rtol=1e-3, atol=1e-4) and np.allclose(out["sim_lp"].numpy(), ref["sim_lp"], rtol=1e-3, atol=1e-4)
+    assert np.allclose(out["H"].numpy(), ref["H"].numpy(), rtol=1e-3, atol=1e-5)
+    # end to end through pinned host buffers: same results as the device-resident run
+    pinned = he.make_inputs(workload, B, seed=5, shared_template=shared, pin=True)
+    h2d, d2h = eng.alloc_host_io(pinned)
+    assert h2d == sum(sum(t.numel() * 4 for t in pinned[k]) if isinstance(pinned[k], list) else pinned[k].numel() * 4 for k in he.FRAME_KEYS)
+    res = eng.run_host(pinned)
+    torch.cuda.synchronize()
+    for k in he.HeadEngine.HOST_OUT:
+        assert torch.equal(res[k], out[k]), k
