@@ -38,7 +38,7 @@ class LockstepTrackers:
         return self._drive([t._track_steps(fr_idx, img) for t, img in zip(self.trackers, imgs)])
 
     def _drive(self, gens):
-        from hdn.tracker.hdn_tracker_proj_e2e import serve
+        from hdn.tracker.hdn_tracker_proj_e2e import serve, stack_requests
         n = len(gens)
         results = [None] * n
 
@@ -59,7 +59,7 @@ class LockstepTrackers:
             kinds = {pending[i][1] for i in live}
             if len(kinds) != 1:
                 raise RuntimeError("trackers left lock-step: %s" % sorted(kinds))
-            answers = serve(self.model, kinds.pop(), np.concatenate([pending[i][2] for i in live], 0))
+            answers = serve(self.model, kinds.pop(), stack_requests([pending[i][2] for i in live]))
             nxt = list(self.pool.map(lambda ia: advance(ia[0], ia[1]), zip(live, answers)))
             for i, p in zip(live, nxt):
                 pending[i] = p

@@ -13,7 +13,13 @@ The three gates (pscore < 0.05, lp score < 0.25, homo_score > 2.5) and the singu
 What differs from the reference is only where work happens: stage epilogues run on the device (K6) with one packed
 read-back each, the template-side head convolutions are cached, the crop for stage 3 is not bounced
 device->host->device, and `get_mask_window` (whose result track_proj never reads, model_builder...py:161) is skipped.
+With cfg.CUDA the per-frame pixel work (warpPerspective, the three crops + resizes, the cubic rotation, the gray
+normalisation: ~45 ms of single-threaded OpenCV per 1280x720 frame in the reference) also runs on the device, bit-compatible
+with OpenCV (hdn_b200/preproc.py): the frame is uploaded once and the host keeps only the 3x3 algebra.
+HDN_B200_DEVICE_PREPROC=0 restores the host path.
 """
+import os
+
 import cv2
 import numpy as np
 import torch
@@ -28,11 +34,22 @@ from homo_estimator.Deep_homography.Oneline_DLTv1.tools.get_img_info import get_
 _EYE = [[1, 0, 0], [0, 1, 0], [0, 0, 1]]
 
 
+def stack_requests(payloads):
+    """Batch the per-sequence payloads of one stage (host arrays or device tensors)."""
+    if isinstance(payloads[0], torch.Tensor):
+        return payloads[0] if len(payloads) == 1 else torch.cat(payloads, 0)
+    return payloads[0] if len(payloads) == 1 else np.concatenate(payloads, 0)
+
+
 def serve(model, kind, batch):
-    """Answer one (possibly batched) stage request.  batch: float32 ndarray [B,...].  -> list of B per-item results."""
-    x = torch.from_numpy(np.ascontiguousarray(batch))
-    if cfg.CUDA:
-        x = x.pin_memory().cuda(non_blocking=True)
+    """Answer one (possibly batched) stage request.  batch: float32 ndarray [B,...] or a device tensor (device-side
+    pre-processing).  -> list of B per-item results."""
+    if isinstance(batch, torch.Tensor):
+        x = batch
+    else:
+        x = torch.from_numpy(np.ascontiguousarray(batch))
+        if cfg.CUDA:
+            x = x.pin_memory().cuda(non_blocking=True)
     B = x.shape[0]
     if kind == "template":
         model.template(x)
@@ -68,6 +85,17 @@ class hdnTrackerHomo(hdnTracker):
         self.p = Point(cfg.POINT.STRIDE, cfg.TRAIN.OUTPUT_SIZE, cfg.TRAIN.EXEMPLAR_SIZE // 2)
         self.points_lp = self.generate_points_lp(cfg.POINT.STRIDE_LP, cfg.POINT.STRIDE_LP, cfg.TRAIN.OUTPUT_SIZE_LP)
         self.model.eval()
+        self._pre = None
+        self.device_preproc = os.environ.get("HDN_B200_DEVICE_PREPROC", "1") != "0"
+
+    def _preproc(self):
+        """The device-side pixel pipeline (None = host OpenCV path: CPU configuration or HDN_B200_DEVICE_PREPROC=0)."""
+        if not (self.device_preproc and cfg.CUDA and torch.cuda.is_available()):
+            return None
+        if self._pre is None:
+            from hdn_b200.preproc import FramePreproc
+            self._pre = FramePreproc(next(self.model.parameters()).device)
+        return self._pre
 
     # ------------------------------------------------------------------ stage 3 network call
     def homo_estimate(self, tmp, search, tmp_mask=None):
@@ -107,6 +135,7 @@ class hdnTrackerHomo(hdnTracker):
         self.lost, self.lost_count, self.last_lost = True, 0, False
         self.init_points = np.array(gt_points).astype(np.float32)
         self.init_homo_tmp, self.print_tmp_img = get_template_info(self.z_crop_sm[:, 0:3, :, :])
+        self._tmpl_gray_dev = None  # float32 device copy of init_homo_tmp, made on first use by the device-side path
         self.H_total = np.array(_EYE, dtype=np.float32)
         self.H_total_sim = np.array(_EYE, dtype=np.float32)
         self.uncertain = 0
@@ -137,7 +166,15 @@ class hdnTrackerHomo(hdnTracker):
         # 0. bring the frame back into the template's pose
         if np.linalg.det(self.H_total) == 0:
             self.H_total = np.array(_EYE).astype(np.float32)
-        img = cv2.warpPerspective(img, np.linalg.inv(self.H_total), (img.shape[1], img.shape[0]), borderMode=cv2.BORDER_REPLICATE)
+        pre = self._preproc()
+        frame_w, frame_h = img.shape[1], img.shape[0]
+        if pre is not None:  # one upload of the frame; every pixel operation below runs on the device, bit-compatible with OpenCV
+            pre.upload(img)
+            img = pre.warp_perspective(np.linalg.inv(self.H_total))
+            crop = lambda src, pos, msz, osz: pre.crop(src, pos, msz, osz, self.channel_average)  # noqa: E731
+        else:
+            img = cv2.warpPerspective(img, np.linalg.inv(self.H_total), (frame_w, frame_h), borderMode=cv2.BORDER_REPLICATE)
+            crop = lambda src, pos, msz, osz: crop_window(src, pos, msz, osz, self.channel_average)[0]  # noqa: E731
         init_points = self.init_points.reshape(-1, 2).astype(np.float32)
         s_z = cur_sz = self.init_s_z
         center_pos = self.init_pos
@@ -146,8 +183,7 @@ class hdnTrackerHomo(hdnTracker):
         s_x = np.floor(s_z * ratio)
 
         # 1. translation
-        x_crop, _ = crop_window(img, center_pos, cfg.TRACK.INSTANCE_SIZE, s_x, self.channel_average)
-        idx, ps, sc, g = yield ("stage1", x_crop)
+        idx, ps, sc, g = yield ("stage1", crop(img, center_pos, cfg.TRACK.INSTANCE_SIZE, s_x))
         best_idx, pbest, best_score, pred_c = int(idx), ps, sc, decode_center(self.points, int(idx), g)
         stop_update = pbest < 0.05
         center = [0, 0] if stop_update else pred_c / scale_z
@@ -156,8 +192,7 @@ class hdnTrackerHomo(hdnTracker):
         self.center_pos = np.array([cx, cy])
 
         # 2. scale / rotation in log-polar coordinates
-        x_moved, _ = crop_window(img, self.center_pos, cfg.TRACK.INSTANCE_SIZE, s_x, self.channel_average)
-        idx, _, lp_score, g = yield ("stage2", x_moved)
+        idx, _, lp_score, g = yield ("stage2", crop(img, self.center_pos, cfg.TRACK.INSTANCE_SIZE, s_x))
         sim_lp = decode_logpolar(self.points_lp, int(idx), g)
         if stop_update or lp_score < 0.25:
             sim_lp = [1, 1, 0, 0]
@@ -168,12 +203,20 @@ class hdnTrackerHomo(hdnTracker):
         self.scale *= scale_delta
 
         # 3. residual homography on the de-rotated, re-scaled no-context crop
-        rot_img = img_rot_around_center(img, cx, cy, img.shape[1], img.shape[0], -rot_delta)
-        x_homo, _ = crop_window(rot_img, self.center_pos, cfg.TRACK.EXEMPLAR_SIZE, self.init_s_z_sm * scale_delta, self.channel_average)
         crop_w = self.z_crop_points_sm[2] - self.z_crop_points_sm[0] + 1
         crop_h = self.z_crop_points_sm[3] - self.z_crop_points_sm[1] + 1
-        search_gray, _ = get_search_info(torch.from_numpy(x_homo)[:, 0:3, :, :])
-        both = yield ("stage3", np.concatenate([self.init_homo_tmp, search_gray], 0).astype(np.float32)[np.newaxis])  # H (9) + scores
+        if pre is not None:
+            rot_img = pre.rotate(img, cx, cy, -rot_delta)
+            search_gray = pre.crop(rot_img, self.center_pos, cfg.TRACK.EXEMPLAR_SIZE, self.init_s_z_sm * scale_delta, self.channel_average, gray=True)
+            if self._tmpl_gray_dev is None or self._tmpl_gray_dev.device != search_gray.device:
+                self._tmpl_gray_dev = torch.from_numpy(np.asarray(self.init_homo_tmp).astype(np.float32)).to(search_gray.device)
+            pair = torch.cat((self._tmpl_gray_dev, search_gray), 0)[None]
+        else:
+            rot_img = img_rot_around_center(img, cx, cy, frame_w, frame_h, -rot_delta)
+            x_homo, _ = crop_window(rot_img, self.center_pos, cfg.TRACK.EXEMPLAR_SIZE, self.init_s_z_sm * scale_delta, self.channel_average)
+            search_gray, _ = get_search_info(torch.from_numpy(x_homo)[:, 0:3, :, :])
+            pair = np.concatenate([self.init_homo_tmp, search_gray], 0).astype(np.float32)[np.newaxis]
+        both = yield ("stage3", pair)  # H (9) + scores
         homo_score = both[9]
         H_hm = np.linalg.inv(both[:9].reshape(3, 3))
         H_hm = (1.0 / H_hm.item(8)) * H_hm

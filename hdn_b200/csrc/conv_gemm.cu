@@ -114,7 +114,6 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(co
     constexpr int A_TILE = CG_BM * CG_BK * 4;  // bytes of one operand tile (hi or lo)
     constexpr int B_TILE = CG_BK * BN * 4;
     constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
-    constexpr int RAW_STAGE = B_TILE;  // landing ring of the activation prefetch (fp32 as loaded)
     constexpr uint32_t A_SBO = 128, A_LBO = (CG_BM / 8) * 128;  // K-major: 8-row groups 128 B apart, 4-wide K chunks A_LBO apart
     constexpr uint32_t B_SBO = 128, B_LBO = (BN / 8) * 128;     // K-major as well (pixel rows): the tile is transposed while staging
     // kind::tf32, fp32 accumulate, A and B K-major, N = BN, M = 128 (cute::UMMA::InstrDescriptor bit layout)
@@ -221,57 +220,55 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(co
             mbar_arrive(&bar_acc_free[chunk & 1]);
         };
 
-        // Landing ring: block kb's activations are fetched RAW-1 blocks ahead with cp.async into the slot the SAME thread later
-        // converts (so cp.async.wait_group alone orders it), laid out [k/4][pixel][k%4] so that one LDS.128 returns the 4
-        // consecutive-k values a 16-byte row of the K-major core matrix needs.
-        unsigned char *raw = smem + STAGES * STAGE;
-        auto fetch = [&](int kb) {
-            if (kb < nkb) {
-                const int k0 = kb * CG_BK;
-                const int tap = k0 / a.Cin, ci0 = k0 - tap * a.Cin;
-                const int dy = a.taps == 1 ? 0 : (tap / 3 - 1) * a.dil, dx = a.taps == 1 ? 0 : (tap % 3 - 1) * a.dil;
-                float *rb = reinterpret_cast<float *>(raw + (kb % RAW) * RAW_STAGE);
-                const int r = b_r + dy, c = b_c + dx;
-                const bool ok = r >= 0 && r < a.H && c >= 0 && c < a.W;
-                const float *src = xb + (size_t)ci0 * HW + (ok ? r * a.W + c : 0);
+        // Activations: block kb's [32 k][BN pixels] tile is read straight into registers with coalesced 4-byte loads (NCHW rows
+        // of odd length are only 4-byte aligned; consecutive lanes = consecutive pixels -> one 128-byte line per warp load,
+        // predicated off = convolution padding / tile tail), ONE block ahead of the block being converted, so the loads of
+        // block kb+1 are in flight while block kb is split (hi / lo) and stored into the canonical no-swizzle K-major UMMA
+        // layout.  (The first version staged them through a cp.async landing ring: 16 4-byte LDGSTS per thread and block kept
+        // the load/store unit busier than the tensor core -- profiles/r01_ncu_conv_gemm.md.)
+        auto load_block = [&](int kb, float (&v)[NBJ][4]) {
+            const int k0 = kb * CG_BK;
+            const int tap = k0 / a.Cin, ci0 = k0 - tap * a.Cin;
+            const int dy = a.taps == 1 ? 0 : (tap / 3 - 1) * a.dil, dx = a.taps == 1 ? 0 : (tap % 3 - 1) * a.dil;
+            const int r = b_r + dy, c = b_c + dx;
+            const bool ok = r >= 0 && r < a.H && c >= 0 && c < a.W;
+            const float *src = xb + (size_t)ci0 * HW + (ok ? r * a.W + c : 0);
 #pragma unroll
-                for (int j = 0; j < NBJ; ++j) {
-                    const int kc = (tid + CG_THREADS * j) / BN;
+            for (int j = 0; j < NBJ; ++j) {
+                const int kc = (tid + CG_THREADS * j) / BN;
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) cp_async4(rb + (kc * BN + bn) * 4 + e, src + (size_t)(kc * 4 + e) * HW, ok ? 4u : 0u);
-                }
+                for (int e = 0; e < 4; ++e) v[j][e] = ok ? __ldg(src + (size_t)(kc * 4 + e) * HW) : 0.f;
             }
-            cp_async_commit();  // one group per block, also when empty, so the wait count below stays uniform
         };
-#pragma unroll
-        for (int i = 0; i < RAW - 1; ++i) fetch(i);
-
         int drained = 0;
-        for (int kb = 0; kb < nkb; ++kb) {
+        auto stage_block = [&](int kb, const float (&v)[NBJ][4]) {
             const int s = kb % STAGES;
-            fetch(kb + RAW - 1);
-            cp_async_wait<RAW - 1>();  // block kb has landed (this thread's own slots)
             // ---- a chunk that was completely staged a few blocks ago is (nearly) through the tensor core: fold it now ----
             if (drained < nchunks && kb >= (drained + 1) * CG_KCB + 2) drain(drained++);
             // ---- the MMAs that read this stage STAGES blocks ago must have retired ----
             if (kb >= STAGES) mbar_wait(&bar_free[s], ((kb / STAGES) - 1) & 1);
-            // ---- landing slot -> hi / lo -> shared (canonical no-swizzle K-major UMMA layouts) ----
-            const float *rb = reinterpret_cast<const float *>(raw + (kb % RAW) * RAW_STAGE);
             float *b_hi = reinterpret_cast<float *>(smem + s * STAGE + 2 * A_TILE), *b_lo = b_hi + B_TILE / 4;
 #pragma unroll
             for (int j = 0; j < NBJ; ++j) {
                 const int kc = (tid + CG_THREADS * j) / BN;
-                const float4 v = *reinterpret_cast<const float4 *>(rb + (kc * BN + bn) * 4);
                 float4 h, l;
-                split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+                split_tf32(v[j][0], h.x, l.x); split_tf32(v[j][1], h.y, l.y); split_tf32(v[j][2], h.z, l.z); split_tf32(v[j][3], h.w, l.w);
                 const int off = (kc * B_LBO + (bn >> 3) * B_SBO + (bn & 7) * 16) >> 2;
                 *reinterpret_cast<float4 *>(b_hi + off) = h;
                 *reinterpret_cast<float4 *>(b_lo + off) = l;
             }
-#ifndef HDN_EXP_NOFENCE
             fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
-#endif
             mbar_arrive(&bar_full[s]);
+        };
+        float va[NBJ][4], vb[NBJ][4];
+        load_block(0, va);
+        for (int kb = 0; kb < nkb; kb += 2) {
+            if (kb + 1 < nkb) load_block(kb + 1, vb);
+            stage_block(kb, va);
+            if (kb + 1 < nkb) {
+                if (kb + 2 < nkb) load_block(kb + 2, va);
+                stage_block(kb + 1, vb);
+            }
         }
 
         // ---- epilogue: remaining chunks -> registers -> BN / residual / ReLU -> global NCHW ----
@@ -326,7 +323,7 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(co
 
 template <int BN, int STAGES, int RAW, bool PROJECT = false>
 static int launch_conv_gemm(const ConvGemmArgs &a, int nprob, cudaStream_t st) {
-    constexpr size_t SMEM = (size_t)STAGES * (2 * CG_BM * CG_BK * 4 + 2 * CG_BK * BN * 4) + (size_t)RAW * (CG_BK * BN * 4) + 1024;
+    constexpr size_t SMEM = (size_t)STAGES * (2 * CG_BM * CG_BK * 4 + 2 * CG_BK * BN * 4) + 1024;
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
     static_assert(!PROJECT || (size_t)(CG_BM * (BN + 1) + 8 * CG_BM) * 4 <= SMEM, "projection staging must fit the pipeline's shared memory");
     static DeviceOnce once;
@@ -398,11 +395,11 @@ static int conv_gemm_multi(int n, const float *const *x, const float *const *wpk
     a.Ho = H - shrink; a.Wo = W - shrink; a.off = shrink / 2;
     if (w2) {  // fused second 1x1: narrow pixel tiles (the projection's staging pitch), L <= 8
         if (L < 1 || L > 8) return HDN_ERR_UNSUPPORTED;
-        return launch_conv_gemm<64, 3, 5, true>(a, n, st);
+        return launch_conv_gemm<64, 4, 0, true>(a, n, st);
     }
     const long long tiles128 = (long long)((a.Ho * a.Wo + 127) / 128) * (Cout / CG_BM) * B * n;
     // small problems (tracking batch sizes): narrower pixel tiles put more CTAs on the 148 SMs
-    return tiles128 >= 2 * sm_count() ? launch_conv_gemm<128, 2, 4>(a, n, st) : launch_conv_gemm<64, 3, 5>(a, n, st);
+    return tiles128 >= 2 * sm_count() ? launch_conv_gemm<128, 3, 0>(a, n, st) : launch_conv_gemm<64, 4, 0>(a, n, st);
 }
 
 extern "C" int hdn_conv_gemm_f32(const float *x, const float *wpk, const float *scale, const float *shift, const float *residual, float *out,

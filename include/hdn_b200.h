@@ -159,6 +159,29 @@ int hdn_head_score_f32(int nlev, int ntile, const float *const *cls_parts_host, 
                        double win_influence, int64_t *idx, double *pscore, float *score, float *gathered, int B, int L, int N,
                        hdn_stream_t stream);
 
+/* ---- device-side frame pre-processing: bit-compatible with the OpenCV calls of the reference ------------------
+ * Frames are uint8 HWC (BGR, 3 channels, dense) in DEVICE memory; small parameters are HOST pointers. */
+
+/* cv2.warpPerspective(img, M, (W, H), borderMode=BORDER_REPLICATE) of hdn/tracker/hdn_tracker_proj_e2e.py:154 (bilinear, 5-bit
+ * positions, 15-bit weights).  Minv_host: the 3x3 DESTINATION -> SOURCE map, i.e. cv2.invert(M) (row-major doubles): OpenCV inverts
+ * the matrix it is given before sampling, the caller passes that inverse.  dst != src. */
+int hdn_warp_perspective_u8(const uint8_t *src, uint8_t *dst, int H, int W, const double *Minv_host, hdn_stream_t stream);
+
+/* cv2.warpAffine(img, M, (W, H), flags=2 (INTER_CUBIC), borderMode=BORDER_REPLICATE) of img_rot_around_center,
+ * hdn/utils/transform.py:69-100.  M_host: the FORWARD 2x3 matrix the reference passes (it is inverted here exactly as cv::warpAffine
+ * does).  tab_dev: the 32x32x16 int16 bicubic weight table in device memory; fill a host copy with hdn_cubic_table_host. */
+int hdn_cubic_table_host(int16_t *tab /* [32*32*16] */);
+int hdn_warp_affine_cubic_u8(const uint8_t *src, uint8_t *dst, int H, int W, const double *M_host, const int16_t *tab_dev, hdn_stream_t stream);
+
+/* SiameseTracker.get_subwindow (hdn/tracker/base_tracker.py:61-136) on the device: the n x n window whose top-left pixel is
+ * (x0, y0) in frame coordinates (it may stick out of the frame: outside pixels take fill_host[3], the channel means cast to uint8)
+ * resized to S x S like cv2.resize (INTER_LINEAR; exact 2x decimation = INTER_AREA; n == S = copy) and converted to float32.
+ *   gray = 0: out [3,S,S] planar BGR (what the reference uploads as x_crop)
+ *   gray = 1: out [S,S] = get_search_info's normalised gray image, mean over channels of (v - mean_host[c]) / std_host[c] in float64
+ *             (Oneline_DLTv1/tools/get_img_info.py:42-70). */
+int hdn_crop_resize_u8(const uint8_t *frame, int H, int W, int x0, int y0, int n, const uint8_t *fill_host, int S, int gray,
+                       const double *mean_host, const double *std_host, float *out, hdn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

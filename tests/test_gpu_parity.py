@@ -344,3 +344,73 @@ def test_score_argmax_nan_scores_follow_numpy():
     assert np.array_equal(gath.cpu().numpy(), np.stack([loc[b].reshape(L, -1)[:, expect[b]] for b in range(B)]))
     ridx = c_oracle.score_argmax(cls, loc, win, w)[0]
     assert np.array_equal(ridx, expect)
+
+
+# ------------------------------------------------------------------ device-side frame pre-processing
+def _frame(rng, h, w):
+    from hdn_b200 import synthetic
+    img = synthetic.texture(int(rng.integers(1 << 30)), h, w)
+    return np.ascontiguousarray(np.clip(img.astype(np.int32) + rng.integers(-20, 21, img.shape), 0, 255).astype(np.uint8))
+
+
+def test_device_warp_perspective_is_bit_exact_with_opencv():
+    import cv2
+    from hdn_b200.preproc import FramePreproc
+    from oracle import cv_port
+    rng = np.random.default_rng(21)
+    pre = FramePreproc(DEV)
+    for t, (h, w) in enumerate([(360, 480), (720, 1280), (97, 131), (15, 40), (804, 1920)]):
+        img = _frame(rng, h, w)
+        src = np.array([[0, 0], [w, 0], [w, h], [0, h]], np.float32)
+        Hm = cv2.getPerspectiveTransform(src, src + rng.normal(0, 12 + 10 * t, (4, 2)).astype(np.float32))
+        M = np.linalg.inv(Hm)
+        pre.upload(img)
+        got = pre.warp_perspective(M).cpu().numpy()
+        assert np.array_equal(got, cv2.warpPerspective(img, M, (w, h), borderMode=cv2.BORDER_REPLICATE)), (h, w)
+        if h * w < 200000:
+            assert np.array_equal(got, cv_port.warp_perspective_u8(img, M))
+    img = _frame(rng, 120, 160)
+    pre.upload(img)
+    assert np.array_equal(pre.warp_perspective(np.eye(3)).cpu().numpy(), img)  # identity reproduces the frame
+
+
+def test_device_rotation_is_bit_exact_with_opencv():
+    import cv2
+    from hdn_b200.preproc import FramePreproc
+    rng = np.random.default_rng(22)
+    pre = FramePreproc(DEV)
+    for h, w in [(360, 480), (720, 1280), (97, 131)]:
+        img = _frame(rng, h, w)
+        for rot in (0.0, 0.013, -0.4, 1.3):
+            cx, cy = float(rng.uniform(0, w)), float(rng.uniform(0, h))
+            cc, ss = np.cos(rot), np.sin(rot)
+            M = np.array([[cc, -ss, cx - cx * cc + cy * ss], [ss, cc, cy - cy * cc - cx * ss]])
+            ref = cv2.warpAffine(img, M, (w, h), flags=2, borderMode=cv2.BORDER_REPLICATE)
+            got = pre.rotate(pre.upload(img), cx, cy, rot).cpu().numpy()
+            assert np.array_equal(got, ref), (h, w, rot)
+
+
+def test_device_crops_are_bit_exact_with_the_trackers_crop_window():
+    """300 random windows (inside, across every border, fully outside, exact 2x, no resize) + the gray normalisation."""
+    from hdn_b200 import compat
+    compat.activate()
+    from hdn.tracker.base_tracker import crop_window
+    from hdn_b200.preproc import FramePreproc
+    from oracle import cv_port
+    rng = np.random.default_rng(23)
+    img = _frame(rng, 360, 480)
+    avg = np.mean(img, axis=(0, 1))
+    pre = FramePreproc(DEV)
+    dev = pre.upload(img)
+    cases = [([240.3, 180.9], 127, 181.0), ([20.0, 340.5], 255, 363.0), ([200.0, 200.0], 127, 127.0), ([230.0, 170.0], 255, 510.0),
+             ([-300.0, -300.0], 127, 90.0), ([100.0, 100.0], 127, 254.0)]
+    cases += [([float(rng.uniform(-60, 540)), float(rng.uniform(-60, 420))], int(rng.choice([127, 255])), float(np.floor(rng.uniform(40, 700))))
+              for _ in range(294)]
+    for pos, msz, osz in cases:
+        ref, _ = crop_window(img, np.array(pos), msz, osz, avg)
+        got = pre.crop(dev, pos, msz, osz, avg).cpu().numpy()
+        assert np.array_equal(got, ref), (pos, msz, osz)
+    for pos, msz, osz in cases[:40]:
+        ref = cv_port.gray_normalise(crop_window(img, np.array(pos), 127, osz, avg)[0]).astype(np.float32)
+        got = pre.crop(dev, pos, 127, osz, avg, gray=True).cpu().numpy()
+        assert np.array_equal(got, ref), (pos, osz)
