@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--shared-template", type=int, default=-1, help="1 = one template for the whole batch (default at N>1: config 3)")
     ap.add_argument("--chunk", type=int, default=8, help="pairs per chunk of the fused chain (intermediates of a chunk stay in L2)")
     ap.add_argument("--chunks", type=int, default=12, help="pipeline depth of the round-1 boundary's end-to-end path (e2e_m1)")
+    ap.add_argument("--f32-crop", action="store_true", help="e2e: upload the search crop widened to fp32 (as the reference does) instead of the uint8 it is")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-e2e-m1", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -366,8 +367,8 @@ def main():
         if world > 1 and full:
             shard.gather_results(eng.inp["off"], eng.out["H"])
 
-    def timed(fn, steps):
-        """barrier + synchronize on both sides, CUDA events, max over ranks -> ms for `steps` calls of fn"""
+    def timed(fn, steps, after=None):
+        """barrier + synchronize on both sides, CUDA events, max over ranks -> ms for `steps` calls of fn (+ `after`: joins side streams)"""
         torch.cuda.synchronize()
         shard.barrier()
         torch.cuda.synchronize()
@@ -375,6 +376,8 @@ def main():
         e0.record()
         for _ in range(steps):
             fn()
+        if after is not None:
+            after()
         e1.record()
         torch.cuda.synchronize()
         shard.barrier()
@@ -404,7 +407,7 @@ def main():
     e2e = fused = e2e_m1 = None
     if full and not a.no_e2e:
         from hdn_b200 import head_engine as he
-        hhost = he.make_inputs(a.workload, B, seed=101 + rank, shared_template=shared, pin=True)
+        hhost = he.make_inputs(a.workload, B, seed=101 + rank, shared_template=shared, pin=True, u8_crop=not a.f32_crop)
         heng = he.HeadEngine(a.workload, B, dev, chunk=a.chunk)
         up = lambda v: [t.to(dev) for t in v] if isinstance(v, list) else v.to(dev)  # noqa: E731
         zf, zf_lp = up(hhost["zf"]), up(hhost["zf_lp"])
@@ -429,17 +432,21 @@ def main():
         h2d, d2h = heng.alloc_host_io(hhost)
 
         def e2e_step():
-            heng.run_host(hhost)
+            # a stream of batches: step i + 1 starts uploading while step i's last chunks compute (results alternate between two
+            # pinned result sets); the timed region ends with finish() + synchronize, i.e. with every result in host memory
+            heng.run_host(hhost, wait=False)
             if world > 1:
+                torch.cuda.current_stream().wait_stream(heng.s_cmp)
                 shard.gather_results(heng.inp["off"], heng.out["H"])
 
         for _ in range(W):
             e2e_step()
+        heng.finish()
         n0 = _lib.launch_count()
-        ms_e = timed(e2e_step, a.steps)
+        ms_e = timed(e2e_step, a.steps, after=heng.finish)
         e2e = {"value": world * B * a.steps / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": ms_e / a.steps, "chunk_pairs": heng.chunk, "gpu_launches": int(_lib.launch_count() - n0),
-               "h2d_gbs_per_gpu": h2d / (ms_e / a.steps * 1e-3) / 1e9,
+               "h2d_gbs_per_gpu": h2d / (ms_e / a.steps * 1e-3) / 1e9, "crop_dtype": "f32" if a.f32_crop else "u8",
                "scope": "per-frame neck features + crops in pinned host memory -> fused BAN heads, K3, K5/K4, K6 -> results in pinned host memory "
                         "(HeadEngine.run_host); template kernels cached on the device by set_template, as in the tracker",
                "check": float(heng.host_out["cls"][0, 0, 0, 0])}  # a value read back on the host

@@ -25,6 +25,7 @@ SIGNATURES = {
     "hdn_xcorr_is_staged": (_ci, [_ci, _ci, _ci, _ci, _ci, _ci, _i64]),
     "hdn_xcorr_generic_launches": (_i64, []),
     "hdn_logpolar_f32": (_ci, [_vp, _vp, _f, _vp, _ci, _ci, _ci, _ci, _ci, _vp]),
+    "hdn_logpolar_u8": (_ci, [_vp, _vp, _f, _vp, _ci, _ci, _ci, _ci, _ci, _vp]),
     "hdn_dlt4_f32": (_ci, [_vp, _vp, _vp, _ci, _vp]),
     "hdn_homo_warp_f32": (_ci, [_vp, _vp, ctypes.POINTER(_f), ctypes.POINTER(_f), _vp, _ci, _ci, _ci, _ci, _vp]),
     "hdn_dlt_warp_f32": (_ci, [_vp, _vp, _vp, ctypes.POINTER(_f), ctypes.POINTER(_f), _vp, _vp, _ci, _ci, _ci, _ci, _vp]),

@@ -56,9 +56,12 @@ __device__ __forceinline__ LpSample logpolar_sample_pos(int i, int j, float px, 
     return s;
 }
 
-template <int BC>
+__device__ __forceinline__ float lp_px(const float *p) { return __ldg(p); }
+__device__ __forceinline__ float lp_px(const unsigned char *p) { return (float)__ldg(p); }  // uint8 crops: exact in fp32
+
+template <int BC, typename T>
 __global__ void __launch_bounds__(256)
-    logpolar_kernel(const float *__restrict__ img, const float *__restrict__ polar, float rot_delta, float *__restrict__ out, int B, int Ch,
+    logpolar_kernel(const T *__restrict__ img, const float *__restrict__ polar, float rot_delta, float *__restrict__ out, int B, int Ch,
                     int H, int W, int S, float mag) {
     const int chunks = (B + BC - 1) / BC;
     const long long total = (long long)chunks * S * S;
@@ -72,13 +75,13 @@ __global__ void __launch_bounds__(256)
             const int b = b0 + bb;
             if (b >= B) break;
             if (polar) s = logpolar_sample_pos(i, j, __ldg(polar + 2 * b), __ldg(polar + 2 * b + 1), rot_delta, mag, H, W, S);
-            const float *ip = img + (long long)b * Ch * H * W + s.o00;
+            const T *ip = img + (long long)b * Ch * H * W + s.o00;
             float *op = out + ((long long)b * Ch * S + i) * S + j;
             for (int c = 0; c < Ch; ++c) {
-                float v = __fmul_rn(__ldg(ip), s.w00);
-                if (s.xin) v = __fadd_rn(v, __fmul_rn(__ldg(ip + 1), s.w10));
-                if (s.yin) v = __fadd_rn(v, __fmul_rn(__ldg(ip + W), s.w01));
-                if (s.xin && s.yin) v = __fadd_rn(v, __fmul_rn(__ldg(ip + W + 1), s.w11));
+                float v = __fmul_rn(lp_px(ip), s.w00);
+                if (s.xin) v = __fadd_rn(v, __fmul_rn(lp_px(ip + 1), s.w10));
+                if (s.yin) v = __fadd_rn(v, __fmul_rn(lp_px(ip + W), s.w01));
+                if (s.xin && s.yin) v = __fadd_rn(v, __fmul_rn(lp_px(ip + W + 1), s.w11));
                 *op = v;
                 ip += (long long)H * W;
                 op += (long long)S * S;
@@ -260,8 +263,8 @@ static void default_M(int W, int H, Mat9 &M, Mat9 &Mi) {
 
 using namespace hdn;
 
-extern "C" int hdn_logpolar_f32(const float *img, const float *polar, float rot_delta, float *out, int B, int Ch, int H, int W, int S,
-                                hdn_stream_t stream) {
+template <typename T>
+static int logpolar_launch(const T *img, const float *polar, float rot_delta, float *out, int B, int Ch, int H, int W, int S, hdn_stream_t stream) {
     if (!img || !out) return HDN_ERR_NULL;
     if (B < 1 || Ch < 1 || H < 2 || W < 2 || S < 2) return HDN_ERR_SHAPE;
     const float mag = (float)(log((double)S / 2.0) / (double)S);  // logpolar.py:63
@@ -273,10 +276,20 @@ extern "C" int hdn_logpolar_f32(const float *img, const float *polar, float rot_
         if (blocks > cap) blocks = cap;
         kern<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(img, polar, rot_delta, out, B, Ch, H, W, S, mag);
     };
-    if ((long long)B * S * S >= 4 * cap * 256) launch(logpolar_kernel<4>, 4);
-    else launch(logpolar_kernel<1>, 1);
+    if ((long long)B * S * S >= 4 * cap * 256) launch(logpolar_kernel<4, T>, 4);
+    else launch(logpolar_kernel<1, T>, 1);
     count_launch();
     return launch_status();
+}
+
+extern "C" int hdn_logpolar_f32(const float *img, const float *polar, float rot_delta, float *out, int B, int Ch, int H, int W, int S,
+                                hdn_stream_t stream) {
+    return logpolar_launch(img, polar, rot_delta, out, B, Ch, H, W, S, stream);
+}
+
+extern "C" int hdn_logpolar_u8(const uint8_t *img, const float *polar, float rot_delta, float *out, int B, int Ch, int H, int W, int S,
+                               hdn_stream_t stream) {
+    return logpolar_launch(img, polar, rot_delta, out, B, Ch, H, W, S, stream);
 }
 
 extern "C" int hdn_dlt4_f32(const float *src4, const float *off4, float *Hm, int B, hdn_stream_t stream) {

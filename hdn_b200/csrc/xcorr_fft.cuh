@@ -58,7 +58,12 @@ struct FCfg {
     // (offset 0: the window ends 2 floats into the next group -- never the last one, whose offset is 2 because B*C % 4 == 0.)
     static constexpr int XWIN = (G * XPL + (G % 4 && XPL % 2 ? 2 : 0) + 3) / 4 * 4, KWIN = (G * KPL + (G % 4 && KPL % 2 ? 2 : 0) + 3) / 4 * 4;
     static constexpr int RAW_FLOATS = XWIN + KWIN, OUT_FLOATS = G * OPL;
-    static constexpr int R_PAIRS = (HP - KH + 1) / 2;         // the x rows without a kernel row are packed in pairs (r, r + R_PAIRS):
+    // Rows that phase R transforms.  K2's padded plane repeats itself: padded row r is source row (r - PH) mod HX with the SAME
+    // replicate-padded columns, so only the HX distinct source rows are transformed and each spectrum is stored at every padded
+    // row it stands for (57 padded rows -> 29 transforms at 29x29: phase R drops from two half-empty passes to one full pass).
+    static constexpr bool DEDUP = CIRC && HX >= KH;
+    static constexpr int XSRC = DEDUP ? HX : HP;
+    static constexpr int R_PAIRS = (XSRC - KH + 1) / 2;       // the x rows without a kernel row are packed in pairs (r, r + R_PAIRS):
     static constexpr int R_UNITS_PLANE = KH + R_PAIRS;        // consecutive units read consecutive rows (odd pitch: no bank conflicts)
     static constexpr int R_UNITS = G * R_UNITS_PLANE, O_UNITS = (G / 2) * HO;
     static constexpr int pad32(int n) { return (n + 31) / 32 * 32; }
@@ -105,6 +110,12 @@ HDN_HD int fft_src_row(int r) {
     return sr;
 }
 
+// source row of transformed row j: j itself when the padded plane's repeated rows are de-duplicated (or there is no padding)
+template <class Cfg>
+HDN_HD int fft_x_row(int j) {
+    return Cfg::DEDUP ? j : fft_src_row<Cfg>(j);
+}
+
 // ---- loads: the 64 complex inputs a[n] of the unit's transform, folded on the fly into the half's 32 values ---------------------
 //      s[n] = a[n] + sgn * a[n+32]      sgn = +1 (h = 0) / -1 (h = 1), one FFMA per value; 64 live registers instead of 128
 template <class Cfg>
@@ -125,7 +136,7 @@ HDN_HD bool fftc_load(int ph, const FftBufs &b, int unit, int h, float (&re)[32]
     if (ph == FFT_PH_R) {
         if (unit >= Cfg::R_UNITS) return false;
         const int p = unit / Cfg::R_UNITS_PLANE, j = unit - p * Cfg::R_UNITS_PLANE;
-        fftc_fold_row<Cfg>(b.rawx + p * Cfg::XPL + fft_src_row<Cfg>(j) * Cfg::WX, true, sgn, re);
+        fftc_fold_row<Cfg>(b.rawx + p * Cfg::XPL + fft_x_row<Cfg>(j) * Cfg::WX, true, sgn, re);
         if (j < Cfg::KH) {  // (x_j, k_j)
             const float *krow = b.rawk + p * Cfg::KPL + j * Cfg::KW;
 #pragma unroll
@@ -135,8 +146,8 @@ HDN_HD bool fftc_load(int ph, const FftBufs &b, int unit, int h, float (&re)[32]
             }
         } else {  // (x_j, x_{j + R_PAIRS})
             const int r2 = j + Cfg::R_PAIRS;
-            const bool has2 = r2 < Cfg::HP;
-            fftc_fold_row<Cfg>(b.rawx + p * Cfg::XPL + fft_src_row<Cfg>(has2 ? r2 : j) * Cfg::WX, has2, sgn, im);
+            const bool has2 = r2 < Cfg::XSRC;
+            fftc_fold_row<Cfg>(b.rawx + p * Cfg::XPL + fft_x_row<Cfg>(has2 ? r2 : j) * Cfg::WX, has2, sgn, im);
         }
         return true;
     }
@@ -173,18 +184,32 @@ HDN_HD void fftc_store_R(const FftBufs &b, int unit, const float (&re)[32], cons
     using namespace fft;
     const int p = unit / Cfg::R_UNITS_PLANE, j = unit - p * Cfg::R_UNITS_PLANE;
     const bool ktype = j < Cfg::KH;
-    float2 *d1 = b.XR + p * Cfg::XR_PLANE + j * Cfg::PITCH;
-    float2 *d2 = ktype ? b.KR + p * Cfg::KR_PLANE + j * Cfg::PITCH : d1 + Cfg::R_PAIRS * Cfg::PITCH;
-    const bool has2 = ktype || j + Cfg::R_PAIRS < Cfg::HP;
+    float2 *xr = b.XR + p * Cfg::XR_PLANE;
+    // first padded row of x row j (DEDUP: source row j stands for padded rows j + PH - HX, j + PH, j + PH + HX inside [0, HP))
+    const int j2 = j + Cfg::R_PAIRS;
+    const int r1 = Cfg::DEDUP ? (j + Cfg::PH >= Cfg::HX ? j + Cfg::PH - Cfg::HX : j + Cfg::PH) : j;
+    const int r2 = Cfg::DEDUP ? (j2 + Cfg::PH >= Cfg::HX ? j2 + Cfg::PH - Cfg::HX : j2 + Cfg::PH) : j2;
+    float2 *d1 = xr + r1 * Cfg::PITCH;
+    float2 *d2 = ktype ? b.KR + p * Cfg::KR_PLANE + j * Cfg::PITCH : xr + r2 * Cfg::PITCH;
+    const bool has2 = ktype || j2 < Cfg::XSRC;
+    // the same spectrum again HX rows further down (rows past HP are never read by a valid output)
+    const bool rep1 = Cfg::DEDUP && r1 + Cfg::HX < Cfg::HP, rep2 = Cfg::DEDUP && !ktype && has2 && r2 + Cfg::HX < Cfg::HP;
+    constexpr int REP = Cfg::HX * Cfg::PITCH;
     if (H == 0) {
-        d1[0] = float2{2.f * re[HPOS(0)], 2.f * re[HPOS(32)]};
-        if (has2) d2[0] = float2{2.f * im[HPOS(0)], 2.f * im[HPOS(32)]};
+        const float2 v1 = float2{2.f * re[HPOS(0)], 2.f * re[HPOS(32)]}, v2 = float2{2.f * im[HPOS(0)], 2.f * im[HPOS(32)]};
+        d1[0] = v1;
+        if (rep1) d1[REP] = v1;
+        if (has2) d2[0] = v2;
+        if (rep2) d2[REP] = v2;
     }
 #pragma unroll
     for (int f = 2 - H; f < 32; f += 2) {  // 2A(f) = Z(f) + conj Z(-f),  2B(f) = (Z(f) - conj Z(-f)) / i
         const float ar = re[HPOS(f)], ai = im[HPOS(f)], br = re[HPOS(64 - f)], bi = im[HPOS(64 - f)];
-        d1[f] = float2{ar + br, ai - bi};
-        if (has2) d2[f] = float2{ai + bi, br - ar};
+        const float2 v1 = float2{ar + br, ai - bi}, v2 = float2{ai + bi, br - ar};
+        d1[f] = v1;
+        if (rep1) d1[f + REP] = v1;
+        if (has2) d2[f] = v2;
+        if (rep2) d2[f + REP] = v2;
     }
 }
 

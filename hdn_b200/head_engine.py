@@ -105,7 +105,7 @@ class HeadWeights:
         return self
 
 
-def make_inputs(workload, B, seed=1, shared_template=False, pin=False):
+def make_inputs(workload, B, seed=1, shared_template=False, pin=False, u8_crop=False):
     """Synthetic NECK features (BatchNorm outputs: zero-mean, unit scale), crops U[0,255), offsets U(-8,8) -- SURVEY 8(d) config 2/3."""
     n = NECK[workload]
     g = torch.Generator(device="cpu").manual_seed(seed)
@@ -114,7 +114,9 @@ def make_inputs(workload, B, seed=1, shared_template=False, pin=False):
     d = {
         "xf": [rn(B, C, n["xf"], n["xf"]) for _ in range(LEVELS)], "xf_lp": [rn(B, C, n["xf_lp"], n["xf_lp"]) for _ in range(LEVELS)],
         "zf": [rn(Bk, C, n["zf"], n["zf"]) for _ in range(LEVELS)], "zf_lp": [rn(Bk, C, n["zf_lp"], n["zf_lp"]) for _ in range(LEVELS)],
-        "img": torch.rand((B, 3, n["img"], n["img"]), generator=g) * 255.0,
+        # the search crop: what get_subwindow hands over -- integer pixel values, as fp32 (the reference's upload) or as the uint8 they are
+        "img": torch.randint(0, 256, (B, 3, n["img"], n["img"]), generator=g, dtype=torch.uint8) if u8_crop
+        else torch.randint(0, 256, (B, 3, n["img"], n["img"]), generator=g, dtype=torch.uint8).float(),
         "gray": torch.randn((B, 1, 127, 127), generator=g),
         "off": torch.rand((B, 8), generator=g) * 16.0 - 8.0,
         "src": torch.tensor(H4P).repeat(B, 1),
@@ -215,7 +217,8 @@ class HeadEngine:
         head(self.w_lp, inp["xf_lp"], self.S_lp, self.F_lp, self.P_lp, self.k_lp, True, self.s_lp_hw, self.k_lp_hw, self.N_lp, 4,
              (o["cls_lp"], o["loc_lp"]), (o["idx_lp"], o["pscore_lp"], o["score_lp"], o["sim_lp"]), None, 0.0)
         n = self.n
-        _lib.check(L.hdn_logpolar_f32(p(inp["img"][s0:s0 + b]), None, 0.0, p(o["x_lp"][lo:hi]), b, 3, n["img"], n["img"], n["S"], st), "K3")
+        k3 = L.hdn_logpolar_u8 if inp["img"].dtype == torch.uint8 else L.hdn_logpolar_f32
+        _lib.check(k3(p(inp["img"][s0:s0 + b]), None, 0.0, p(o["x_lp"][lo:hi]), b, 3, n["img"], n["img"], n["S"], st), "K3")
         _lib.check(L.hdn_dlt_warp_f32(p(inp["src"][s0:s0 + b]), p(inp["off"][s0:s0 + b]), p(inp["gray"][s0:s0 + b]), None, None, p(o["H"][lo:hi]),
                                       p(o["warp"][lo:hi]), b, 1, 127, 127, st), "K5+K4")
 
@@ -236,22 +239,33 @@ class HeadEngine:
         backbone pass, ShareFeature) run there in the real pipeline."""
         c = self.chunk
         self.slots = slots
-        self.stage = [{k: ([torch.empty((c,) + tuple(t.shape[1:]), device=self.device) for t in host_inputs[k]] if isinstance(host_inputs[k], list)
-                           else torch.empty((c,) + tuple(host_inputs[k].shape[1:]), device=self.device)) for k in FRAME_KEYS} for _ in range(slots)]
-        self.host_out = {k: torch.empty_like(self.out[k], device="cpu").pin_memory() for k in self.HOST_OUT}
+        self.stage = [{k: ([torch.empty((c,) + tuple(t.shape[1:]), device=self.device, dtype=t.dtype) for t in host_inputs[k]]
+                           if isinstance(host_inputs[k], list)
+                           else torch.empty((c,) + tuple(host_inputs[k].shape[1:]), device=self.device, dtype=host_inputs[k].dtype)) for k in FRAME_KEYS}
+                      for _ in range(slots)]
+        # two result sets: the host reads step i's results while step i + 1 is in flight
+        self.host_out_sets = [{k: torch.empty_like(self.out[k], device="cpu").pin_memory() for k in self.HOST_OUT} for _ in range(2)]
+        self.host_out = self.host_out_sets[0]
         self.s_h2d, self.s_cmp, self.s_d2h = (torch.cuda.Stream(device=self.device) for _ in range(3))
         self.ev_free = [None] * slots
+        self.ev_read = None   # results of the previous step have left the device (its result buffers may be overwritten)
+        self.steps_in_flight = 0
         nb = lambda t: t.numel() * t.element_size()  # noqa: E731
         h2d = sum(sum(nb(t) for t in host_inputs[k]) if isinstance(host_inputs[k], list) else nb(host_inputs[k]) for k in FRAME_KEYS)
         return h2d, sum(nb(t) for t in self.host_out.values())
 
-    def run_host(self, host_inputs):
+    def run_host(self, host_inputs, wait=True):
         """Per-frame inputs in pinned host memory -> results in pinned host memory.  Chunk i+1 uploads while chunk i computes;
-        the (small) results of the whole batch are downloaded once at the end."""
+        the (small) results of the whole batch are downloaded once at the end.
+        wait=False: return as soon as the step is queued (the caller's stream is not joined), so the uploads of the next step
+        overlap this step's last chunks -- a stream of batches keeps the link busy; call finish() before reading the LAST
+        returned result set.  Result sets alternate between two pinned buffers."""
         B, c = self.B, self.chunk
         cur = torch.cuda.current_stream(self.device)
-        for s in (self.s_h2d, self.s_cmp, self.s_d2h):
-            s.wait_stream(cur)
+        if self.steps_in_flight == 0:
+            for s in (self.s_h2d, self.s_cmp, self.s_d2h):
+                s.wait_stream(cur)
+        host_out = self.host_out_sets[self.steps_in_flight % 2] if not wait else self.host_out_sets[0]
         for i, lo in enumerate(range(0, B, c)):
             hi = min(B, lo + c)
             slot = i % self.slots
@@ -268,6 +282,8 @@ class HeadEngine:
                 ev_up.record(self.s_h2d)
             with torch.cuda.stream(self.s_cmp):
                 self.s_cmp.wait_event(ev_up)
+                if i == 0 and self.ev_read is not None:
+                    self.s_cmp.wait_event(self.ev_read)  # the previous step's results have been read out of self.out
                 self._launch_chunk(stage, lo, hi, src_lo=0)
                 ev = torch.cuda.Event()
                 ev.record(self.s_cmp)
@@ -275,10 +291,22 @@ class HeadEngine:
         with torch.cuda.stream(self.s_d2h):
             self.s_d2h.wait_stream(self.s_cmp)
             for k in self.HOST_OUT:
-                self.host_out[k].copy_(self.out[k], non_blocking=True)
+                host_out[k].copy_(self.out[k], non_blocking=True)
+            self.ev_read = torch.cuda.Event()
+            self.ev_read.record(self.s_d2h)
+        self.host_out = host_out
+        if wait:
+            self.finish()
+        else:
+            self.steps_in_flight += 1
+        return host_out
+
+    def finish(self):
+        """Join the pipeline streams into the caller's stream (results are in host memory once that stream is synchronised)."""
+        cur = torch.cuda.current_stream(self.device)
         for s in (self.s_h2d, self.s_cmp, self.s_d2h):
             cur.wait_stream(s)
-        return self.host_out
+        self.steps_in_flight = 0
 
 
 def ctypes_floats(values):
@@ -292,7 +320,7 @@ def algorithmic_bytes_per_pair(workload):
     n = NECK[workload]
     N = n["xf"] - 2 - (n["zf"] - 2) + 1
     N_lp = n["xf_lp"] - 2
-    inp = 4 * (LEVELS * C * (n["xf"] ** 2 + n["xf_lp"] ** 2) + 3 * n["img"] ** 2 + 127 * 127 + 16)
+    inp = 4 * (LEVELS * C * (n["xf"] ** 2 + n["xf_lp"] ** 2) + 3 * n["img"] ** 2 + 127 * 127 + 16)  # (uint8 crop: 3 * img^2 bytes less 3/4)
     out = 4 * (4 * N * N + 6 * N_lp * N_lp + 3 * n["S"] ** 2 + 127 * 127 + 9) + 2 * 28 + 24
     return {"in": inp, "out": out, "total": inp + out}
 

@@ -89,6 +89,10 @@ int64_t hdn_xcorr_generic_launches(void);
  *   rot_delta = delta[1] of the reference call. */
 int hdn_logpolar_f32(const float *img, const float *polar, float rot_delta, float *out, int B, int Ch, int H, int W, int S,
                      hdn_stream_t stream);
+/* The same for a uint8 crop [B,Ch,H,W] (the crop get_subwindow resizes is 8-bit; the reference widens it to fp32 on the host
+ * before the upload, base_tracker.py:127-131): identical results, a quarter of the bytes across the bus. */
+int hdn_logpolar_u8(const uint8_t *img, const float *polar, float rot_delta, float *out, int B, int Ch, int H, int W, int S,
+                    hdn_stream_t stream);
 
 /* K5.  Replaces Oneline_DLTv1/utils.py:7-67 DLT_solve for 8-vectors (one quad per item).
  *   src4, off4 [B,8] (x0,y0,...,x3,y3) -> Hm [B,9] row-major 3x3 with Hm[8] = 1. */

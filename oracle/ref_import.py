@@ -61,6 +61,9 @@ def install():
     torch.nn.Module.cuda = lambda self, *a, **k: self
     torch.cuda.is_available = lambda: True
     torch.cuda.current_device = lambda: 0
+    for storage in (getattr(torch, "UntypedStorage", None), getattr(torch.storage, "TypedStorage", None)):
+        if storage is not None:  # load_pretrain maps checkpoints with `storage.cuda(device)` (hdn/utils/model_load.py:50-53)
+            storage.cuda = lambda self, *a, **k: self
 
     # 4. no downloads
     import torch.utils.model_zoo as model_zoo

@@ -145,8 +145,8 @@ def test_fused_head_tail_equals_reference_ops(B, N, L):
     assert torch.equal(buf[:20 * B + 4 * B * L], buf2[:20 * B + 4 * B * L])  # (the buffer's tail is alignment padding)
 
 
-@pytest.mark.parametrize("workload,B,chunk,shared", [("127/255", 5, 2, False), ("127/255", 3, 4, True), ("256/512", 2, 1, False)])
-def test_head_engine_equals_cpu_port(workload, B, chunk, shared):
+@pytest.mark.parametrize("workload,B,chunk,shared,u8", [("127/255", 5, 2, False, False), ("127/255", 3, 4, True, True), ("256/512", 2, 1, False, True)])
+def test_head_engine_equals_cpu_port(workload, B, chunk, shared, u8):
     """The fused chain from neck features (HeadEngine: conv_search -> correlation -> 1x1 tail -> level sum + K6, K3, K5 + K4),
     device-resident and through the pinned-host pipeline, against the CPU port of the reference's own torch calls
     (oracle/torch_port.fused_chain).  Maps within 1e-3; arg-max indices bit-exact."""
@@ -154,7 +154,7 @@ def test_head_engine_equals_cpu_port(workload, B, chunk, shared):
     from hdn_b200.engine import WIN_INFL
     from oracle import c_oracle, torch_port as tp
     dev = torch.device("cuda")
-    host = he.make_inputs(workload, B, seed=5, shared_template=shared)
+    host = he.make_inputs(workload, B, seed=5, shared_template=shared, u8_crop=u8)
     eng = he.HeadEngine(workload, B, dev, chunk=chunk)
     up = lambda v: [t.to(dev) for t in v] if isinstance(v, list) else v.to(dev)  # noqa: E731
     eng.set_template(up(host["zf"]), up(host["zf_lp"]))
@@ -163,7 +163,7 @@ def test_head_engine_equals_cpu_port(workload, B, chunk, shared):
     w_sim, w_lp = ({k: ([t.cpu() for t in v] if isinstance(v, list) and isinstance(v[0], torch.Tensor) else v) for k, v in w.raw.items()}
                    for w in (eng.w_sim, eng.w_lp))
     M, Mi = c_oracle.default_M(127, 127)
-    feats = dict(host, S=he.NECK[workload]["S"], M=torch.from_numpy(M), Minv=torch.from_numpy(Mi))
+    feats = dict(host, S=he.NECK[workload]["S"], M=torch.from_numpy(M), Minv=torch.from_numpy(Mi), img=host["img"].float())
     win = np.outer(np.hanning(eng.N), np.hanning(eng.N)).flatten()
     ref = tp.fused_chain(feats, w_sim, w_lp, win, WIN_INFL)
     for k in ("cls", "loc", "cls_lp", "loc_lp", "x_lp"):
@@ -174,10 +174,18 @@ def test_head_engine_equals_cpu_port(workload, B, chunk, shared):
     assert np.allclose(out["center"].numpy(), ref["center"], rtol=1e-3, atol=1e-4) and np.allclose(out["sim_lp"].numpy(), ref["sim_lp"], rtol=1e-3, atol=1e-4)
     assert np.allclose(out["H"].numpy(), ref["H"].numpy(), rtol=1e-3, atol=1e-5)
     # end to end through pinned host buffers: same results as the device-resident run
-    pinned = he.make_inputs(workload, B, seed=5, shared_template=shared, pin=True)
+    pinned = he.make_inputs(workload, B, seed=5, shared_template=shared, pin=True, u8_crop=u8)
     h2d, d2h = eng.alloc_host_io(pinned)
-    assert h2d == sum(sum(t.numel() * 4 for t in pinned[k]) if isinstance(pinned[k], list) else pinned[k].numel() * 4 for k in he.FRAME_KEYS)
+    nb = lambda t: t.numel() * t.element_size()  # noqa: E731
+    assert h2d == sum(sum(nb(t) for t in pinned[k]) if isinstance(pinned[k], list) else nb(pinned[k]) for k in he.FRAME_KEYS)
     res = eng.run_host(pinned)
     torch.cuda.synchronize()
     for k in he.HeadEngine.HOST_OUT:
         assert torch.equal(res[k], out[k]), k
+    # a stream of batches (wait=False): steps overlap, result sets alternate, every set equals the synchronous result
+    sets = [eng.run_host(pinned, wait=False) for _ in range(3)]
+    eng.finish()
+    torch.cuda.synchronize()
+    assert sets[0] is sets[2] and sets[0] is not sets[1]
+    for k in he.HeadEngine.HOST_OUT:
+        assert torch.equal(sets[1][k], out[k]) and torch.equal(sets[2][k], out[k]), k

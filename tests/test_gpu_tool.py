@@ -1,0 +1,56 @@
+"""GPU: the twin of tools/test.py's loop (hdn_b200/stream_bench.py) on a POT-format benchmark, against the result files the
+REFERENCE'S OWN tools/test.py wrote for the same benchmark and weights (oracle/gen_golden_tool.py ran the tool unmodified on
+the CPU; tests/golden/pot_results/).  Per-frame polygons within 1e-3 of the frame diagonal, and the benchmark's own score
+(HomoBenchmark alignment-error precision, toolkit/evaluation/homo_benchmark.py) equal within 1e-3."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def read_rows(path):
+    return np.asarray([[float(v) for v in line.split()] for line in open(path) if line.strip()])
+
+
+def test_stream_runner_reproduces_the_reference_tools_result_files(tmp_path):
+    from hdn_b200 import pot_fixture, stream_bench
+    gold = os.path.join(GOLDEN, "pot_results")
+    fx = json.load(open(os.path.join(gold, "fixture.json")))
+    root = str(tmp_path / "testing_dataset" / "POT")
+    pot_fixture.write_dataset(root, fx["n_sequences"], fx["n_frames"], tuple(fx["size"]), fx["seed0"], ext=fx["ext"])
+    tracker, model = stream_bench.build(graphs=False)
+    from toolkit.datasets import DatasetFactory
+    from toolkit.evaluation import HomoBenchmark
+    dataset = DatasetFactory.create_dataset(name="POT210", dataset_root=root, load_img=False)
+    assert [v.name for v in dataset] == ["V01_1", "V01_2"]
+    results = str(tmp_path / "results")
+    busy, frames = stream_bench.run_dataset(dataset, tracker, model, list(range(len(dataset))), results, "hdn_b200")
+    assert frames == fx["n_sequences"] * (fx["n_frames"] - 1) and busy > 0
+    diag = float(np.hypot(*fx["size"]))
+    for v in dataset:
+        ours = read_rows(os.path.join(results, "POT210", "hdn_b200", v.name + ".txt"))
+        ref = read_rows(os.path.join(gold, v.name + ".txt"))
+        assert ours.shape == ref.shape == (fx["n_frames"], 8)
+        assert np.array_equal(ours[0], ref[0])  # frame 0 is the ground truth in both files
+        assert np.abs(ours - ref).max() <= 1e-3 * diag, (v.name, np.abs(ours - ref).max())
+    # the benchmark's score of both result sets
+    os.makedirs(os.path.join(results, "POT210", "reference"), exist_ok=True)
+    for v in dataset:
+        with open(os.path.join(gold, v.name + ".txt")) as src, open(os.path.join(results, "POT210", "reference", v.name + ".txt"), "w") as dst:
+            dst.write(src.read())
+    dataset.set_tracker(os.path.join(results, "POT210"), ["hdn_b200", "reference"])
+    prec = HomoBenchmark(dataset).eval_4pts_precision()
+    for v in dataset:
+        assert np.abs(np.asarray(prec["hdn_b200"][v.name]) - np.asarray(prec["reference"][v.name])).max() <= 1e-3
+    # lock-step batching of both videos gives the same files within fp32 noise
+    results2 = str(tmp_path / "results_lockstep")
+    stream_bench.run_dataset(dataset, tracker, model, [0, 1], results2, "hdn_b200", lockstep=2)
+    for v in dataset:
+        a = read_rows(os.path.join(results, "POT210", "hdn_b200", v.name + ".txt"))
+        b = read_rows(os.path.join(results2, "POT210", "hdn_b200", v.name + ".txt"))
+        assert np.abs(a - b).max() <= 1e-3 * diag
