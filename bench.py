@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-e2e-m1", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-m2", action="store_true", help="skip the full-forward (M2) block")
+    ap.add_argument("--m2-batch", type=int, default=None, help="pairs per M2 step (default: --batch)")
     ap.add_argument("--no-traffic", action="store_true", help="skip the ncu dram-traffic measurement of the dominant kernel")
     ap.add_argument("--cpu-seconds", type=float, default=25.0, help="time budget of the cpu_baseline leg")
     ap.add_argument("--xcorr-algo", default="auto", choices=["auto", "direct", "fft"], help="auto = FFT correlation where it beats the direct sum")
@@ -210,18 +212,85 @@ def workload_name(workload, scope="m1"):
     return "%s crops: 6xK1 + 6xK2 + K3 + K5/K4 + 2xK6 per pair" % workload
 
 
+def cpu_m2_rate(workload, repeats=3):
+    """Model-level CPU forward of ONE pair: the mirrored ModelBuilder on CPU tensors with its operators backed
+    by oracle/torch_port.py (oracle/cpu_shim.py) -- track_new + track_new_lp + track_proj of a 256/512 (or 127/255) crop."""
+    import torch
+    from oracle import cpu_shim
+    from hdn_b200 import synthetic
+    ex, inst = (256, 512) if workload == "256/512" else (127, 255)
+    model, cfg = cpu_shim.build_cpu_model(inst, ex)
+    z = torch.from_numpy(synthetic.crop_tensor(1, (1, 6, ex, ex)))
+    x = torch.from_numpy(synthetic.crop_tensor(2, (1, 3, inst, inst)))
+    pair = torch.randn(1, 2, 127, 127)
+    h4p = torch.tensor([[0.0, 0.0, 0.0, 127.0, 127.0, 127.0, 127.0, 0.0]])
+    with torch.no_grad():
+        model.template(z)
+
+        def frame():
+            model._stage1_packed(x, cfg.TRACK.WINDOW_INFLUENCE)
+            model._stage2_packed(x)
+            model._stage3_packed(pair, h4p)
+        rate, ms, spread = _median_rate(frame, 1, repeats, 1)
+    return {"value": rate, "unit": UNIT, "ms_per_step": ms, "pairs_per_step": 1, "steps": repeats, "spread": spread,
+            "scope": "full forward of one %s pair on CPU (mirrored ModelBuilder, operators = the reference's torch calls)" % workload}
+
+
+def run_reference_stream(a):
+    """CPU arm of config 4: hdnTrackerHomo.init / track_new of the mirrored tracker on CPU tensors (oracle/cpu_shim.py: the
+    reference's own torch / NumPy / OpenCV calls) over a bounded sample of one synthetic sequence of the same frame size."""
+    import numpy as np
+    import torch
+    from oracle import cpu_shim
+    from hdn_b200 import synthetic
+    cores = host_threads()
+    torch.set_num_threads(cores)
+    H, W = (int(v) for v in a.frame_size.lower().split("x"))
+    n = max(3, min(a.steps, 12))
+    model, cfg = cpu_shim.build_cpu_model()
+    from hdn.tracker.tracker_builder import build_tracker
+    from hdn.utils.bbox import get_min_max_bbox, get_w_h_from_poly
+    tracker = build_tracker(model)
+    frames, polys = synthetic.sequence(100, n + 2, size=(H, W), obj=(H // 3, W // 3))
+    gt = polys[0]
+    cx, cy, w, h = get_min_max_bbox(np.array(gt))
+    with torch.no_grad():
+        tracker.init(frames[0], [cx - (w - 1) / 2, cy - (h - 1) / 2, w, h], get_w_h_from_poly(np.array(gt)), gt, np.array([gt[:2]]))
+        tracker.track_new(1, frames[1], None, None, None)  # warm-up frame
+        ts = []
+        for i in range(2, n + 2):
+            t = time.perf_counter()
+            tracker.track_new(i, frames[i], None, None, None)
+            ts.append(time.perf_counter() - t)
+    med = statistics.median(ts)
+    sample = "%d frames of one %dx%d synthetic sequence, mirrored tracker on CPU (oracle/cpu_shim.py), torch %s, %d threads, median frame" % (
+        n, W, H, torch.__version__, cores)
+    line = {"impl": "reference", "metric": "frames/sec (hdnTrackerHomo.init/track_new, POT-shaped stream)", "value": 1.0 / med, "unit": UNIT,
+            "n_gpus": a.gpus, "steps": n, "warmup": 1, "ms_per_step": 1e3 * med, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name("stream"), "frame_size": [H, W], "sample_frames": n, "parallelism": "host cores of rank 0 (CPU arm)"},
+            "cpu_baseline": {"value": 1.0 / med, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "spread": (max(ts) - min(ts)) / med},
+            "e2e": {"value": 1.0 / med, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
 def run_reference(a, rank):
     if rank != 0:
         return
     if a.workload == "stream":
-        print(json.dumps({"impl": "reference", "unavailable": "the stream workload needs the reference tracker itself, which cannot travel to the GPU box; "
-                          "the CPU arm is defined for the chain workloads"}), flush=True)
-        return
+        return run_reference_stream(a)
     B = a.batch or (256 if a.workload == "win15" else 64)
     # K steps, each a bounded sample; the whole run within a few minutes
     r = cpu_rates(a.workload, budget_s=150.0, steps=max(a.steps, 1), warmup=max(a.warmup, 1), pairs=B, single_thread=False)
     m1, fused = r["m1"], r.get("fused")
     e2e_leg = fused or m1
+    m2 = None
+    if fused and not a.no_m2:
+        try:
+            m2 = cpu_m2_rate(a.workload)
+        except Exception as e:
+            m2 = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
     sample = "%d step(s) x %d pair(s) of the M1 chain%s, torch %s CPU fp32 (oracle/torch_port.py), %d threads, median step" % (
         m1["steps"], m1["pairs_per_step"], (" / x %d pair(s) of the fused chain from neck features" % fused["pairs_per_step"]) if fused else "",
         r["torch"], r["cores"])
@@ -235,7 +304,7 @@ def run_reference(a, rank):
                        "same_config": bool(m1["same_config"] and e2e_leg["same_config"]), "channels": 256, "template": "per pair",
                        "parallelism": "host cores of rank 0 (CPU arm)"},
             "cpu_baseline": {"value": m1["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample, "spread": m1["spread"],
-                             "fused": fused},
+                             "fused": fused, "m2": m2},
             "e2e": {"value": e2e_leg["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "ms_per_step": e2e_leg["ms_per_step"],
                     "spread": e2e_leg["spread"]},
             "gpu_launches": 0}
@@ -285,6 +354,60 @@ def measure_traffic(a):
     if seen < 2:
         return None, "ncu gave no dram metrics (rc %d): %s" % (res.returncode, (res.stderr or res.stdout).strip().splitlines()[-1][:160] if (res.stderr or res.stdout).strip() else "")
     return total, "ncu dram__bytes_read.sum + dram__bytes_write.sum, one K1 launch, measured in this run"
+
+
+# ------------------------------------------------------------------------------------------ M2: the full forward
+M2_GFLOP_PER_PAIR = {"256/512": 510.0, "127/255": 124.0}  # SURVEY 8(d) [probed with FlopCounterMode on the reference]: backbones + necks + heads + homography net
+
+
+def m2_block(workload, B, steps=3, warmup=2):
+    """SURVEY 8(d) "M2": the three network stages of a frame (ModelBuilder.track_new / track_new_lp / track_proj with their K6
+    epilogues) for a batch of B crops through the mirrored model -- ResNet-50 x2, necks, fused BAN heads, ResNet-34 homography net,
+    K3, K5/K4 -- with random-init weights of the architecture.  -> frames/s and dense TFLOP/s (fp32 accuracy: 3xTF32 on tcgen05 for
+    the stride-1 layers, cuDNN fp32 for the stem / strided layers) against the measured bf16 peak."""
+    import torch
+    from hdn_b200 import compat, synthetic
+    compat.activate()
+    from hdn.core.config import cfg
+    cfg.merge_from_file(os.path.join(ROOT, "experiments", "tracker_homo_config", "proj_e2e_GOT_unconstrained_v2.yaml"))
+    ex, inst = (256, 512) if workload == "256/512" else (127, 255)
+    cfg.TRACK.INSTANCE_SIZE, cfg.TRACK.EXEMPLAR_SIZE = inst, ex
+    cfg.CUDA = True
+    from hdn.models.model_builder_e2e_unconstrained_v2 import ModelBuilder
+    model = synthetic.fill_weights(ModelBuilder()).cuda().eval()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    z = torch.rand((B, 6, ex, ex), device="cuda", generator=g) * 255.0
+    x = torch.rand((B, 3, inst, inst), device="cuda", generator=g) * 255.0
+    pair = torch.randn((B, 2, 127, 127), device="cuda", generator=g)
+    h4p = torch.tensor([[0.0, 0.0, 0.0, 127.0, 127.0, 127.0, 127.0, 0.0]], device="cuda").repeat(B, 1)
+    with torch.no_grad():
+        model.template(z)  # once per sequence, outside the per-frame step
+
+        def frame():
+            a_ = model._stage1_packed(x, cfg.TRACK.WINDOW_INFLUENCE)
+            b_ = model._stage2_packed(x)
+            c_ = model._stage3_packed(pair, h4p)
+            return a_, b_, c_
+
+        for _ in range(warmup):
+            frame()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = frame()
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    _, _, bf16 = peaks()
+    tf = M2_GFLOP_PER_PAIR[workload] * B / ms  # GFLOP per ms = TFLOP/s
+    del model
+    torch.cuda.empty_cache()
+    return {"value": B / ms * 1e3, "unit": UNIT, "ms_per_step": ms, "pairs_per_step": B, "steps": steps, "gflop_per_pair": M2_GFLOP_PER_PAIR[workload],
+            "tflops": tf, "bf16_peak_tflops_sustained": bf16, "frac_of_bf16_peak": tf / bf16 if bf16 else None,
+            "precision": "fp32-accurate: 3xTF32 on tcgen05 (3 tensor-core MACs per MAC) for the stride-1 backbone / neck / head layers, cuDNN fp32 "
+                         "(TF32 off) for the stem, layer1 and the strided layers",
+            "check": float(out[0].float().sum().item() * 0 + out[2][0, 8].item())}
 
 
 # ------------------------------------------------------------------------------------------ GPU arm: chain workloads
@@ -494,6 +617,12 @@ def main():
                 "kernel_ms": kern_avg,
                 "kernel_frac": {n: (ab[key] * B / (kern_avg[n] * 1e-3) / 1e9 / peak) for n, key in (("k1", "k1"), ("k2", "k2"), ("k3", "k3")) if n in kern_avg and key in ab}}
 
+    m2 = None
+    if full and world == 1 and not a.no_m2:
+        try:
+            m2 = m2_block(a.workload, a.m2_batch or B)
+        except Exception as e:  # the M2 block is informative; the line stands without it
+            m2 = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
     cpu = None
     if not a.no_cpu and world == 1:
         r = cpu_rates(a.workload, a.cpu_seconds, pairs=B)
@@ -503,6 +632,11 @@ def main():
                    "fused (e2e scope: BAN heads from neck features + K3 + K5/K4 + K6)" if "fused" in r else "M1", lead["steps"], lead["pairs_per_step"],
                    r["torch"], r["cores"]),
                "spread": lead["spread"], "same_config": lead["same_config"], "m1_chain": r["m1"], "single_thread": r.get("single_thread")}
+        if full and not a.no_m2:
+            try:
+                cpu["m2"] = cpu_m2_rate(a.workload, repeats=2)
+            except Exception as e:
+                cpu["m2"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": W, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -513,7 +647,7 @@ def main():
                        "template": "shared, NCCL broadcast from rank 0" if shared else "per pair",
                        "parallelism": "pairs sharded over %d GPU(s), no data-path collective" % world,
                        "l2": "inputs per step (%.2f GB) exceed the 126 MB L2; no flush needed" % (ab["total"] * B / 1e9)},
-            "clocks": clocks, "e2e": e2e, "fused": fused, "e2e_m1": e2e_m1, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+            "clocks": clocks, "e2e": e2e, "fused": fused, "e2e_m1": e2e_m1, "m2": m2, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
 
 

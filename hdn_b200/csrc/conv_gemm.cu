@@ -243,10 +243,13 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(co
         int drained = 0;
         auto stage_block = [&](int kb, const float (&v)[NBJ][4]) {
             const int s = kb % STAGES;
-            // ---- a chunk that was completely staged a few blocks ago is (nearly) through the tensor core: fold it now ----
-            if (drained < nchunks && kb >= (drained + 1) * CG_KCB + 2) drain(drained++);
             // ---- the MMAs that read this stage STAGES blocks ago must have retired ----
             if (kb >= STAGES) mbar_wait(&bar_free[s], ((kb / STAGES) - 1) & 1);
+            // ---- fold a finished accumulation chunk into the fp32 registers.  Only once block kb - STAGES -- the chunk's last or a
+            //      later one -- is known to have retired (the wait above), so this never stalls on the tensor core: draining two
+            //      blocks after a chunk was STAGED made all producers wait ~2 blocks of MMA time per chunk and then starved the
+            //      tensor core in turn (tensor pipe 40 %, profiles/r02_ncu_conv_search.md) ----
+            if (drained < nchunks && kb >= (drained + 1) * CG_KCB - 1 + STAGES) drain(drained++);
             float *b_hi = reinterpret_cast<float *>(smem + s * STAGE + 2 * A_TILE), *b_lo = b_hi + B_TILE / 4;
 #pragma unroll
             for (int j = 0; j < NBJ; ++j) {
@@ -278,14 +281,24 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(co
         const float sc = scp ? __ldg(scp + co) : 1.f, sh = shp ? __ldg(shp + co) : 0.f;
         const size_t obase = ((size_t)img * a.Cout + co) * HWo;
         if (!PROJECT) {
+            // A thread owns one CHANNEL row of the tile, so direct stores would touch 32 different lines per warp instruction.
+            // The pipeline stages are dead by now: transpose through them (pitch BN + 1) and write pixel-contiguous rows,
+            // residual add and ReLU applied on the way out (coalesced residual reads as well).
+            constexpr int YP = BN + 1;
+            float *ys = reinterpret_cast<float *>(smem);
 #pragma unroll
-            for (int e = 0; e < HALF; ++e) {
-                const int p = pix0 + col_lo + e;
+            for (int e = 0; e < HALF; ++e) ys[row * YP + col_lo + e] = fmaf(racc[e], sc, sh);
+            asm volatile("bar.sync 1, %0;" ::"n"(CG_THREADS) : "memory");  // the 256 producer threads only
+            const size_t tile_base = ((size_t)img * a.Cout + co0) * HWo;
+            float *outp = a.out[prob];
+#pragma unroll 4
+            for (int i = tid; i < CG_BM * BN; i += CG_THREADS) {
+                const int r = i / BN, c = i - r * BN, p = pix0 + c;
                 if (p < HWo) {
-                    float y = fmaf(racc[e], sc, sh);
-                    if (resp) y += __ldg(resp + obase + p);
+                    float y = ys[r * YP + c];
+                    if (resp) y += __ldg(resp + tile_base + (size_t)r * HWo + p);
                     if (a.relu) y = fmaxf(y, 0.f);
-                    a.out[prob][obase + p] = y;
+                    outp[tile_base + (size_t)r * HWo + p] = y;
                 }
             }
         } else {
@@ -325,7 +338,7 @@ template <int BN, int STAGES, int RAW, bool PROJECT = false>
 static int launch_conv_gemm(const ConvGemmArgs &a, int nprob, cudaStream_t st) {
     constexpr size_t SMEM = (size_t)STAGES * (2 * CG_BM * CG_BK * 4 + 2 * CG_BK * BN * 4) + 1024;
     static_assert(SMEM <= 227 * 1024, "shared memory budget");
-    static_assert(!PROJECT || (size_t)(CG_BM * (BN + 1) + 8 * CG_BM) * 4 <= SMEM, "projection staging must fit the pipeline's shared memory");
+    static_assert((size_t)(CG_BM * (BN + 1) + 8 * CG_BM) * 4 <= SMEM, "epilogue staging must fit the pipeline's shared memory");
     static DeviceOnce once;
     if (int e = once.run([] { return cudaFuncSetAttribute(conv_gemm_tf32x3_kernel<BN, STAGES, RAW, PROJECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM); }))
         return e;

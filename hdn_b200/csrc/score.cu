@@ -97,7 +97,7 @@ __device__ __forceinline__ float head_combine(const float *const (&parts)[4], co
     return acc;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
     head_score_kernel(const __grid_constant__ HeadLevels h, float *__restrict__ cls_out, float *__restrict__ loc_out, const double *__restrict__ window,
                       double w_infl, float one_minus_w, long long *__restrict__ idx, double *__restrict__ pscore, float *__restrict__ score,
                       float *__restrict__ gathered, int B, int L, int n) {
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256)
         o.s = __shfl_xor_sync(0xffffffffu, best.s, off);
         best = better(best, o);
     }
-    __shared__ Best sb[8];
+    __shared__ Best sb[32];
     __shared__ int s_idx;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (lane == 0) sb[warp] = best;
@@ -171,7 +171,8 @@ extern "C" int hdn_head_score_f32(int nlev, int ntile, const float *const *cls_p
     }
     h.nlev = nlev;
     h.ntile = ntile;
-    head_score_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(h, cls_out, loc_out, window, win_influence, (float)(1.0 - win_influence),
+    // one block per pair; 1024 threads: the block is latency-bound on its ~20 independent loads per pixel, so width buys time
+    head_score_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(h, cls_out, loc_out, window, win_influence, (float)(1.0 - win_influence),
                                                           reinterpret_cast<long long *>(idx), pscore, score, gathered, B, L, N * N);
     count_launch();
     return launch_status();

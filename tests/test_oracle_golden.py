@@ -145,3 +145,38 @@ def test_oracle_argmax_nan_semantics_match_numpy():
     idx = c_oracle.score_argmax(cls, loc, None, 0.0)[0]
     assert np.array_equal(idx, np.argmax(score, 1))
     assert list(idx[:2]) == [0, 3 * N + 7]
+
+
+def test_cpu_shim_runs_the_mirror_like_the_reference():
+    """oracle/cpu_shim.py (bench.py's model / tracker-level CPU arm): the mirrored ModelBuilder + hdnTrackerHomo on CPU tensors,
+    operators backed by torch_port, reproduce the REFERENCE's own outputs (model_native golden, first frames of tracker_seq7)."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r + "/tests")
+from conftest import load_golden, assert_close
+from oracle import cpu_shim
+from hdn_b200 import synthetic
+model, cfg = cpu_shim.build_cpu_model()
+g = load_golden("model_native")
+seed = int(g["seed"])
+with torch.no_grad():
+    model.template(torch.from_numpy(synthetic.crop_tensor(seed, (1, 6, 127, 127))))
+    out = model.track_new(torch.from_numpy(synthetic.crop_tensor(seed + 1, (1, 3, 255, 255))))
+assert_close(out["cls"].numpy(), g["cls"], what="cls"); assert_close(out["loc_c"].numpy(), g["loc_c"], what="loc_c")
+from hdn.tracker.tracker_builder import build_tracker
+from hdn.utils.bbox import get_min_max_bbox, get_w_h_from_poly
+t = load_golden("tracker_seq7")
+tracker = build_tracker(model)
+frames, polys = synthetic.sequence(int(t["seed"]), 3)
+gt = polys[0]; cx, cy, w, h = get_min_max_bbox(np.array(gt))
+tracker.init(frames[0], [cx - (w - 1) / 2, cy - (h - 1) / 2, w, h], get_w_h_from_poly(np.array(gt)), gt, np.array([gt[:2]]))
+for i in (1, 2):
+    o = tracker.track_new(i, frames[i], None, None, None)
+    assert np.abs(np.asarray(o["polygon"], np.float64) - t["polygon"][i - 1]).max() <= 1e-3 * 600, i
+print("OK")
+''' % (ROOT, ROOT)
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0 and "OK" in res.stdout, res.stdout[-1500:] + res.stderr[-1500:]
