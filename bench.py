@@ -398,13 +398,30 @@ def m2_block(workload, B, steps=3, warmup=2):
             out = frame()
         e1.record()
         torch.cuda.synchronize()
+        # where the step goes: one extra pass with an event after every stage / sub-module
+        marks = [("start", torch.cuda.Event(enable_timing=True))]
+        marks[0][1].record()
+
+        def mark(name):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev))
+
+        feats = model.backbone(x); mark("backbone(search crop)")
+        xf = model.neck(feats); mark("neck")
+        model.head.fused(xf, model._k_sim, model._window(model.head.out_size(xf, model._k_sim), x.device), cfg.TRACK.WINDOW_INFLUENCE, want_maps=False)
+        mark("fused BAN head + K6")
+        model._stage2_packed(x); mark("stage 2: K3 + backbone(log-polar crop) + neck + fused head_lp + K6")
+        model._stage3_packed(pair, h4p); mark("stage 3: ShareFeature + ResNet-34 + K5/K4 + scores")
+        torch.cuda.synchronize()
+        stages = {marks[i + 1][0]: marks[i][1].elapsed_time(marks[i + 1][1]) for i in range(len(marks) - 1)}
     ms = e0.elapsed_time(e1) / steps
     _, _, bf16 = peaks()
     tf = M2_GFLOP_PER_PAIR[workload] * B / ms  # GFLOP per ms = TFLOP/s
     del model
     torch.cuda.empty_cache()
     return {"value": B / ms * 1e3, "unit": UNIT, "ms_per_step": ms, "pairs_per_step": B, "steps": steps, "gflop_per_pair": M2_GFLOP_PER_PAIR[workload],
-            "tflops": tf, "bf16_peak_tflops_sustained": bf16, "frac_of_bf16_peak": tf / bf16 if bf16 else None,
+            "tflops": tf, "stage_ms": stages, "bf16_peak_tflops_sustained": bf16, "frac_of_bf16_peak": tf / bf16 if bf16 else None,
             "precision": "fp32-accurate: 3xTF32 on tcgen05 (3 tensor-core MACs per MAC) for the stride-1 backbone / neck / head layers, cuDNN fp32 "
                          "(TF32 off) for the stem, layer1 and the strided layers",
             "check": float(out[0].float().sum().item() * 0 + out[2][0, 8].item())}

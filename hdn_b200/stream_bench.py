@@ -45,10 +45,32 @@ def write_result(path, rows):
             fh.write(" ".join(str(i) for i in x) + "\n")
 
 
+def prefetch(iterable, depth=3):
+    """Iterate `iterable` on a background thread, `depth` items ahead: the dataset iterator decodes a frame per step (cv2.imread,
+    ~4 ms at 1280x720, GIL released), which the reference does serially between tracker calls (toolkit/datasets/video.py:79-81)."""
+    import queue
+    import threading
+    q, end = queue.Queue(maxsize=depth), object()
+
+    def work():
+        try:
+            for item in iterable:
+                q.put(item)
+        finally:
+            q.put(end)
+
+    threading.Thread(target=work, daemon=True).start()
+    while True:
+        item = q.get()
+        if item is end:
+            return
+        yield item
+
+
 def track_video(tracker, video):
     """The per-video loop of tools/test.py:115-175.  -> (rows for the result file, seconds inside init/track_new, frames tracked)."""
     rows, toc = [], 0.0
-    for idx, (img, gt_bbox) in enumerate(video):
+    for idx, (img, gt_bbox) in enumerate(prefetch(video)):
         tic = time.perf_counter()
         if idx == 0:
             tracker.init(img, *first_frame_args(gt_bbox))
@@ -64,7 +86,7 @@ def track_videos_lockstep(model, videos):
     """S videos of equal length advanced together (hdn_b200.batched.LockstepTrackers).  -> (rows per video, seconds, frames)."""
     from hdn_b200.batched import LockstepTrackers
     group = LockstepTrackers(model, len(videos))
-    iters = [iter(v) for v in videos]
+    iters = [prefetch(v) for v in videos]
     rows = [[] for _ in videos]
     toc = 0.0
     for idx in range(min(len(v) for v in videos)):
@@ -130,8 +152,11 @@ def run(a):
     dev = torch.device("cuda", local_rank)
     H, W = (int(v) for v in a.frame_size.lower().split("x"))
     root = os.path.join(ROOT, "testing_dataset", "POT")  # where tools/test.py looks for it (:58-62)
-    if rank == 0:
-        pot_fixture.write_dataset(root, a.sequences, a.frames, (H, W))
+    if not pot_fixture.is_current(root, a.sequences, a.frames, (H, W)):  # every rank renders its own sequences, rank 0 merges the JSON
+        pot_fixture.write_dataset(root, a.sequences, a.frames, (H, W), only=shard.round_robin(a.sequences, rank, world), merge=False)
+        shard.barrier()
+        if rank == 0:
+            pot_fixture.write_dataset(root, a.sequences, a.frames, (H, W), only=[], merge=True)
     shard.barrier()
     if a.host_preproc:
         os.environ["HDN_B200_DEVICE_PREPROC"] = "0"
