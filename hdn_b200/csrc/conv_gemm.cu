@@ -95,6 +95,7 @@ struct ConvGemmArgs {
     float *out[HDN_MAX_PROBLEMS];
     const float *w2[HDN_MAX_PROBLEMS];  // PROJECT mode: second 1x1 convolution [L, Cout] row-major (device); out = partial sums
     int B, L;
+    int splitk;  // > 1: a cluster of `splitk` CTAs shares one output tile, each taking 1/splitk of K (blockIdx.x = tile * splitk + rank)
     int Cin, Cout, H, W, taps, dil, relu;
     int Ho, Wo, off;  // output extent and the input offset of output pixel (0,0): 'same' -> (H, W, 0); 'valid' 3x3 -> (H-2d, W-2d, d)
 };
@@ -124,9 +125,16 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(co
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int HW = a.H * a.W, HWo = a.Ho * a.Wo;
-    const int pix0 = blockIdx.x * BN, co0 = blockIdx.y * CG_BM, prob = blockIdx.z / a.B, img = blockIdx.z - prob * a.B;
+    // SPLIT-K over a thread-block cluster (small problems, tracking batch sizes): the `splitk` CTAs of a cluster own the same output
+    // tile and 1/splitk of the K blocks each; their fp32 partial tiles meet in the leader through distributed shared memory.
+    const int S = PROJECT ? 1 : a.splitk;
+    uint32_t crank = 0;
+    if (S > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const int tile_x = S > 1 ? (int)blockIdx.x / S : (int)blockIdx.x;
+    const int pix0 = tile_x * BN, co0 = blockIdx.y * CG_BM, prob = blockIdx.z / a.B, img = blockIdx.z - prob * a.B;
     const int Ktot = a.taps * a.Cin;
-    const int nkb = Ktot / CG_BK;
+    const int nkb = Ktot / CG_BK / S;     // K blocks of THIS CTA ...
+    const int kb0 = (int)crank * nkb;     // ... starting at global block kb0
     const int nchunks = (nkb + CG_KCB - 1) / CG_KCB;
 
     if (tid == 0) {
@@ -179,12 +187,12 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(co
     } else if (warp == CG_THREADS / 32 + 1) {
         // ============================== weight loader: one 32 KB TMA bulk copy per K block ==============================
         if (elect_one()) {
-            const float *wsrc = a.wpk[prob] + (size_t)blockIdx.y * nkb * (2 * A_TILE / 4);
+            const float *wsrc = a.wpk[prob] + (size_t)blockIdx.y * (nkb * S) * (2 * A_TILE / 4);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % STAGES;
                 if (kb >= STAGES) mbar_wait(&bar_free[s], ((kb / STAGES) - 1) & 1);
                 mbar_expect_tx(&bar_full[s], 2 * A_TILE);
-                bulk_g2s(smem + s * STAGE, wsrc + (size_t)kb * (2 * A_TILE / 4), 2 * A_TILE, &bar_full[s]);
+                bulk_g2s(smem + s * STAGE, wsrc + (size_t)(kb0 + kb) * (2 * A_TILE / 4), 2 * A_TILE, &bar_full[s]);
             }
         }
         __syncwarp();
@@ -227,7 +235,7 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(co
         // layout.  (The first version staged them through a cp.async landing ring: 16 4-byte LDGSTS per thread and block kept
         // the load/store unit busier than the tensor core -- profiles/r01_ncu_conv_gemm.md.)
         auto load_block = [&](int kb, float (&v)[NBJ][4]) {
-            const int k0 = kb * CG_BK;
+            const int k0 = (kb0 + kb) * CG_BK;
             const int tap = k0 / a.Cin, ci0 = k0 - tap * a.Cin;
             const int dy = a.taps == 1 ? 0 : (tap / 3 - 1) * a.dil, dx = a.taps == 1 ? 0 : (tap % 3 - 1) * a.dil;
             const int r = b_r + dy, c = b_c + dx;
@@ -286,6 +294,10 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(co
             // residual add and ReLU applied on the way out (coalesced residual reads as well).
             constexpr int YP = BN + 1;
             float *ys = reinterpret_cast<float *>(smem);
+            if (S > 1) {  // split-K: leave the raw fp32 partial tile in shared memory; the cluster reduces it below
+#pragma unroll
+                for (int e = 0; e < HALF; ++e) ys[row * YP + col_lo + e] = racc[e];
+            } else {
 #pragma unroll
             for (int e = 0; e < HALF; ++e) ys[row * YP + col_lo + e] = fmaf(racc[e], sc, sh);
             asm volatile("bar.sync 1, %0;" ::"n"(CG_THREADS) : "memory");  // the 256 producer threads only
@@ -300,6 +312,7 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(co
                     if (a.relu) y = fmaxf(y, 0.f);
                     outp[tile_base + (size_t)r * HWo + p] = y;
                 }
+            }
             }
         } else {
             // The pipeline stages are dead (the last accumulator was committed after every MMA had read them): stage the tile as
@@ -331,6 +344,39 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(co
     }
     tc_fence_before();
     __syncthreads();
+    if (!PROJECT && S > 1) {
+        // ---- split-K reduction through distributed shared memory: every CTA of the cluster holds its partial tile in ys; the leader
+        //      adds them in rank order (deterministic), applies BatchNorm / residual / ReLU and stores pixel-contiguous rows ----
+        constexpr int YP = BN + 1;
+        const float *ys = reinterpret_cast<const float *>(smem);
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        if (crank == 0) {
+            const float *scp = a.scale[prob], *shp = a.shift[prob], *resp = a.residual[prob];
+            const size_t tile_base = ((size_t)img * a.Cout + co0) * HWo;
+            float *outp = a.out[prob];
+            const uint32_t ys_s = smem_u32(ys);
+            for (int i = tid; i < CG_BM * BN; i += CG_THREADS + 64) {
+                const int r = i / BN, c = i - r * BN, p = pix0 + c;
+                if (p < HWo) {
+                    float acc = ys[r * YP + c];
+                    for (int peer = 1; peer < S; ++peer) {
+                        uint32_t remote;
+                        float v;
+                        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(ys_s + (uint32_t)(r * YP + c) * 4u), "r"(peer));
+                        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+                        acc += v;
+                    }
+                    const int co = co0 + r;
+                    float y = fmaf(acc, scp ? __ldg(scp + co) : 1.f, shp ? __ldg(shp + co) : 0.f);
+                    if (resp) y += __ldg(resp + tile_base + (size_t)r * HWo + p);
+                    if (a.relu) y = fmaxf(y, 0.f);
+                    outp[tile_base + (size_t)r * HWo + p] = y;
+                }
+            }
+        }
+        // nobody leaves (and frees its shared memory) before the leader has read every partial tile
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)(2 * BN)));
 }
 
@@ -342,8 +388,26 @@ static int launch_conv_gemm(const ConvGemmArgs &a, int nprob, cudaStream_t st) {
     static DeviceOnce once;
     if (int e = once.run([] { return cudaFuncSetAttribute(conv_gemm_tf32x3_kernel<BN, STAGES, RAW, PROJECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM); }))
         return e;
-    dim3 grid((a.Ho * a.Wo + BN - 1) / BN, a.Cout / CG_BM, a.B * nprob);
-    conv_gemm_tf32x3_kernel<BN, STAGES, RAW, PROJECT><<<grid, CG_THREADS + 64, SMEM, st>>>(a);
+    const int S = a.splitk > 1 ? a.splitk : 1;
+    dim3 grid((a.Ho * a.Wo + BN - 1) / BN * S, a.Cout / CG_BM, a.B * nprob);
+    if (S == 1) {
+        conv_gemm_tf32x3_kernel<BN, STAGES, RAW, PROJECT><<<grid, CG_THREADS + 64, SMEM, st>>>(a);
+    } else {  // a cluster of S CTAs along x per output tile
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(CG_THREADS + 64);
+        cfg.dynamicSmemBytes = SMEM;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = S;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_tf32x3_kernel<BN, STAGES, RAW, PROJECT>, a);
+        if (e != cudaSuccess) return (int)e;
+    }
     count_launch();
     return launch_status();
 }
@@ -382,6 +446,8 @@ extern "C" int hdn_conv_gemm_supported(int Cin, int Cout, int ksize, int dilatio
     return (Cin >= 32 && Cin % 32 == 0 && Cout % CG_BM == 0 && (ksize == 1 || ksize == 3) && dilation >= 1) ? 1 : 0;
 }
 
+static int g_conv_splitk = 1;  // hdn_conv_gemm_set_splitk (A/B switch; the result is deterministic either way)
+
 static int conv_gemm_multi(int n, const float *const *x, const float *const *wpk, const float *const *scale, const float *const *shift,
                            const float *const *residual, const float *const *w2, float *const *out, int B, int Cin, int Cout, int H, int W,
                            int ksize, int dilation, int valid, int relu, int L, cudaStream_t st) {
@@ -403,7 +469,7 @@ static int conv_gemm_multi(int n, const float *const *x, const float *const *wpk
         a.w2[i] = w2 ? w2[i] : nullptr;
         a.out[i] = out[i];
     }
-    a.B = B; a.L = L;
+    a.B = B; a.L = L; a.splitk = 1;
     a.Cin = Cin; a.Cout = Cout; a.H = H; a.W = W; a.taps = ksize * ksize; a.dil = dilation; a.relu = relu;
     a.Ho = H - shrink; a.Wo = W - shrink; a.off = shrink / 2;
     if (w2) {  // fused second 1x1: narrow pixel tiles (the projection's staging pitch), L <= 8
@@ -411,8 +477,17 @@ static int conv_gemm_multi(int n, const float *const *x, const float *const *wpk
         return launch_conv_gemm<64, 4, 0, true>(a, n, st);
     }
     const long long tiles128 = (long long)((a.Ho * a.Wo + 127) / 128) * (Cout / CG_BM) * B * n;
-    // small problems (tracking batch sizes): narrower pixel tiles put more CTAs on the 148 SMs
-    return tiles128 >= 2 * sm_count() ? launch_conv_gemm<128, 3, 0>(a, n, st) : launch_conv_gemm<64, 4, 0>(a, n, st);
+    // small problems (tracking batch sizes): narrower pixel tiles put more CTAs on the 148 SMs ...
+    if (tiles128 >= 2 * sm_count()) return launch_conv_gemm<128, 3, 0>(a, n, st);
+    // ... and when even those leave most SMs idle (a 15x15 or 31x31 map at batch 1), K is split over a cluster of 2 / 4 / 8 CTAs
+    const long long ctas = (long long)((a.Ho * a.Wo + 63) / 64) * (Cout / CG_BM) * B * n;
+    const int nkb = a.taps * Cin / CG_BK;
+    int split = 1;
+    if (g_conv_splitk != 0)
+        for (int s2 = 8; s2 >= 2; s2 /= 2)
+            if (nkb % s2 == 0 && nkb / s2 >= 4 && ctas * s2 <= sm_count() + sm_count() / 4) { split = s2; break; }
+    a.splitk = split;
+    return launch_conv_gemm<64, 4, 0>(a, n, st);
 }
 
 extern "C" int hdn_conv_gemm_f32(const float *x, const float *wpk, const float *scale, const float *shift, const float *residual, float *out,
@@ -435,4 +510,9 @@ extern "C" int hdn_head_project_multi_f32(int n, const float *const *x_host, con
     if (!w2_host) return HDN_ERR_NULL;
     return conv_gemm_multi(n, x_host, wpk_host, scale_host, shift_host, nullptr, w2_host, part_host, B, C, C, H, W, 1, 1, 0, 1, L,
                            (cudaStream_t)stream);
+}
+
+extern "C" int hdn_conv_gemm_set_splitk(int enable) {
+    g_conv_splitk = enable ? 1 : 0;
+    return HDN_OK;
 }

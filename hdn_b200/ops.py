@@ -398,6 +398,11 @@ def head_score(cls_parts, loc_parts, cls_bias, loc_bias, cls_w, loc_scale, loc_w
     return cls, loc, buf
 
 
+def set_conv_splitk(enable=True):
+    """Split-K over a thread-block cluster for small convolutions (default on); off = one CTA per output tile (A/B runs)."""
+    _lib.check(_lib.lib().hdn_conv_gemm_set_splitk(int(bool(enable))), "hdn_conv_gemm_set_splitk")
+
+
 def conv_gemm_supported(Cin, Cout, ksize, dilation=1):
     return bool(_lib.lib().hdn_conv_gemm_supported(Cin, Cout, ksize, dilation))
 

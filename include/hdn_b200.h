@@ -131,6 +131,10 @@ int hdn_score_argmax_f32(const float *cls, const float *loc, const double *windo
  * hdn_conv_pack_weight_f32: wt [Cout, Ktot = ksize*ksize*Cin] tap-major (weight.permute(0,2,3,1)) -> packed [2*Cout*Ktot]
  *   floats (TF32 hi / lo halves, tiled per 128-channel x 32-deep block in the tensor core's shared-memory layout). */
 int hdn_conv_gemm_supported(int Cin, int Cout, int ksize, int dilation);
+/* Small problems (a 15x15 or 31x31 map at tracking batch sizes fills a fraction of the 148 SMs) split K over a thread-block
+ * cluster of 2 / 4 / 8 CTAs whose fp32 partial tiles are added in rank order through distributed shared memory (deterministic).
+ * enable = 0 switches that off (A/B runs); default on. */
+int hdn_conv_gemm_set_splitk(int enable);
 int hdn_conv_pack_weight_f32(const float *wt, float *packed, int Cout, int Ktot, hdn_stream_t stream);
 int hdn_conv_gemm_f32(const float *x, const float *wpk, const float *scale, const float *shift, const float *residual, float *out, int B,
                       int Cin, int Cout, int H, int W, int ksize, int dilation, int valid, int relu, hdn_stream_t stream);

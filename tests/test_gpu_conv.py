@@ -86,10 +86,16 @@ def test_conv_gemm_multi_equals_single_launches():
     sc = [1 + 0.1 * torch.randn(256, device="cuda", generator=g) for _ in range(6)]
     sh = [0.1 * torch.randn(256, device="cuda", generator=g) for _ in range(6)]
     packs = [ops.pack_conv_weight(w) for w in ws]
-    multi = ops.conv_gemm_multi([xs[i // 2] for i in range(6)], packs, sc, sh, ksize=3, relu=True, valid=True)
-    for i in range(6):
-        single = ops.conv_gemm(xs[i // 2], packs[i], sc[i], sh[i], ksize=3, relu=True, valid=True)
-        assert tuple(single.shape) == (2, 256, 15, 15) and torch.equal(single, multi[i])
+    ops.set_conv_splitk(False)  # (a lone small launch would split K over a cluster and sum in another order: same result to fp32 rounding only)
+    try:
+        multi = ops.conv_gemm_multi([xs[i // 2] for i in range(6)], packs, sc, sh, ksize=3, relu=True, valid=True)
+        for i in range(6):
+            single = ops.conv_gemm(xs[i // 2], packs[i], sc[i], sh[i], ksize=3, relu=True, valid=True)
+            assert tuple(single.shape) == (2, 256, 15, 15) and torch.equal(single, multi[i])
+    finally:
+        ops.set_conv_splitk(True)
+    split = ops.conv_gemm(xs[0], packs[0], sc[0], sh[0], ksize=3, relu=True, valid=True)
+    assert float((split - multi[0]).abs().max()) <= 5e-6 * float(multi[0].abs().max())
 
 
 @pytest.mark.parametrize("B,N,L", [(1, 25, 2), (3, 33, 2), (2, 13, 4), (2, 29, 4)])
@@ -189,3 +195,32 @@ def test_head_engine_equals_cpu_port(workload, B, chunk, shared, u8):
     assert sets[0] is sets[2] and sets[0] is not sets[1]
     for k in he.HeadEngine.HOST_OUT:
         assert torch.equal(sets[1][k], out[k]) and torch.equal(sets[2][k], out[k]), k
+
+
+@pytest.mark.parametrize("case", [(1, 256, 256, 15, 15, 3, 2), (1, 1024, 256, 31, 31, 1, 1), (1, 512, 512, 31, 31, 3, 4), (2, 256, 1024, 15, 15, 1, 1)])
+def test_conv_gemm_cluster_split_k(case):
+    """Tracking-batch-size layers split K over a thread-block cluster (partial tiles added through distributed shared memory in
+    rank order): same fp32 accuracy as the single-CTA kernel, deterministic (bitwise repeatable), residual / ReLU epilogue intact."""
+    from hdn_b200 import ops
+    B, Cin, Cout, H, W, k, d = case
+    g = torch.Generator(device="cuda").manual_seed(Cin + Cout + H + k)
+    x = torch.randn(B, Cin, H, W, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, k, k, device="cuda", generator=g) * (2.0 / (Cin * k * k)) ** 0.5
+    scale = 1 + 0.1 * torch.randn(Cout, device="cuda", generator=g)
+    shift = 0.1 * torch.randn(Cout, device="cuda", generator=g)
+    res = torch.randn(B, Cout, H, W, device="cuda", generator=g)
+    wp = ops.pack_conv_weight(w)
+    try:
+        ops.set_conv_splitk(False)
+        one = ops.conv_gemm(x, wp, scale, shift, res, ksize=k, dilation=d, relu=True)
+        ops.set_conv_splitk(True)
+        a = ops.conv_gemm(x, wp, scale, shift, res, ksize=k, dilation=d, relu=True)
+        b = ops.conv_gemm(x, wp, scale, shift, res, ksize=k, dilation=d, relu=True)
+    finally:
+        ops.set_conv_splitk(True)
+    assert torch.equal(a, b)
+    want = F.relu(F.conv2d(x.double(), w.double(), padding=d * (k // 2), dilation=d) * scale.double().view(1, -1, 1, 1) + shift.double().view(1, -1, 1, 1)
+                  + res.double())
+    den = float(want.abs().max())
+    assert float((a.double() - want).abs().max()) / den < 1e-5 and float((one.double() - want).abs().max()) / den < 1e-5
+    assert float((a - one).abs().max()) / den < 5e-6
