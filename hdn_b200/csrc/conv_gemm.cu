@@ -139,12 +139,12 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(co
 
     if (tid == 0) {
         for (int i = 0; i < STAGES; ++i) {
-            mbar_init(&bar_full[i], CG_THREADS + 1);  // 256 producer arrivals + the TMA issuer's arrive.expect_tx
+            mbar_init(&bar_full[i], CG_THREADS / 32 + 1);  // one arrival per producer warp + the TMA issuer's arrive.expect_tx
             mbar_init(&bar_free[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bar_acc_full[i], 1);
-            mbar_init(&bar_acc_free[i], CG_THREADS);
+            mbar_init(&bar_acc_free[i], CG_THREADS / 32);  // one arrival per producer warp
         }
         mbar_fence_init();
     }
@@ -225,7 +225,8 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(co
                 for (int e = 0; e < 16; ++e) racc[c0 + e] += v[e];
             }
             tc_fence_before();
-            mbar_arrive(&bar_acc_free[chunk & 1]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_acc_free[chunk & 1]);
         };
 
         // Activations: block kb's [32 k][BN pixels] tile is read straight into registers with coalesced 4-byte loads (NCHW rows
@@ -234,20 +235,43 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(co
         // block kb+1 are in flight while block kb is split (hi / lo) and stored into the canonical no-swizzle K-major UMMA
         // layout.  (The first version staged them through a cp.async landing ring: 16 4-byte LDGSTS per thread and block kept
         // the load/store unit busier than the tensor core -- profiles/r01_ncu_conv_gemm.md.)
-        auto load_block = [&](int kb, float (&v)[NBJ][4]) {
-            const int k0 = (kb0 + kb) * CG_BK;
-            const int tap = k0 / a.Cin, ci0 = k0 - tap * a.Cin;
-            const int dy = a.taps == 1 ? 0 : (tap / 3 - 1) * a.dil, dx = a.taps == 1 ? 0 : (tap % 3 - 1) * a.dil;
-            const int r = b_r + dy, c = b_c + dx;
-            const bool ok = r >= 0 && r < a.H && c >= 0 && c < a.W;
-            const float *src = xb + (size_t)ci0 * HW + (ok ? r * a.W + c : 0);
+        // Everything that does not change from block to block is hoisted: the producers' issue slots, not the tensor core, bounded
+        // the first versions (3,800 warp instructions per K block and CTA, 40 % of them 64-bit address arithmetic and integer
+        // divisions, 22 % barrier polling).  A block's loads are  ublk[toff[j][e]]:  ublk = warp-uniform base of (channel block,
+        // tap shift), advanced incrementally (no division), toff = 16 per-thread element offsets fixed for the whole kernel.
+        unsigned toff[NBJ][4];
+        {
+            const unsigned pix_off = bp < HWo ? (unsigned)(b_r * a.W + b_c) : 0u;
 #pragma unroll
-            for (int j = 0; j < NBJ; ++j) {
-                const int kc = (tid + CG_THREADS * j) / BN;
+            for (int j = 0; j < NBJ; ++j)
 #pragma unroll
-                for (int e = 0; e < 4; ++e) v[j][e] = ok ? __ldg(src + (size_t)(kc * 4 + e) * HW) : 0.f;
+                for (int e = 0; e < 4; ++e) toff[j][e] = (unsigned)(((tid + CG_THREADS * j) / BN) * 4 + e) * (unsigned)HW + pix_off;
+        }
+        int ld_tap, ld_ci0, ld_ty, ld_tx;  // position of the NEXT block to load (blocks are loaded in order)
+        {
+            const int k0 = kb0 * CG_BK;
+            ld_tap = k0 / a.Cin;
+            ld_ci0 = k0 - ld_tap * a.Cin;
+            ld_ty = ld_tap / 3;
+            ld_tx = ld_tap - 3 * ld_ty;
+        }
+        auto load_block = [&](int, float (&v)[NBJ][4]) {
+            const int dy = a.taps == 1 ? 0 : (ld_ty - 1) * a.dil, dx = a.taps == 1 ? 0 : (ld_tx - 1) * a.dil;
+            const bool ok = (unsigned)(b_r + dy) < (unsigned)a.H && (unsigned)(b_c + dx) < (unsigned)a.W;
+            const float *ublk = xb + ((long long)ld_ci0 * HW + dy * a.W + dx);  // the same for every thread of the CTA
+#pragma unroll
+            for (int j = 0; j < NBJ; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[j][e] = ok ? __ldg(ublk + toff[j][e]) : 0.f;
+            ld_ci0 += CG_BK;
+            if (ld_ci0 == a.Cin) {
+                ld_ci0 = 0;
+                if (++ld_tx == 3) { ld_tx = 0; ++ld_ty; }
             }
         };
+        unsigned soff[NBJ];  // this thread's 16-byte slots inside a stage's B tile (canonical K-major layout), in floats
+#pragma unroll
+        for (int j = 0; j < NBJ; ++j) soff[j] = (unsigned)((((tid + CG_THREADS * j) / BN) * B_LBO + (bn >> 3) * B_SBO + (bn & 7) * 16) >> 2);
         int drained = 0;
         auto stage_block = [&](int kb, const float (&v)[NBJ][4]) {
             const int s = kb % STAGES;
@@ -261,16 +285,19 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(co
             float *b_hi = reinterpret_cast<float *>(smem + s * STAGE + 2 * A_TILE), *b_lo = b_hi + B_TILE / 4;
 #pragma unroll
             for (int j = 0; j < NBJ; ++j) {
-                const int kc = (tid + CG_THREADS * j) / BN;
                 float4 h, l;
                 split_tf32(v[j][0], h.x, l.x); split_tf32(v[j][1], h.y, l.y); split_tf32(v[j][2], h.z, l.z); split_tf32(v[j][3], h.w, l.w);
-                const int off = (kc * B_LBO + (bn >> 3) * B_SBO + (bn & 7) * 16) >> 2;
-                *reinterpret_cast<float4 *>(b_hi + off) = h;
-                *reinterpret_cast<float4 *>(b_lo + off) = l;
+                *reinterpret_cast<float4 *>(b_hi + soff[j]) = h;
+                *reinterpret_cast<float4 *>(b_lo + soff[j]) = l;
             }
             fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
-            mbar_arrive(&bar_full[s]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_full[s]);  // one arrival per producer warp (its 32 threads' stores are fenced and ordered by the warp barrier)
         };
+#ifndef HDN_CG_PREFETCH
+#define HDN_CG_PREFETCH 1  // K blocks of activation loads in flight ahead of the block being converted (build-time A/B switch)
+#endif
+#if HDN_CG_PREFETCH == 1
         float va[NBJ][4], vb[NBJ][4];
         load_block(0, va);
         for (int kb = 0; kb < nkb; kb += 2) {
@@ -281,6 +308,23 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(co
                 stage_block(kb + 1, vb);
             }
         }
+#else
+        float va[NBJ][4], vb[NBJ][4], vc[NBJ][4];  // three register sets rotate: two blocks of loads are in flight behind the one in hand
+        load_block(0, va);
+        if (nkb > 1) load_block(1, vb);
+        for (int kb = 0; kb < nkb; kb += 3) {
+            if (kb + 2 < nkb) load_block(kb + 2, vc);
+            stage_block(kb, va);
+            if (kb + 1 < nkb) {
+                if (kb + 3 < nkb) load_block(kb + 3, va);
+                stage_block(kb + 1, vb);
+            }
+            if (kb + 2 < nkb) {
+                if (kb + 4 < nkb) load_block(kb + 4, vb);
+                stage_block(kb + 2, vc);
+            }
+        }
+#endif
 
         // ---- epilogue: remaining chunks -> registers -> BN / residual / ReLU -> global NCHW ----
         while (drained < nchunks) drain(drained++);
