@@ -26,83 +26,10 @@
 //   * a dedicated warp's elected lane issues 4 k-steps x 3 tcgen05.mma (kind::tf32, M=128, N=BN, K=8) per block and commits
 //     them to the mbarrier that frees the stage.
 // Epilogue: tcgen05.ld (32 lanes x 32b x 16 columns) -> y = acc*scale[co] + shift[co] (+ residual) (ReLU) -> global NCHW.
-#include "common.cuh"
+#include "umma.cuh"
 
 namespace hdn {
 
-constexpr int CG_BM = 128, CG_BK = 32, CG_THREADS = 256;
-constexpr int CG_KCB = 8;  // K blocks per TMEM accumulation chunk (8 x 32 = 256 of K)
-
-__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    // cute::UMMA::SmemDescriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout=0 (no swizzle) [61,64)
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
-}
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    const uint32_t zero = 0;  // disable-output-lane mask: all lanes enabled
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(zero)
-        : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
-          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
-    hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-    lo = x - hi;
-}
-
-// cp.async (LDGSTS): global -> shared without a register round trip; src_bytes = 0 zero-fills (conv padding / tile tail)
-__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void *dst, const void *src, uint32_t src_bytes) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-// Up to HDN_MAX_PROBLEMS same-shape convolutions per launch (the 3 levels x {cls, loc} branches of a BAN head share one shape):
-// blockIdx.z = problem * B + image.
-struct ConvGemmArgs {
-    const float *x[HDN_MAX_PROBLEMS], *wpk[HDN_MAX_PROBLEMS], *scale[HDN_MAX_PROBLEMS], *shift[HDN_MAX_PROBLEMS],
-        *residual[HDN_MAX_PROBLEMS];  // wpk: hdn_conv_pack_weight_f32 output
-    float *out[HDN_MAX_PROBLEMS];
-    const float *w2[HDN_MAX_PROBLEMS];  // PROJECT mode: second 1x1 convolution [L, Cout] row-major (device); out = partial sums
-    int B, L;
-    int splitk;  // > 1: a cluster of `splitk` CTAs shares one output tile, each taking 1/splitk of K (blockIdx.x = tile * splitk + rank)
-    int Cin, Cout, H, W, taps, dil, relu;
-    int Ho, Wo, off;  // output extent and the input offset of output pixel (0,0): 'same' -> (H, W, 0); 'valid' 3x3 -> (H-2d, W-2d, d)
-};
-
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 // Warp-specialised: warps 0..7 (256 threads) are PRODUCERS (global -> registers -> hi/lo -> shared, TMEM drains, epilogue),
 // warp 8 is the MMA ISSUER.  Stages hand over through mbarriers (full: 256 producer arrivals; free: tcgen05.commit), so
@@ -259,6 +186,7 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(co
             const int dy = a.taps == 1 ? 0 : (ld_ty - 1) * a.dil, dx = a.taps == 1 ? 0 : (ld_tx - 1) * a.dil;
             const bool ok = (unsigned)(b_r + dy) < (unsigned)a.H && (unsigned)(b_c + dx) < (unsigned)a.W;
             const float *ublk = xb + ((long long)ld_ci0 * HW + dy * a.W + dx);  // the same for every thread of the CTA
+            asm volatile("" : "+l"(ublk));  // keep it ONE pointer: each load is then base + toff * 4 (a single IMAD.WIDE), not a re-associated 64-bit sum
 #pragma unroll
             for (int j = 0; j < NBJ; ++j)
 #pragma unroll
@@ -295,7 +223,7 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(co
             if (lane == 0) mbar_arrive(&bar_full[s]);  // one arrival per producer warp (its 32 threads' stores are fenced and ordered by the warp barrier)
         };
 #ifndef HDN_CG_PREFETCH
-#define HDN_CG_PREFETCH 1  // K blocks of activation loads in flight ahead of the block being converted (build-time A/B switch)
+#define HDN_CG_PREFETCH 2  // K blocks of activation loads in flight ahead of the block being converted (build-time A/B switch)
 #endif
 #if HDN_CG_PREFETCH == 1
         float va[NBJ][4], vb[NBJ][4];
@@ -491,6 +419,7 @@ extern "C" int hdn_conv_gemm_supported(int Cin, int Cout, int ksize, int dilatio
 }
 
 static int g_conv_splitk = 1;  // hdn_conv_gemm_set_splitk (A/B switch; the result is deterministic either way)
+static int g_conv_shift = 1;   // hdn_conv_gemm_set_shift: conv_shift.cu for 3x3 'valid' layers (A/B switch)
 
 static int conv_gemm_multi(int n, const float *const *x, const float *const *wpk, const float *const *scale, const float *const *shift,
                            const float *const *residual, const float *const *w2, float *const *out, int B, int Cin, int Cout, int H, int W,
@@ -516,6 +445,8 @@ static int conv_gemm_multi(int n, const float *const *x, const float *const *wpk
     a.B = B; a.L = L; a.splitk = 1;
     a.Cin = Cin; a.Cout = Cout; a.H = H; a.W = W; a.taps = ksize * ksize; a.dil = dilation; a.relu = relu;
     a.Ho = H - shrink; a.Wo = W - shrink; a.off = shrink / 2;
+    // 3x3 'valid' layers (the heads' conv_search / conv_kernel): activations staged once per channel block, taps = shifted windows
+    if (!w2 && g_conv_shift && conv_shift_applicable(a, ksize, valid)) return launch_conv_shift(a, n, st);
     if (w2) {  // fused second 1x1: narrow pixel tiles (the projection's staging pitch), L <= 8
         if (L < 1 || L > 8) return HDN_ERR_UNSUPPORTED;
         return launch_conv_gemm<64, 4, 0, true>(a, n, st);
@@ -558,5 +489,10 @@ extern "C" int hdn_head_project_multi_f32(int n, const float *const *x_host, con
 
 extern "C" int hdn_conv_gemm_set_splitk(int enable) {
     g_conv_splitk = enable ? 1 : 0;
+    return HDN_OK;
+}
+
+extern "C" int hdn_conv_gemm_set_shift(int enable) {
+    g_conv_shift = enable ? 1 : 0;
     return HDN_OK;
 }

@@ -403,6 +403,11 @@ def set_conv_splitk(enable=True):
     _lib.check(_lib.lib().hdn_conv_gemm_set_splitk(int(bool(enable))), "hdn_conv_gemm_set_splitk")
 
 
+def set_conv_shift(enable=True):
+    """3x3 'valid' layers on the shifted-window kernel (conv_shift.cu; default on); off = the generic implicit GEMM (A/B runs)."""
+    _lib.check(_lib.lib().hdn_conv_gemm_set_shift(int(bool(enable))), "hdn_conv_gemm_set_shift")
+
+
 def conv_gemm_supported(Cin, Cout, ksize, dilation=1):
     return bool(_lib.lib().hdn_conv_gemm_supported(Cin, Cout, ksize, dilation))
 

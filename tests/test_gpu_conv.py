@@ -224,3 +224,35 @@ def test_conv_gemm_cluster_split_k(case):
     den = float(want.abs().max())
     assert float((a.double() - want).abs().max()) / den < 1e-5 and float((one.double() - want).abs().max()) / den < 1e-5
     assert float((a - one).abs().max()) / den < 5e-6
+
+
+@pytest.mark.parametrize("case", [(2, 256, 256, 63, 63), (3, 256, 256, 31, 31), (1, 64, 128, 9, 12), (2, 256, 256, 7, 7), (1, 512, 256, 15, 15), (5, 32, 128, 3, 3)])
+def test_conv3x3_valid_shifted_window_kernel(case):
+    """conv_shift.cu (activations staged once per channel block, the nine taps = shifted windows of one shared-memory tile):
+    fp32-accurate against fp64, equal to the generic implicit GEMM up to summation order, multi-problem launches, BN + residual + ReLU."""
+    from hdn_b200 import ops
+    B, Cin, Cout, H, W = case
+    g = torch.Generator(device="cuda").manual_seed(Cin + Cout + H * 7 + W)
+    xs = [torch.randn(B, Cin, H, W, device="cuda", generator=g) + 0.3 for _ in range(2)]
+    ws = [torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) * (2.0 / (Cin * 9)) ** 0.5 for _ in range(3)]
+    sc = [1 + 0.1 * torch.randn(Cout, device="cuda", generator=g) for _ in range(3)]
+    sh = [0.1 * torch.randn(Cout, device="cuda", generator=g) for _ in range(3)]
+    packs = [ops.pack_conv_weight(w) for w in ws]
+    res = torch.randn(B, Cout, H - 2, W - 2, device="cuda", generator=g)
+    try:
+        ops.set_conv_shift(False)
+        old = ops.conv_gemm(xs[0], packs[0], sc[0], sh[0], res, ksize=3, relu=True, valid=True)
+        ops.set_conv_shift(True)
+        new = ops.conv_gemm(xs[0], packs[0], sc[0], sh[0], res, ksize=3, relu=True, valid=True)
+        again = ops.conv_gemm(xs[0], packs[0], sc[0], sh[0], res, ksize=3, relu=True, valid=True)
+        multi = ops.conv_gemm_multi([xs[0], xs[1], xs[1]], packs, sc, sh, ksize=3, relu=False, valid=True)
+    finally:
+        ops.set_conv_shift(True)
+    assert torch.equal(new, again)
+    want = F.relu(F.conv2d(xs[0].double(), ws[0].double()) * sc[0].double().view(1, -1, 1, 1) + sh[0].double().view(1, -1, 1, 1) + res.double())
+    den = float(want.abs().max())
+    err_new, err_old = float((new.double() - want).abs().max()) / den, float((old.double() - want).abs().max()) / den
+    assert err_new < 1e-5 and err_new < 4 * max(err_old, 3e-7), (err_new, err_old)
+    for i, xi in enumerate([0, 1, 1]):
+        w64 = F.conv2d(xs[xi].double(), ws[i].double()) * sc[i].double().view(1, -1, 1, 1) + sh[i].double().view(1, -1, 1, 1)
+        assert float((multi[i].double() - w64).abs().max()) / float(w64.abs().max()) < 1e-5, i
