@@ -492,7 +492,12 @@ extern "C" int hdn_conv_gemm_set_splitk(int enable) {
     return HDN_OK;
 }
 
-extern "C" int hdn_conv_gemm_set_shift(int enable) {
-    g_conv_shift = enable ? 1 : 0;
+namespace hdn {
+extern int g_conv_shift_multicast;  // conv_shift.cu
+}
+
+extern "C" int hdn_conv_gemm_set_shift(int mode) {
+    g_conv_shift = mode ? 1 : 0;
+    hdn::g_conv_shift_multicast = mode == 2 ? 1 : 0;
     return HDN_OK;
 }

@@ -21,22 +21,67 @@
 namespace hdn {
 
 constexpr int CS_BN = 128;       // output pixels (on the input-width grid) per CTA
-constexpr int CS_WIN = 256;      // staged pixels per channel block: BN + halo, halo = 2 * W + 2 <= 128
-constexpr int CS_ASTAGES = 3;    // weight ring
 constexpr int CS_A_TILE = CG_BM * CG_BK * 4;           // one operand tile (hi or lo) of the weights
-constexpr int CS_B_TILE = CG_BK * CS_WIN * 4;          // one operand tile (hi or lo) of the staged window
 constexpr uint32_t CS_A_SBO = 128, CS_A_LBO = (CG_BM / 8) * 128;
-constexpr uint32_t CS_B_SBO = 128, CS_B_LBO = CS_WIN * 16;  // k-groups of 4 are WIN pixel rows apart
-constexpr size_t CS_SMEM = 2 * 2 * (size_t)CS_B_TILE + CS_ASTAGES * 2 * (size_t)CS_A_TILE + 1024;
-static_assert(CS_SMEM <= 227 * 1024, "shared memory budget");
+constexpr uint32_t CS_B_SBO = 128;
+// Two shapes: WIN = staged pixels per channel block (BN + halo, halo = 2 * W + 2), ASTAGES = depth of the weight ring that the
+// rest of the 227 KB buys.  W <= 63 (61x61 conv_search at 256/512 crops): 256 / 3;  W <= 31 (the tracker's native crops, the
+// log-polar branch, the template side): 192 / 4.
+template <int WIN, int ASTAGES>
+struct CSCfg {
+    static constexpr int B_TILE = CG_BK * WIN * 4;  // one operand tile (hi or lo) of the staged window
+    static constexpr uint32_t B_LBO = WIN * 16;     // k-groups of 4 are WIN pixel rows apart
+    static constexpr size_t SMEM = 2 * 2 * (size_t)B_TILE + ASTAGES * 2 * (size_t)CS_A_TILE + 1024;
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+    static_assert((size_t)(CG_BM * (CS_BN + 1)) * 4 <= 2 * 2 * (size_t)B_TILE, "epilogue staging must fit the window buffers");
+};
 
+// ---- cluster helpers (MC = a cluster of two CTAs on neighbouring pixel tiles shares every weight record through TMA multicast) ----
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t cta) {  // arrive on the barrier at the same offset in CTA `cta` of the cluster
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)),
+        "r"(cta)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {  // wait for arrivals that may come from the peer CTA
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAITC:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1, %2;\n"
+        "@P1 bra DONEC;\n"
+        "bra LAB_WAITC;\n"
+        "DONEC:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(0x989680u)
+        : "memory");
+}
+// global -> the SAME shared-memory offset in every CTA of `mask`; each destination's mbarrier (same offset) gets the complete_tx
+__device__ __forceinline__ void bulk_g2s_multicast(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+
+template <bool MC, int CS_WIN, int CS_ASTAGES>
 __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv3x3_shift_kernel(const __grid_constant__ ConvGemmArgs a) {
     constexpr int BN = CS_BN;
+    constexpr int CS_B_TILE = CSCfg<CS_WIN, CS_ASTAGES>::B_TILE;
+    constexpr uint32_t CS_B_LBO = CSCfg<CS_WIN, CS_ASTAGES>::B_LBO;
+#ifdef HDN_EXP_HALFN  // timing experiment only (wrong results): the same number of MMA instructions, half the math each
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((BN / 2) >> 3) << 17) | ((uint32_t)(CG_BM >> 4) << 24);
+#else
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(CG_BM >> 4) << 24);
+#endif
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *smem_b = smem;                                  // [2 buffers][hi | lo][k/4 (8)][WIN pixels][4]
     unsigned char *smem_a = smem + 2 * 2 * CS_B_TILE;              // [ASTAGES][hi | lo] packed weight records
-    __shared__ uint64_t bar_bfull[2], bar_bdone[2], bar_afull[CS_ASTAGES], bar_afree[CS_ASTAGES];
+    __shared__ uint64_t bar_bfull[2], bar_bdone[2], bar_afull[CS_ASTAGES], bar_afree[CS_ASTAGES], bar_peer[CS_ASTAGES];
     __shared__ uint32_t tmem_base_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -53,9 +98,12 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv3x3_shift_kernel(const
         for (int i = 0; i < CS_ASTAGES; ++i) {
             mbar_init(&bar_afull[i], 1);                // the loader's arrive.expect_tx
             mbar_init(&bar_afree[i], 1);
+            mbar_init(&bar_peer[i], 1);                 // MC: the peer CTA's "my stage is free and armed"
         }
         mbar_fence_init();
     }
+    uint32_t crank = 0;
+    if (MC) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"((uint32_t)(2 * BN)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -63,6 +111,7 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv3x3_shift_kernel(const
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (MC) cluster_sync_all();  // the peer's barriers are initialised before anybody arrives on them or multicasts into its shared memory
     const uint32_t tmem_d = tmem_base_slot;
 
     if (warp == CG_THREADS / 32) {
@@ -106,7 +155,18 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv3x3_shift_kernel(const
                     const int s = blk % CS_ASTAGES;
                     if (blk >= CS_ASTAGES) mbar_wait(&bar_afree[s], ((blk / CS_ASTAGES) - 1) & 1);
                     mbar_expect_tx(&bar_afull[s], 2 * CS_A_TILE);
-                    bulk_g2s(smem_a + s * 2 * CS_A_TILE, wsrc + (size_t)(tap * ncb + cb) * (2 * CS_A_TILE / 4), 2 * CS_A_TILE, &bar_afull[s]);
+                    const float *rec = wsrc + (size_t)(tap * ncb + cb) * (2 * CS_A_TILE / 4);
+                    if (!MC) {
+                        bulk_g2s(smem_a + s * 2 * CS_A_TILE, rec, 2 * CS_A_TILE, &bar_afull[s]);
+                    } else {
+                        // Both CTAs of the cluster consume the same record: each fetches ONE half (rank 0 the hi tile, rank 1 the lo
+                        // tile) and multicasts it into both shared memories -- half the L2 reads per CTA.  A stage may only be written
+                        // once it is free and armed in BOTH CTAs: tell the peer about mine, wait for the peer's.
+                        mbar_arrive_remote(&bar_peer[s], crank ^ 1u);
+                        mbar_wait_cluster(&bar_peer[s], (blk / CS_ASTAGES) & 1);
+                        bulk_g2s_multicast(smem_a + s * 2 * CS_A_TILE + crank * CS_A_TILE, rec + crank * (CS_A_TILE / 4), CS_A_TILE, &bar_afull[s],
+                                           (uint16_t)3);
+                    }
                 }
         }
         __syncwarp();
@@ -199,21 +259,53 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv3x3_shift_kernel(const
     }
     tc_fence_before();
     __syncthreads();
+    if (MC) cluster_sync_all();  // nobody leaves while the peer could still address this CTA's shared memory
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)(2 * BN)));
 }
 
 bool conv_shift_applicable(const ConvGemmArgs &a, int ksize, int valid) {
-    return ksize == 3 && valid && a.dil == 1 && 2 * a.W + 2 <= CS_WIN - CS_BN && a.H >= 3 && a.W >= 3 && a.Cin % CG_BK == 0 && a.Cout % CG_BM == 0;
+    return ksize == 3 && valid && a.dil == 1 && 2 * a.W + 2 <= 256 - CS_BN && a.H >= 3 && a.W >= 3 && a.Cin % CG_BK == 0 && a.Cout % CG_BM == 0;
+}
+
+int g_conv_shift_multicast = 0;  // hdn_conv_gemm_set_shift(2): weight records multicast across a 2-CTA cluster -- built, correct, and measured
+                                 // SLOWER than every CTA loading its own (16.1 vs 14.2 ms for the fused chain): the per-block handshake couples
+                                 // the two CTAs' pipelines and L2 bandwidth was not the limit.  Kept as an A/B switch.
+
+template <int WIN, int ASTAGES>
+static int launch_conv_shift_cfg(const ConvGemmArgs &a, int nprob, cudaStream_t st) {
+    constexpr size_t SMEM = CSCfg<WIN, ASTAGES>::SMEM;
+    static DeviceOnce once;
+    if (int e = once.run([] {
+            cudaError_t e1 = cudaFuncSetAttribute(conv3x3_shift_kernel<false, WIN, ASTAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+            return e1 != cudaSuccess ? e1 : cudaFuncSetAttribute(conv3x3_shift_kernel<true, WIN, ASTAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+        }))
+        return e;
+    const int nq = (a.Ho - 1) * a.W + a.Wo;  // outputs on the input-width grid (the last row stops at its last valid column)
+    const int tiles = (nq + CS_BN - 1) / CS_BN;
+    if (!g_conv_shift_multicast || tiles < 2) {
+        conv3x3_shift_kernel<false, WIN, ASTAGES><<<dim3(tiles, a.Cout / CG_BM, a.B * nprob), CG_THREADS + 64, SMEM, st>>>(a);
+    } else {  // clusters of two neighbouring pixel tiles (an odd tile count gets one idle partner that stores nothing)
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((tiles + 1) / 2 * 2, a.Cout / CG_BM, a.B * nprob);
+        cfg.blockDim = dim3(CG_THREADS + 64);
+        cfg.dynamicSmemBytes = SMEM;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, conv3x3_shift_kernel<true, WIN, ASTAGES>, a);
+        if (e != cudaSuccess) return (int)e;
+    }
+    count_launch();
+    return launch_status();
 }
 
 int launch_conv_shift(const ConvGemmArgs &a, int nprob, cudaStream_t st) {
-    static DeviceOnce once;
-    if (int e = once.run([] { return cudaFuncSetAttribute(conv3x3_shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CS_SMEM); })) return e;
-    const int nq = (a.Ho - 1) * a.W + a.Wo;  // outputs on the input-width grid (the last row stops at its last valid column)
-    dim3 grid((nq + CS_BN - 1) / CS_BN, a.Cout / CG_BM, a.B * nprob);
-    conv3x3_shift_kernel<<<grid, CG_THREADS + 64, CS_SMEM, st>>>(a);
-    count_launch();
-    return launch_status();
+    return 2 * a.W + 2 <= 192 - CS_BN ? launch_conv_shift_cfg<192, 4>(a, nprob, st) : launch_conv_shift_cfg<256, 3>(a, nprob, st);
 }
 
 }  // namespace hdn

@@ -403,9 +403,11 @@ def set_conv_splitk(enable=True):
     _lib.check(_lib.lib().hdn_conv_gemm_set_splitk(int(bool(enable))), "hdn_conv_gemm_set_splitk")
 
 
-def set_conv_shift(enable=True):
-    """3x3 'valid' layers on the shifted-window kernel (conv_shift.cu; default on); off = the generic implicit GEMM (A/B runs)."""
-    _lib.check(_lib.lib().hdn_conv_gemm_set_shift(int(bool(enable))), "hdn_conv_gemm_set_shift")
+def set_conv_shift(mode=True):
+    """3x3 'valid' layers on the shifted-window kernel (conv_shift.cu).  True / 1 (default): on; 2: on, with weight multicast
+    across 2-CTA clusters (correct, measured slower: A/B switch); False / 0: the generic implicit GEMM."""
+    mode = 1 if mode is True else int(mode)
+    _lib.check(_lib.lib().hdn_conv_gemm_set_shift(mode), "hdn_conv_gemm_set_shift")
 
 
 def conv_gemm_supported(Cin, Cout, ksize, dilation=1):

@@ -136,9 +136,10 @@ int hdn_conv_gemm_supported(int Cin, int Cout, int ksize, int dilation);
  * enable = 0 switches that off (A/B runs); default on. */
 int hdn_conv_gemm_set_splitk(int enable);
 /* 3x3 'valid' layers with W <= 63 (the heads' conv_search / conv_kernel) run a kernel that stages the activations once per
- * 32-channel block and feeds the nine taps as shifted windows of that tile (conv_shift.cu).  enable = 0: the generic implicit
- * GEMM instead (A/B runs); default on.  Same fp32-accurate 3xTF32 arithmetic either way. */
-int hdn_conv_gemm_set_shift(int enable);
+ * 32-channel block and feeds the nine taps as shifted windows of that tile (conv_shift.cu).  mode = 1 (default): on; 2: on, and
+ * clusters of two neighbouring pixel tiles share every weight record through TMA multicast (built and correct, measured slower:
+ * an A/B switch); 0: the generic implicit GEMM instead.  Same fp32-accurate 3xTF32 arithmetic in all three. */
+int hdn_conv_gemm_set_shift(int mode);
 int hdn_conv_pack_weight_f32(const float *wt, float *packed, int Cout, int Ktot, hdn_stream_t stream);
 int hdn_conv_gemm_f32(const float *x, const float *wpk, const float *scale, const float *shift, const float *residual, float *out, int B,
                       int Cin, int Cout, int H, int W, int ksize, int dilation, int valid, int relu, hdn_stream_t stream);
