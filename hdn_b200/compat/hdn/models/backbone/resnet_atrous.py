@@ -8,8 +8,8 @@ downsample.{0,1}), same geometry:
     `2 - stride` when undilated -- i.e. layer2's stride-2 3x3 has padding 0 (:68-80);
   * projection shortcuts are 1x1 only for layer1; every other stage uses a 3x3 (padding 0 at stride 2, else the
     halved dilation) (:150-173).
-The dense convolutions run on cuDNN / cuBLAS through torch (library GEMMs); the wide dilated 3x3
-layers go through hdn_b200.convs.dilated_conv3x3 (cuDNN has no fast fp32 kernel for them).
+Every 1x1 / 3x3 convolution (+ BatchNorm, residual, ReLU) with Cin % 32 == 0 and Cout % 64 == 0 -- all of layer1..layer4, strided
+and dilated alike -- is one fused tcgen05 launch (hdn_b200.convs.conv_bn_act); the 7x7 stem (3 input channels) stays on cuDNN.
 """
 import math
 
@@ -73,10 +73,9 @@ class BasicBlock(nn.Module):
         self.stride = stride
 
     def forward(self, x):
-        y = self.relu(self.bn1(self.conv1(x)))
-        y = self.bn2(self.conv2(y))
-        y += x if self.downsample is None else self.downsample(x)
-        return self.relu(y)
+        y = conv_bn_act(self.conv1, self.bn1, x, relu=True)
+        shortcut = x if self.downsample is None else conv_bn_act(self.downsample[0], self.downsample[1], x)
+        return conv_bn_act(self.conv2, self.bn2, y, residual=shortcut, relu=True)
 
 
 class ResNet(nn.Module):

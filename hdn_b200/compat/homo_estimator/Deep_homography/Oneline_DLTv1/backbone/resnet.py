@@ -24,7 +24,7 @@ class BasicBlock(nn.Module):
 
     def forward(self, x):
         y = conv_bn_act(self.conv1, self.bn1, x, relu=True)
-        shortcut = x if self.downsample is None else self.downsample(x)
+        shortcut = x if self.downsample is None else conv_bn_act(self.downsample[0], self.downsample[1], x)  # 1x1 stride-2 projection
         return conv_bn_act(self.conv2, self.bn2, y, residual=shortcut, relu=True)
 
 
@@ -44,11 +44,10 @@ class Bottleneck(nn.Module):
         self.stride = stride
 
     def forward(self, x):
-        y = self.relu(self.bn1(self.conv1(x)))
-        y = self.relu(self.bn2(self.conv2(y)))
-        y = self.bn3(self.conv3(y))
-        y += x if self.downsample is None else self.downsample(x)
-        return self.relu(y)
+        y = conv_bn_act(self.conv1, self.bn1, x, relu=True)
+        y = conv_bn_act(self.conv2, self.bn2, y, relu=True)
+        shortcut = x if self.downsample is None else conv_bn_act(self.downsample[0], self.downsample[1], x)
+        return conv_bn_act(self.conv3, self.bn3, y, residual=shortcut, relu=True)
 
 
 class ResNet(nn.Module):

@@ -70,22 +70,23 @@ def _folded(conv, bn):
 
 
 def tensor_core_eligible(conv, x):
-    """The tcgen05 3xTF32 kernel covers stride-1 1x1 and 3x3 ('same' or 'valid') convolutions with Cin % 32 == 0, Cout % 128 == 0."""
+    """The tcgen05 3xTF32 kernels cover 1x1 and 3x3 convolutions with stride 1 or 2, zero padding 0 <= p <= dilation * (k // 2),
+    Cin % 32 == 0 and Cout % 64 == 0 -- every convolution of the two ResNets and the heads except the 7x7 stems."""
     k = conv.kernel_size[0]
-    return (x.is_cuda and x.dtype == torch.float32 and conv.kernel_size[0] == conv.kernel_size[1] and k in (1, 3) and conv.stride == (1, 1)
-            and conv.groups == 1 and conv.bias is None and conv.dilation[0] == conv.dilation[1]
-            and conv.padding in ((conv.dilation[0] * (k // 2),) * 2, (0, 0)) and conv.in_channels % 32 == 0 and conv.out_channels % 128 == 0
-            and not torch.is_grad_enabled())
+    return (x.is_cuda and x.dtype == torch.float32 and conv.kernel_size[0] == conv.kernel_size[1] and k in (1, 3) and conv.stride in ((1, 1), (2, 2))
+            and conv.groups == 1 and conv.bias is None and conv.dilation[0] == conv.dilation[1] and conv.padding[0] == conv.padding[1]
+            and isinstance(conv.padding[0], int) and 0 <= conv.padding[0] <= conv.dilation[0] * (k // 2) and conv.padding_mode == "zeros"
+            and conv.in_channels % 32 == 0 and conv.out_channels % 64 == 0 and not torch.is_grad_enabled())
 
 
 def conv_bn_act(conv, bn, x, residual=None, relu=False):
     """relu?(bn(conv(x)) + residual?) for an eval-mode block.  Eligible layers run as ONE tcgen05 launch (implicit GEMM, fp32-accurate
-    3xTF32, BatchNorm / residual / ReLU in the epilogue: hdn_conv_gemm_f32); the rest fall back to cuDNN / the shifted-GEMM path."""
+    3xTF32, BatchNorm / residual / ReLU in the epilogue: hdn_conv_gemm_ex_f32); the rest fall back to cuDNN / the shifted-GEMM path."""
     if USE_TENSOR_CORES and not bn.training and tensor_core_eligible(conv, x):
         from hdn_b200 import ops
         wt, scale, shift = _folded(conv, bn)
         return ops.conv_gemm(x, wt, scale, shift, residual, ksize=conv.kernel_size[0], dilation=conv.dilation[0], relu=relu,
-                             valid=conv.kernel_size[0] == 3 and conv.padding == (0, 0))
+                             stride=conv.stride[0], padding=conv.padding[0], cout=conv.out_channels)
     y = bn(conv3x3(conv, x))
     if residual is not None:
         y = y + residual

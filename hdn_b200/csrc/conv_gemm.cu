@@ -132,7 +132,8 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(co
         constexpr int NBJ = BN / 32;
         const int bn = tid % BN;
         const int bp = pix0 + bn;
-        const int b_r = bp < HWo ? bp / a.Wo + a.off : -(1 << 20), b_c = bp < HWo ? bp - (bp / a.Wo) * a.Wo + a.off : 0;  // beyond the tile: never valid
+        const int b_r = bp < HWo ? (bp / a.Wo) * a.stride + a.off : -(1 << 20);  // beyond the tile: never valid
+        const int b_c = bp < HWo ? (bp - (bp / a.Wo) * a.Wo) * a.stride + a.off : 0;
 
         // fp32 register accumulator of this thread's share of the tile: TMEM lane (= channel) row, columns [col_lo, col_lo + BN/2)
         constexpr int HALF = BN / 2;
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(co
         // tap shift), advanced incrementally (no division), toff = 16 per-thread element offsets fixed for the whole kernel.
         unsigned toff[NBJ][4];
         {
-            const unsigned pix_off = bp < HWo ? (unsigned)(b_r * a.W + b_c) : 0u;
+            const unsigned pix_off = bp < HWo ? (unsigned)(b_r * a.W + b_c) : 0u;  // off >= 0 (pad <= (ksize/2)*dil): never negative
 #pragma unroll
             for (int j = 0; j < NBJ; ++j)
 #pragma unroll
@@ -257,8 +258,9 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(co
         // ---- epilogue: remaining chunks -> registers -> BN / residual / ReLU -> global NCHW ----
         while (drained < nchunks) drain(drained++);
         const int co = co0 + row;
+        const bool co_ok = co < a.Cout;  // Cout = 64 layers run in a zero-padded 128-row tile
         const float *scp = a.scale[prob], *shp = a.shift[prob], *resp = a.residual[prob];
-        const float sc = scp ? __ldg(scp + co) : 1.f, sh = shp ? __ldg(shp + co) : 0.f;
+        const float sc = scp && co_ok ? __ldg(scp + co) : 1.f, sh = shp && co_ok ? __ldg(shp + co) : 0.f;
         const size_t obase = ((size_t)img * a.Cout + co) * HWo;
         if (!PROJECT) {
             // A thread owns one CHANNEL row of the tile, so direct stores would touch 32 different lines per warp instruction.
@@ -278,7 +280,7 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(co
 #pragma unroll 4
             for (int i = tid; i < CG_BM * BN; i += CG_THREADS) {
                 const int r = i / BN, c = i - r * BN, p = pix0 + c;
-                if (p < HWo) {
+                if (p < HWo && co0 + r < a.Cout) {
                     float y = ys[r * YP + c];
                     if (resp) y += __ldg(resp + tile_base + (size_t)r * HWo + p);
                     if (a.relu) y = fmaxf(y, 0.f);
@@ -329,7 +331,7 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(co
             const uint32_t ys_s = smem_u32(ys);
             for (int i = tid; i < CG_BM * BN; i += CG_THREADS + 64) {
                 const int r = i / BN, c = i - r * BN, p = pix0 + c;
-                if (p < HWo) {
+                if (p < HWo && co0 + r < a.Cout) {
                     float acc = ys[r * YP + c];
                     for (int peer = 1; peer < S; ++peer) {
                         uint32_t remote;
@@ -361,7 +363,7 @@ static int launch_conv_gemm(const ConvGemmArgs &a, int nprob, cudaStream_t st) {
     if (int e = once.run([] { return cudaFuncSetAttribute(conv_gemm_tf32x3_kernel<BN, STAGES, RAW, PROJECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM); }))
         return e;
     const int S = a.splitk > 1 ? a.splitk : 1;
-    dim3 grid((a.Ho * a.Wo + BN - 1) / BN * S, a.Cout / CG_BM, a.B * nprob);
+    dim3 grid((a.Ho * a.Wo + BN - 1) / BN * S, (a.Cout + CG_BM - 1) / CG_BM, a.B * nprob);
     if (S == 1) {
         conv_gemm_tf32x3_kernel<BN, STAGES, RAW, PROJECT><<<grid, CG_THREADS + 64, SMEM, st>>>(a);
     } else {  // a cluster of S CTAs along x per output tile
@@ -387,7 +389,8 @@ static int launch_conv_gemm(const ConvGemmArgs &a, int nprob, cudaStream_t st) {
 // Weights -> per (128-channel tile, 32-deep K block) records of [hi | lo] x [k/4 (8)][row/8 (16)][row%8 (8)][k%4 (4)] floats:
 // exactly the bytes a stage's A region holds, so the kernel moves a block's A operand with one bulk copy.
 __global__ void conv_pack_weight_kernel(const float *__restrict__ wt, float *__restrict__ out, int Cout, int Ktot) {
-    const long long total = (long long)Cout * Ktot;
+    const int rows = (Cout + CG_BM - 1) / CG_BM * CG_BM;  // a 64-wide layer is packed into a zero-padded 128-row tile
+    const long long total = (long long)rows * Ktot;
     const int nkb = Ktot / CG_BK;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int co = (int)(i / Ktot), k = (int)(i - (long long)co * Ktot);
@@ -395,7 +398,7 @@ __global__ void conv_pack_weight_kernel(const float *__restrict__ wt, float *__r
         const long long rec = ((long long)mt * nkb + kb) * (2 * CG_BM * CG_BK);
         const int off = (kk >> 2) * (CG_BM * 4) + (row >> 3) * 32 + (row & 7) * 4 + (kk & 3);
         float hi, lo;
-        split_tf32(wt[i], hi, lo);
+        split_tf32(co < Cout ? wt[i] : 0.f, hi, lo);
         out[rec + off] = hi;
         out[rec + CG_BM * CG_BK + off] = lo;
     }
@@ -407,7 +410,7 @@ using namespace hdn;
 
 extern "C" int hdn_conv_pack_weight_f32(const float *wt, float *packed, int Cout, int Ktot, hdn_stream_t stream) {
     if (!wt || !packed) return HDN_ERR_NULL;
-    if (Cout < CG_BM || Cout % CG_BM || Ktot < CG_BK || Ktot % CG_BK) return HDN_ERR_SHAPE;
+    if (Cout < 64 || Cout % 64 || Ktot < CG_BK || Ktot % CG_BK) return HDN_ERR_SHAPE;
     if (reinterpret_cast<uintptr_t>(packed) & 15u) return HDN_ERR_ALIGN;
     conv_pack_weight_kernel<<<sm_count() * 4, 256, 0, (cudaStream_t)stream>>>(wt, packed, Cout, Ktot);
     count_launch();
@@ -415,7 +418,7 @@ extern "C" int hdn_conv_pack_weight_f32(const float *wt, float *packed, int Cout
 }
 
 extern "C" int hdn_conv_gemm_supported(int Cin, int Cout, int ksize, int dilation) {
-    return (Cin >= 32 && Cin % 32 == 0 && Cout % CG_BM == 0 && (ksize == 1 || ksize == 3) && dilation >= 1) ? 1 : 0;
+    return (Cin >= 32 && Cin % 32 == 0 && Cout >= 64 && Cout % 64 == 0 && (ksize == 1 || ksize == 3) && dilation >= 1) ? 1 : 0;
 }
 
 static int g_conv_splitk = 1;  // hdn_conv_gemm_set_splitk (A/B switch; the result is deterministic either way)
@@ -423,13 +426,16 @@ static int g_conv_shift = 1;   // hdn_conv_gemm_set_shift: conv_shift.cu for 3x3
 
 static int conv_gemm_multi(int n, const float *const *x, const float *const *wpk, const float *const *scale, const float *const *shift,
                            const float *const *residual, const float *const *w2, float *const *out, int B, int Cin, int Cout, int H, int W,
-                           int ksize, int dilation, int valid, int relu, int L, cudaStream_t st) {
+                           int ksize, int dilation, int valid, int relu, int L, cudaStream_t st, int stride = 1, int pad = -1) {
     if (!x || !wpk || !out) return HDN_ERR_NULL;
     if (n < 1 || n > HDN_MAX_PROBLEMS) return HDN_ERR_UNSUPPORTED;
     if (B < 1 || H < 1 || W < 1 || (long long)B * n > 65535) return HDN_ERR_SHAPE;
     if (!hdn_conv_gemm_supported(Cin, Cout, ksize, dilation)) return HDN_ERR_UNSUPPORTED;
-    const int shrink = (valid && ksize == 3) ? 2 * dilation : 0;
-    if (H - shrink < 1 || W - shrink < 1) return HDN_ERR_SHAPE;
+    if (pad < 0) pad = valid ? 0 : dilation * (ksize / 2);  // the two geometries of hdn_conv_gemm_f32
+    if ((stride != 1 && stride != 2) || pad > dilation * (ksize / 2)) return HDN_ERR_UNSUPPORTED;
+    valid = (pad == 0 && stride == 1) ? 1 : 0;
+    const int Ho_ = (H + 2 * pad - dilation * (ksize - 1) - 1) / stride + 1, Wo_ = (W + 2 * pad - dilation * (ksize - 1) - 1) / stride + 1;
+    if (Ho_ < 1 || Wo_ < 1) return HDN_ERR_SHAPE;
     ConvGemmArgs a{};
     for (int i = 0; i < n; ++i) {
         if (!x[i] || !wpk[i] || !out[i] || (w2 && !w2[i])) return HDN_ERR_NULL;
@@ -444,18 +450,19 @@ static int conv_gemm_multi(int n, const float *const *x, const float *const *wpk
     }
     a.B = B; a.L = L; a.splitk = 1;
     a.Cin = Cin; a.Cout = Cout; a.H = H; a.W = W; a.taps = ksize * ksize; a.dil = dilation; a.relu = relu;
-    a.Ho = H - shrink; a.Wo = W - shrink; a.off = shrink / 2;
+    a.Ho = Ho_; a.Wo = Wo_; a.off = (ksize / 2) * dilation - pad; a.stride = stride;
     // 3x3 'valid' layers (the heads' conv_search / conv_kernel): activations staged once per channel block, taps = shifted windows
     if (!w2 && g_conv_shift && conv_shift_applicable(a, ksize, valid)) return launch_conv_shift(a, n, st);
     if (w2) {  // fused second 1x1: narrow pixel tiles (the projection's staging pitch), L <= 8
         if (L < 1 || L > 8) return HDN_ERR_UNSUPPORTED;
         return launch_conv_gemm<64, 4, 0, true>(a, n, st);
     }
-    const long long tiles128 = (long long)((a.Ho * a.Wo + 127) / 128) * (Cout / CG_BM) * B * n;
+    const int mtiles = (Cout + CG_BM - 1) / CG_BM;
+    const long long tiles128 = (long long)((a.Ho * a.Wo + 127) / 128) * mtiles * B * n;
     // small problems (tracking batch sizes): narrower pixel tiles put more CTAs on the 148 SMs ...
     if (tiles128 >= 2 * sm_count()) return launch_conv_gemm<128, 3, 0>(a, n, st);
     // ... and when even those leave most SMs idle (a 15x15 or 31x31 map at batch 1), K is split over a cluster of 2 / 4 / 8 CTAs
-    const long long ctas = (long long)((a.Ho * a.Wo + 63) / 64) * (Cout / CG_BM) * B * n;
+    const long long ctas = (long long)((a.Ho * a.Wo + 63) / 64) * mtiles * B * n;
     const int nkb = a.taps * Cin / CG_BK;
     int split = 1;
     if (g_conv_splitk != 0)
@@ -470,6 +477,15 @@ extern "C" int hdn_conv_gemm_f32(const float *x, const float *wpk, const float *
     if (!x || !wpk || !out) return HDN_ERR_NULL;
     return conv_gemm_multi(1, &x, &wpk, &scale, &shift, &residual, nullptr, &out, B, Cin, Cout, H, W, ksize, dilation, valid, relu, 0,
                            (cudaStream_t)stream);
+}
+
+extern "C" int hdn_conv_gemm_ex_f32(const float *x, const float *wpk, const float *scale, const float *shift, const float *residual, float *out,
+                                    int B, int Cin, int Cout, int H, int W, int ksize, int stride, int pad, int dilation, int relu,
+                                    hdn_stream_t stream) {
+    if (!x || !wpk || !out) return HDN_ERR_NULL;
+    if (pad < 0) return HDN_ERR_SHAPE;
+    return conv_gemm_multi(1, &x, &wpk, &scale, &shift, &residual, nullptr, &out, B, Cin, Cout, H, W, ksize, dilation, 0, relu, 0,
+                           (cudaStream_t)stream, stride, pad);
 }
 
 extern "C" int hdn_conv_gemm_multi_f32(int n, const float *const *x_host, const float *const *wpk_host, const float *const *scale_host,

@@ -264,7 +264,8 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv3x3_shift_kernel(const
 }
 
 bool conv_shift_applicable(const ConvGemmArgs &a, int ksize, int valid) {
-    return ksize == 3 && valid && a.dil == 1 && 2 * a.W + 2 <= 256 - CS_BN && a.H >= 3 && a.W >= 3 && a.Cin % CG_BK == 0 && a.Cout % CG_BM == 0;
+    return ksize == 3 && valid && a.stride == 1 && a.dil == 1 && 2 * a.W + 2 <= 256 - CS_BN && a.H >= 3 && a.W >= 3 && a.Cin % CG_BK == 0 &&
+           a.Cout % CG_BM == 0;
 }
 
 int g_conv_shift_multicast = 0;  // hdn_conv_gemm_set_shift(2): weight records multicast across a 2-CTA cluster -- built, correct, and measured

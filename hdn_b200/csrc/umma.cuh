@@ -61,7 +61,9 @@ struct ConvGemmArgs {
     int B, L;
     int splitk;  // > 1: a cluster of `splitk` CTAs shares one output tile, each taking 1/splitk of K (blockIdx.x = tile * splitk + rank)
     int Cin, Cout, H, W, taps, dil, relu;
-    int Ho, Wo, off;  // output extent and the input offset of output pixel (0,0): 'same' -> (H, W, 0); 'valid' 3x3 -> (H-2d, W-2d, d)
+    int Ho, Wo, off;  // output extent; input pixel of output (r, c) under the CENTRE tap = (r * stride + off, c * stride + off):
+                      // off = (ksize / 2) * dil - pad   ('same' 3x3: 0; 'valid' 3x3: d; 1x1: -pad)
+    int stride;       // 1 or 2
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {

@@ -307,22 +307,31 @@ def score_argmax_host(cls, loc, window=None, win_influence=0.0):
     return unpack_scores(buf.cpu().numpy(), cls.shape[0], loc.shape[1])
 
 
-def conv_gemm(x, wpk, scale=None, shift=None, residual=None, ksize=1, dilation=1, relu=False, out=None, valid=False):
-    """Stride-1 1x1 / 3x3 (padding = dilation) convolution + folded BatchNorm (+ residual) (+ ReLU) on tcgen05 (3xTF32).
-    x [B,Cin,H,W]; wpk = pack_conv_weight(weight) (done once per layer); scale/shift [Cout]."""
+def conv_gemm(x, wpk, scale=None, shift=None, residual=None, ksize=1, dilation=1, relu=False, out=None, valid=False, stride=1, padding=None,
+              cout=None):
+    """1x1 / 3x3 convolution + folded BatchNorm (+ residual) (+ ReLU) on tcgen05 (3xTF32, fp32-accurate).
+    x [B,Cin,H,W]; wpk = pack_conv_weight(weight) (done once per layer); scale/shift [Cout].
+    Geometry: stride 1 | 2; padding None = 'same' (dilation * (ksize // 2)) or 0 when `valid`; else 0 <= padding <= dilation * (ksize // 2).
+    cout: the layer's output channels when they are not a multiple of 128 (the packed weight is padded to 128-row tiles)."""
     x, wpk = _dev(x, "x"), _dev(wpk, "wpk")
     B, Cin, H, W = x.shape
-    Cout = wpk.numel() // (2 * ksize * ksize * Cin)
-    if wpk.numel() != 2 * Cout * ksize * ksize * Cin:
+    rows = wpk.numel() // (2 * ksize * ksize * Cin)
+    if wpk.numel() != 2 * rows * ksize * ksize * Cin or rows % 128:
         raise RuntimeError("conv_gemm: packed weight of %d floats does not match Cin=%d, ksize=%d" % (wpk.numel(), Cin, ksize))
-    shrink = 2 * dilation if (valid and ksize == 3) else 0
-    out = _out(out, (B, Cout, H - shrink, W - shrink), x)
+    Cout = rows if cout is None else int(cout)
+    if not (rows - 128 < Cout <= rows):
+        raise RuntimeError("conv_gemm: cout=%d does not fit the packed weight (%d rows)" % (Cout, rows))
+    pad = (0 if valid else dilation * (ksize // 2)) if padding is None else int(padding)
+    Ho = (H + 2 * pad - dilation * (ksize - 1) - 1) // stride + 1
+    Wo = (W + 2 * pad - dilation * (ksize - 1) - 1) // stride + 1
+    out = _out(out, (B, Cout, Ho, Wo), x)
     opt = lambda t, n: _ptr(_dev(t, n)) if t is not None else None  # noqa: E731
     if residual is not None and tuple(residual.shape) != tuple(out.shape):
         raise RuntimeError("conv_gemm: residual shape mismatch")
-    st = _lib.lib().hdn_conv_gemm_f32(_ptr(x), _ptr(wpk), opt(scale, "scale"), opt(shift, "shift"), opt(residual, "residual"), _ptr(out), B, Cin,
-                                      Cout, H, W, ksize, dilation, int(bool(valid)), int(bool(relu)), _stream())
-    _lib.check(st, "hdn_conv_gemm_f32")
+    with _on_device(x):
+        st = _lib.lib().hdn_conv_gemm_ex_f32(_ptr(x), _ptr(wpk), opt(scale, "scale"), opt(shift, "shift"), opt(residual, "residual"), _ptr(out), B, Cin,
+                                             Cout, H, W, ksize, int(stride), pad, dilation, int(bool(relu)), _stream())
+    _lib.check(st, "hdn_conv_gemm_ex_f32")
     return out
 
 
@@ -415,9 +424,10 @@ def conv_gemm_supported(Cin, Cout, ksize, dilation=1):
 
 
 def pack_conv_weight(weight):
-    """[Cout,Cin,k,k] conv weight -> the tensor-core record format of hdn_conv_pack_weight_f32 (2*Cout*k*k*Cin floats):
-    tap-major K (K index = tap*Cin + ci), TF32 hi / lo halves, tiled per 128-channel x 32-deep K block."""
+    """[Cout,Cin,k,k] conv weight -> the tensor-core record format of hdn_conv_pack_weight_f32 (2*R*k*k*Cin floats, R = Cout rounded
+    up to 128): tap-major K (K index = tap*Cin + ci), TF32 hi / lo halves, tiled per 128-channel x 32-deep K block."""
     wt = _dev(weight.detach().permute(0, 2, 3, 1).reshape(weight.shape[0], -1), "weight")
-    packed = torch.empty(2 * wt.numel(), device=wt.device, dtype=torch.float32)
+    rows = (wt.shape[0] + 127) // 128 * 128
+    packed = torch.empty(2 * rows * wt.shape[1], device=wt.device, dtype=torch.float32)
     _lib.check(_lib.lib().hdn_conv_pack_weight_f32(_ptr(wt), _ptr(packed), wt.shape[0], wt.shape[1], _stream()), "hdn_conv_pack_weight_f32")
     return packed

@@ -127,10 +127,16 @@ int hdn_score_argmax_f32(const float *cls, const float *loc, const double *windo
  * and hdn/models/neck/neck.py:11-29.
  *   x [B,Cin,H,W];  wpk = the weight packed ONCE by hdn_conv_pack_weight_f32;  scale/shift [Cout] or NULL
  *   (y = conv*scale + shift, the folded BatchNorm);  residual [B,Cout,Ho,Wo] or NULL;  out [B,Cout,Ho,Wo].
- * Requires hdn_conv_gemm_supported(): Cin % 32 == 0, Cout % 128 == 0, ksize in {1,3}.
- * hdn_conv_pack_weight_f32: wt [Cout, Ktot = ksize*ksize*Cin] tap-major (weight.permute(0,2,3,1)) -> packed [2*Cout*Ktot]
- *   floats (TF32 hi / lo halves, tiled per 128-channel x 32-deep block in the tensor core's shared-memory layout). */
+ * Requires hdn_conv_gemm_supported(): Cin % 32 == 0, Cout % 64 == 0, ksize in {1,3}.
+ * hdn_conv_pack_weight_f32: wt [Cout, Ktot = ksize*ksize*Cin] tap-major (weight.permute(0,2,3,1)) -> packed [2*R*Ktot] floats,
+ *   R = Cout rounded up to 128 (a 64-wide layer runs in a zero-padded 128-row tile): TF32 hi / lo halves, tiled per 128-channel x
+ *   32-deep block in the tensor core's shared-memory layout.
+ * hdn_conv_gemm_ex_f32: the same kernel with explicit stride (1 | 2) and zero padding (0 <= pad <= dilation * (ksize / 2)) -- the
+ *   stride-2 3x3 / 1x1 layers of the ResNet stages (hdn/models/backbone/resnet_atrous.py:62-110,169-173; the homography estimator's
+ *   ResNet-34, Oneline_DLTv1/backbone/resnet.py:65-194).  out [B,Cout,Ho,Wo], Ho = (H + 2*pad - dilation*(ksize-1) - 1) / stride + 1. */
 int hdn_conv_gemm_supported(int Cin, int Cout, int ksize, int dilation);
+int hdn_conv_gemm_ex_f32(const float *x, const float *wpk, const float *scale, const float *shift, const float *residual, float *out, int B,
+                         int Cin, int Cout, int H, int W, int ksize, int stride, int pad, int dilation, int relu, hdn_stream_t stream);
 /* Small problems (a 15x15 or 31x31 map at tracking batch sizes fills a fraction of the 148 SMs) split K over a thread-block
  * cluster of 2 / 4 / 8 CTAs whose fp32 partial tiles are added in rank order through distributed shared memory (deterministic).
  * enable = 0 switches that off (A/B runs); default on. */

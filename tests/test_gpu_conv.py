@@ -256,3 +256,51 @@ def test_conv3x3_valid_shifted_window_kernel(case):
     for i, xi in enumerate([0, 1, 1]):
         w64 = F.conv2d(xs[xi].double(), ws[i].double()) * sc[i].double().view(1, -1, 1, 1) + sh[i].double().view(1, -1, 1, 1)
         assert float((multi[i].double() - w64).abs().max()) / float(w64.abs().max()) < 1e-5, i
+
+
+STRIDED = [  # B, Cin, Cout, H, W, k, stride, pad, dil   -- the remaining layer geometries of the two ResNets
+    (2, 64, 64, 63, 63, 3, 1, 1, 1),      # ResNet-50 layer1 conv2 / ResNet-34 layer1: 64-wide, zero-padded 128-row tile
+    (2, 64, 256, 63, 63, 1, 1, 0, 1),     # layer1 conv3 / 1x1 projection
+    (1, 256, 64, 63, 63, 1, 1, 0, 1),     # layer1 conv1 of the later blocks
+    (2, 128, 128, 63, 63, 3, 2, 0, 1),    # ResNet-50 layer2 block 0: 3x3 stride 2, padding 0 (resnet_atrous.py:68-80)
+    (1, 256, 512, 63, 63, 3, 2, 0, 1),    # layer2 projection shortcut: 3x3 stride 2 padding 0
+    (3, 64, 128, 32, 32, 3, 2, 1, 1),     # ResNet-34 layer2 block 0: 3x3 stride 2 padding 1
+    (3, 64, 128, 32, 32, 1, 2, 0, 1),     # ResNet-34 1x1 stride-2 projection
+    (2, 256, 512, 8, 8, 3, 2, 1, 1),      # ResNet-34 layer4 block 0 (tiny maps: split-K)
+    (1, 128, 192, 17, 23, 3, 1, 1, 1),    # Cout = 192 (64-multiple, two tiles, the second half empty), non-square
+]
+
+
+@pytest.mark.parametrize("case", STRIDED)
+def test_conv_gemm_strides_paddings_and_64_wide_layers(case):
+    from hdn_b200 import ops
+    B, Cin, Cout, H, W, k, s, p, d = case
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(Cin + Cout * 3 + H + k + s)
+    x = torch.randn(B, Cin, H, W, device="cuda", generator=g) + 0.2
+    w = torch.randn(Cout, Cin, k, k, device="cuda", generator=g) * (2.0 / (Cin * k * k)) ** 0.5
+    scale = 1 + 0.1 * torch.randn(Cout, device="cuda", generator=g)
+    shift = 0.1 * torch.randn(Cout, device="cuda", generator=g)
+    want = F.conv2d(x.double(), w.double(), stride=s, padding=p, dilation=d) * scale.double().view(1, -1, 1, 1) + shift.double().view(1, -1, 1, 1)
+    res = torch.randn(want.shape, device="cuda", generator=g)
+    want = F.relu(want + res.double())
+    got = ops.conv_gemm(x, ops.pack_conv_weight(w), scale, shift, res, ksize=k, dilation=d, relu=True, stride=s, padding=p, cout=Cout)
+    assert tuple(got.shape) == tuple(want.shape)
+    den = float(want.abs().max())
+    err = float((got.double() - want).abs().max()) / den
+    lib = F.relu(F.conv2d(x, w, stride=s, padding=p, dilation=d) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1) + res)
+    err_lib = float((lib.double() - want).abs().max()) / den
+    assert err < 1e-5 and err < 8 * max(err_lib, 3e-7), (err, err_lib)
+
+
+def test_every_resnet_layer_but_the_stems_runs_on_tcgen05():
+    """After this round only the two 7x7 stems (3 / 2 input channels) and the 1->4->8->1 ShareFeature convolutions are left to cuDNN."""
+    from hdn_b200 import compat, convs
+    compat.activate()
+    from hdn.models.backbone.resnet_atrous import resnet50
+    from homo_estimator.Deep_homography.Oneline_DLTv1.backbone.resnet import resnet34
+    x = torch.zeros(1, 64, 8, 8, device="cuda")
+    with torch.no_grad():
+        for net, stem in ((resnet50(used_layers=[2, 3, 4]), "conv1"), (resnet34(used_layers=[4]), "conv1")):
+            left = [n for n, m in net.named_modules() if isinstance(m, torch.nn.Conv2d) and not convs.tensor_core_eligible(m, x)]
+            assert left == [stem], left

@@ -269,14 +269,25 @@ def test_sanitizer_smoke_shapes():
 
 
 def test_lockstep_batch_equals_single_sequence_tracking():
-    """4 sequences advanced in lock-step (one batched network call per stage) == each tracked alone, within fp32 noise."""
+    """4 sequences advanced in lock-step (one batched network call per stage) == each tracked alone.  Every kernel computes a pair's
+    outputs in the same order whatever the batch size -- except that batch-1 convolutions split K over a cluster (another fp32
+    summation order), and the free-running tracker of UNTRAINED weights turns a last-bit difference at a near-tie of the arg-max
+    into pixels.  So: split-K off -> the trajectories must agree within fp32 noise over all frames; split-K on -> on the first frame."""
     import synth
     from hdn.tracker.tracker_builder import build_tracker
-    from hdn_b200 import runner
+    from hdn_b200 import ops, runner
     model, _ = build_model()
     seqs = [synth.sequence(30 + s, 5) for s in range(4)]
-    polys, _ = runner.track_lockstep(model, seqs)
     diag = float(np.hypot(*seqs[0][0][0].shape[:2]))
+    try:
+        ops.set_conv_splitk(False)
+        polys, _ = runner.track_lockstep(model, seqs)
+        for s, (frames, gt) in enumerate(seqs):
+            alone, _ = runner.track_sequence(build_tracker(model), frames, gt)
+            assert np.abs(polys[s] - alone).max() <= 1e-3 * diag, s
+    finally:
+        ops.set_conv_splitk(True)
+    polys, _ = runner.track_lockstep(model, seqs)
     for s, (frames, gt) in enumerate(seqs):
         alone, _ = runner.track_sequence(build_tracker(model), frames, gt)
-        assert np.abs(polys[s] - alone).max() <= 1e-3 * diag, s
+        assert np.abs(polys[s][:1] - alone[:1]).max() <= 1e-3 * diag, s
