@@ -39,6 +39,8 @@ SIGNATURES = {
     "hdn_cubic_table_host": (_ci, [_vp]),
     "hdn_warp_affine_cubic_u8": (_ci, [_vp, _vp, _ci, _ci, ctypes.POINTER(_d), _vp, _vp]),
     "hdn_crop_resize_u8": (_ci, [_vp, _ci, _ci, _ci, _ci, _ci, ctypes.POINTER(ctypes.c_uint8), _ci, _ci, ctypes.POINTER(_d), ctypes.POINTER(_d), _vp, _vp]),
+    "hdn_conv_small_supported": (_ci, [_ci, _ci, _ci, _ci]),
+    "hdn_conv_small_f32": (_ci, [_vp] * 5 + [_ci] * 9 + [_vp]),
     "hdn_conv_gemm_ex_f32": (_ci, [_vp, _vp, _vp, _vp, _vp, _vp, _ci, _ci, _ci, _ci, _ci, _ci, _ci, _ci, _ci, _ci, _vp]),
     "hdn_conv_gemm_multi_f32": (_ci, [_ci] + [ctypes.POINTER(_vp)] * 5 + [_ci] * 9 + [_vp]),
     "hdn_head_project_multi_f32": (_ci, [_ci] + [ctypes.POINTER(_vp)] * 6 + [_ci] * 5 + [_vp]),

@@ -122,7 +122,7 @@ class ResNet(nn.Module):
         return nn.Sequential(*blocks)
 
     def forward(self, x):
-        stem = self.relu(self.bn1(self.conv1(x)))
+        stem = conv_bn_act(self.conv1, self.bn1, x, relu=True)
         feats = [stem]
         y = self.maxpool(stem)
         for idx in range(1, 5):

@@ -79,7 +79,7 @@ class ResNet(nn.Module):
         return nn.Sequential(*blocks)
 
     def forward(self, x):
-        y = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        y = self.maxpool(conv_bn_act(self.conv1, self.bn1, x, relu=True))
         feats = [y]
         for idx in range(1, 5):
             y = getattr(self, "layer%d" % idx)(y)

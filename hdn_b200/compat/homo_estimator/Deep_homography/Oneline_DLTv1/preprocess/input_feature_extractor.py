@@ -2,6 +2,8 @@
 layers (1 -> 4 -> 8 -> 1 channels, padding 1) applied to each gray patch before the homography trunk."""
 import torch.nn as nn
 
+from hdn_b200.convs import conv_bn_act
+
 
 class PreShareFeature(nn.Module):
     def __init__(self):
@@ -18,4 +20,8 @@ class PreShareFeature(nn.Module):
                 m.bias.data.zero_()
 
     def forward(self, x):
-        return self.ShareFeature(x)
+        # conv -> BatchNorm -> ReLU triples: one direct-sum launch each on the device (hdn_conv_small_f32), the modules themselves otherwise
+        layers = self.ShareFeature
+        for i in range(0, len(layers), 3):
+            x = conv_bn_act(layers[i], layers[i + 1], x, relu=True)
+        return x

@@ -79,14 +79,42 @@ def tensor_core_eligible(conv, x):
             and conv.in_channels % 32 == 0 and conv.out_channels % 64 == 0 and not torch.is_grad_enabled())
 
 
+def small_eligible(conv, x):
+    """The direct few-channel kernel (hdn_conv_small_f32): the 7x7 stride-2 stems and PreShareFeature's 3x3 layers."""
+    k = conv.kernel_size[0]
+    return (x.is_cuda and x.dtype == torch.float32 and conv.kernel_size[0] == conv.kernel_size[1] and conv.stride[0] == conv.stride[1]
+            and (k, conv.stride[0]) in ((7, 2), (3, 1)) and conv.groups == 1 and conv.bias is None and conv.dilation == (1, 1)
+            and conv.padding[0] == conv.padding[1] and isinstance(conv.padding[0], int) and 0 <= conv.padding[0] <= k // 2
+            and conv.padding_mode == "zeros" and conv.in_channels <= 8 and not torch.is_grad_enabled()
+            and ((k == 7 and conv.out_channels % 32 == 0) or (k == 3 and (conv.out_channels == 1 or conv.out_channels % 4 == 0))))
+
+
+def _folded_bn(conv, bn):
+    """(scale, shift) of an eval-mode BatchNorm, cached on the conv module like _folded."""
+    ver = (id(bn), bn.weight.data_ptr(), bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
+           bn.running_mean.data_ptr(), bn.running_var.data_ptr(), float(bn.eps))
+    hit = conv.__dict__.get("_hdn_folded_bn")
+    if hit is None or hit[0] != ver:
+        scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).detach().float().contiguous()
+        shift = (bn.bias - bn.running_mean * scale).detach().float().contiguous()
+        hit = (ver, scale, shift)
+        conv.__dict__["_hdn_folded_bn"] = hit
+    return hit[1:]
+
+
 def conv_bn_act(conv, bn, x, residual=None, relu=False):
     """relu?(bn(conv(x)) + residual?) for an eval-mode block.  Eligible layers run as ONE tcgen05 launch (implicit GEMM, fp32-accurate
-    3xTF32, BatchNorm / residual / ReLU in the epilogue: hdn_conv_gemm_ex_f32); the rest fall back to cuDNN / the shifted-GEMM path."""
+    3xTF32, BatchNorm / residual / ReLU in the epilogue: hdn_conv_gemm_ex_f32), the few-channel stems and PreShareFeature layers as one
+    direct-sum launch (hdn_conv_small_f32); anything else (training mode, CPU tensors, other shapes) falls back to cuDNN."""
     if USE_TENSOR_CORES and not bn.training and tensor_core_eligible(conv, x):
         from hdn_b200 import ops
         wt, scale, shift = _folded(conv, bn)
         return ops.conv_gemm(x, wt, scale, shift, residual, ksize=conv.kernel_size[0], dilation=conv.dilation[0], relu=relu,
                              stride=conv.stride[0], padding=conv.padding[0], cout=conv.out_channels)
+    if USE_TENSOR_CORES and not bn.training and residual is None and small_eligible(conv, x):
+        from hdn_b200 import ops
+        scale, shift = _folded_bn(conv, bn)
+        return ops.conv_small(x, conv.weight.detach(), scale, shift, stride=conv.stride[0], padding=conv.padding[0], relu=relu)
     y = bn(conv3x3(conv, x))
     if residual is not None:
         y = y + residual

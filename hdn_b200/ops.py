@@ -335,6 +335,28 @@ def conv_gemm(x, wpk, scale=None, shift=None, residual=None, ksize=1, dilation=1
     return out
 
 
+def conv_small(x, weight, scale=None, shift=None, stride=1, padding=0, relu=False, out=None):
+    """Few-channel convolution + folded BatchNorm (+ ReLU) as a direct fp32 sum (hdn_conv_small_f32): the 7x7 stride-2 stems and
+    PreShareFeature's 3x3 layers.  x [B,Cin<=8,H,W]; weight [Cout,Cin,k,k] as the module holds it."""
+    x, weight = _dev(x, "x"), _dev(weight, "weight")
+    B, Cin, H, W = x.shape
+    Cout, Cw, k, k2 = weight.shape
+    if Cw != Cin or k != k2:
+        raise RuntimeError("conv_small: weight %s does not match %d input channels" % (tuple(weight.shape), Cin))
+    Ho, Wo = (H + 2 * padding - k) // stride + 1, (W + 2 * padding - k) // stride + 1
+    out = _out(out, (B, Cout, Ho, Wo), x)
+    opt = lambda t, n: _ptr(_dev(t, n)) if t is not None else None  # noqa: E731
+    with _on_device(x):
+        st = _lib.lib().hdn_conv_small_f32(_ptr(x), _ptr(weight), opt(scale, "scale"), opt(shift, "shift"), _ptr(out), B, Cin, Cout, H, W, k,
+                                           int(stride), int(padding), int(bool(relu)), _stream())
+    _lib.check(st, "hdn_conv_small_f32")
+    return out
+
+
+def conv_small_supported(Cin, Cout, ksize, stride):
+    return bool(_lib.lib().hdn_conv_small_supported(Cin, Cout, ksize, stride))
+
+
 def _ptr_array(tensors):
     return (_vp * len(tensors))(*[t.data_ptr() if t is not None else None for t in tensors])
 

@@ -120,6 +120,16 @@ int hdn_dlt_warp_f32(const float *src4, const float *off4, const float *img, con
 int hdn_score_argmax_f32(const float *cls, const float *loc, const double *window, double win_influence, int64_t *idx, double *pscore,
                          float *score, float *gathered, int B, int L, int N, hdn_stream_t stream);
 
+/* Few-channel convolutions (K7c): the 7x7 stride-2 stems (3 -> 64 pad 0, hdn/models/backbone/resnet_atrous.py:121-131; 2 -> 64 pad 3,
+ * Oneline_DLTv1/backbone/resnet.py:142-160) and PreShareFeature's 3x3 stride-1 layers (1 -> 4 -> 8 -> 1, pad 1,
+ * Oneline_DLTv1/preprocess/input_feature_extractor.py:3-29) + eval-mode BatchNorm + optional ReLU as a direct fp32 FMA sum.
+ *   x [B,Cin,H,W];  w [Cout,Cin,k,k] (the module's own layout);  scale/shift [Cout] or NULL;  out [B,Cout,Ho,Wo],
+ *   Ho = (H + 2*pad - k) / stride + 1.  Supported: Cin <= 8 and (k,stride) = (7,2) with Cout % 32 == 0, or (3,1) with Cout == 1 or
+ *   Cout % 4 == 0;  0 <= pad <= k/2. */
+int hdn_conv_small_supported(int Cin, int Cout, int ksize, int stride);
+int hdn_conv_small_f32(const float *x, const float *w, const float *scale, const float *shift, float *out, int B, int Cin, int Cout, int H,
+                       int W, int ksize, int stride, int pad, int relu, hdn_stream_t stream);
+
 /* Backbone / neck / head convolution: stride-1 1x1 or 3x3 convolution (valid = 0: padding =
  * dilation, same-size output; valid = 1: no padding, output H-2d x W-2d) + eval-mode
  * BatchNorm + optional residual add + optional ReLU, as a 3xTF32 (fp32-accurate) implicit GEMM on tcgen05 / TMEM.

@@ -293,14 +293,80 @@ def test_conv_gemm_strides_paddings_and_64_wide_layers(case):
     assert err < 1e-5 and err < 8 * max(err_lib, 3e-7), (err, err_lib)
 
 
-def test_every_resnet_layer_but_the_stems_runs_on_tcgen05():
-    """After this round only the two 7x7 stems (3 / 2 input channels) and the 1->4->8->1 ShareFeature convolutions are left to cuDNN."""
+def test_every_convolution_of_the_path_runs_on_our_kernels():
+    """tcgen05 for every 1x1 / 3x3 layer of the two ResNets, the direct few-channel kernel for the 7x7 stems and ShareFeature: no cuDNN
+    convolution is left on the path."""
     from hdn_b200 import compat, convs
     compat.activate()
     from hdn.models.backbone.resnet_atrous import resnet50
     from homo_estimator.Deep_homography.Oneline_DLTv1.backbone.resnet import resnet34
+    from homo_estimator.Deep_homography.Oneline_DLTv1.preprocess.input_feature_extractor import PreShareFeature
     x = torch.zeros(1, 64, 8, 8, device="cuda")
     with torch.no_grad():
-        for net, stem in ((resnet50(used_layers=[2, 3, 4]), "conv1"), (resnet34(used_layers=[4]), "conv1")):
+        for net in (resnet50(used_layers=[2, 3, 4]), resnet34(used_layers=[4])):
             left = [n for n, m in net.named_modules() if isinstance(m, torch.nn.Conv2d) and not convs.tensor_core_eligible(m, x)]
-            assert left == [stem], left
+            assert left == ["conv1"], left
+            assert convs.small_eligible(net.conv1, x)
+        assert all(convs.small_eligible(m, x) for m in PreShareFeature().modules() if isinstance(m, torch.nn.Conv2d))
+
+
+@pytest.mark.parametrize("cin,cout,k,s,p,hw", [(3, 64, 7, 2, 0, (255, 255)), (3, 64, 7, 2, 0, (127, 127)), (2, 64, 7, 2, 3, (127, 127)),
+                                                (1, 4, 3, 1, 1, (127, 127)), (4, 8, 3, 1, 1, (127, 127)), (8, 1, 3, 1, 1, (127, 127)),
+                                                (3, 32, 7, 2, 3, (40, 77)), (5, 12, 3, 1, 0, (9, 35)), (8, 8, 3, 1, 1, (1, 1))])
+def test_conv_small_matches_torch(cin, cout, k, s, p, hw):
+    """hdn_conv_small_f32 (stems, ShareFeature) against torch's fp32 convolution + BatchNorm affine + ReLU; the sums have at most
+    8 * 49 terms, so the two orders agree to a few ulp of the accumulated magnitude."""
+    from hdn_b200 import ops
+    g = torch.Generator().manual_seed(cin * 100 + cout)
+    x = torch.randn(3, cin, *hw, generator=g).cuda()
+    w = torch.randn(cout, cin, k, k, generator=g).cuda() * 0.2
+    scale, shift = (torch.rand(cout, generator=g) + 0.5).cuda(), torch.randn(cout, generator=g).cuda()
+    torch.backends.cudnn.allow_tf32 = False
+    ref64 = torch.nn.functional.conv2d(x.double(), w.double(), stride=s, padding=p) * scale.double()[None, :, None, None] + shift.double()[None, :, None, None]
+    for relu in (True, False):
+        got = ops.conv_small(x, w, scale, shift, stride=s, padding=p, relu=relu)
+        want = torch.relu(ref64) if relu else ref64
+        assert got.shape == want.shape
+        err = (got.double() - want).abs().max().item()
+        assert err <= 2e-6 * max(1.0, ref64.abs().max().item()), err
+    plain = ops.conv_small(x, w, stride=s, padding=p)
+    ref = torch.nn.functional.conv2d(x.double(), w.double(), stride=s, padding=p)
+    assert (plain.double() - ref).abs().max().item() <= 2e-6 * max(1.0, ref.abs().max().item())
+
+
+def test_conv_small_rejects_what_it_does_not_cover():
+    from hdn_b200 import ops
+    x = torch.zeros(1, 16, 8, 8, device="cuda")
+    with pytest.raises((ValueError, RuntimeError)):
+        ops.conv_small(x, torch.zeros(4, 16, 3, 3, device="cuda"), padding=1)       # too many input channels
+    with pytest.raises((ValueError, RuntimeError)):
+        ops.conv_small(x[:, :3], torch.zeros(4, 3, 5, 5, device="cuda"), padding=1)   # 5x5
+    with pytest.raises((ValueError, RuntimeError)):
+        ops.conv_small(x[:, :3], torch.zeros(4, 3, 3, 3, device="cuda"), padding=2)   # padding beyond k // 2
+    assert not ops.conv_small_supported(3, 48, 7, 2) and ops.conv_small_supported(2, 64, 7, 2) and ops.conv_small_supported(8, 1, 3, 1)
+
+
+def test_share_feature_and_stems_equal_the_module_path():
+    """PreShareFeature.forward and the two stems through conv_bn_act == the plain nn.Module evaluation (cuDNN) of the same layers."""
+    from hdn_b200 import compat, convs, synthetic
+    compat.activate()
+    from hdn.models.backbone.resnet_atrous import resnet50
+    from homo_estimator.Deep_homography.Oneline_DLTv1.backbone.resnet import resnet34
+    from homo_estimator.Deep_homography.Oneline_DLTv1.preprocess.input_feature_extractor import PreShareFeature
+    torch.manual_seed(5)
+    torch.backends.cudnn.allow_tf32 = False
+    with torch.no_grad():
+        sf = PreShareFeature().cuda().eval()
+        for m in sf.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.3), m.running_var.uniform_(0.5, 2.0), m.weight.uniform_(0.5, 1.5), m.bias.normal_(0, 0.2)
+        x = torch.randn(2, 1, 127, 127, device="cuda")
+        got, want = sf(x), sf.ShareFeature(x)
+        assert (got - want).abs().max().item() <= 1e-5 * max(1.0, want.abs().max().item())
+        for net, xin in ((resnet50(used_layers=[2, 3, 4]), torch.randn(2, 3, 255, 255)), (resnet34(used_layers=[4]), torch.randn(2, 2, 127, 127))):
+            net = net.cuda().eval()
+            net.bn1.running_mean.normal_(0, 0.3), net.bn1.running_var.uniform_(0.5, 2.0)
+            xin = xin.cuda()
+            got = convs.conv_bn_act(net.conv1, net.bn1, xin, relu=True)
+            want = torch.relu(net.bn1(net.conv1(xin)))
+            assert got.shape == want.shape and (got - want).abs().max().item() <= 1e-5 * max(1.0, want.abs().max().item())
