@@ -59,7 +59,7 @@ def parse():
     ap.add_argument("--m2-batch", type=int, default=None, help="pairs per M2 step (default: --batch)")
     ap.add_argument("--no-traffic", action="store_true", help="skip the ncu dram-traffic measurement of the dominant kernel")
     ap.add_argument("--cpu-seconds", type=float, default=25.0, help="time budget of the cpu_baseline leg")
-    ap.add_argument("--xcorr-algo", default="auto", choices=["auto", "direct", "fft"], help="auto = FFT correlation where it beats the direct sum")
+    ap.add_argument("--xcorr-algo", default="auto", choices=["auto", "direct", "fft", "fft_phased", "fft_pipe", "fft_ws"], help="auto = FFT correlation where it beats the direct sum")
     ap.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)
     # --workload stream (config 4)
     ap.add_argument("--sequences", type=int, default=8)

@@ -40,7 +40,7 @@ struct XProblems {
     float *out[HDN_MAX_PROBLEMS];
 };
 // xcorr_fft.cu: FFT correlation for the FMA-bound shapes.  Returns HDN_ERR_UNSUPPORTED when the shape has no FFT kernel.
-int xcorr_fft_dispatch(const XProblems &P, int n, int B, int C, int Hx, int Wx, int Hk, int Wk, int circular, long long kbs, cudaStream_t st);
+int xcorr_fft_dispatch(const XProblems &P, int n, int B, int C, int Hx, int Wx, int Hk, int Wk, int circular, long long kbs, int variant, cudaStream_t st);
 bool xcorr_fft_applicable(int C, int Hx, int Wx, int Hk, int Wk, int circular);
 
 // ---- mbarrier + bulk async copy (TMA, 1-D) -------------------------------------------------
@@ -53,6 +53,9 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     // try_wait suspends the thread in hardware until the phase completes or the time hint expires; with the default (short)

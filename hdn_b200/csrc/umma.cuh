@@ -66,10 +66,6 @@ struct ConvGemmArgs {
     int stride;       // 1 or 2
 };
 
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
 // conv_shift.cu: 3x3 'valid' convolutions with the activations staged ONCE per channel block (9 shifted operand windows).
 bool conv_shift_applicable(const ConvGemmArgs &a, int ksize, int valid);
 int launch_conv_shift(const ConvGemmArgs &a, int nprob, cudaStream_t st);

@@ -589,7 +589,7 @@ static int xcorr_dispatch(const XProblems &P, int n, int B, int C, int Hx, int W
     fast = fast && (kbs == 0 || kbs == (long long)C * Hk * Wk);
     // FMA-bound shapes (29x29 / 15x15 templates): 64x64 FFT correlation, ~5x fewer instructions than the direct sum (xcorr_fft.cu)
     if (fast && fft_selected(C, Hx, Wx, Hk, Wk, circular))
-        return xcorr_fft_dispatch(P, n, B, C, Hx, Wx, Hk, Wk, circular, kbs, st);
+        return xcorr_fft_dispatch(P, n, B, C, Hx, Wx, Hk, Wk, circular, kbs, g_xcorr_algo >= HDN_XCORR_FFT_PHASED ? g_xcorr_algo - HDN_XCORR_FFT_PHASED + 1 : 0, st);
 #define HDN_TRY(CFG)                                                                                                               \
     if (fast && Hk == CFG::KH && Wk == CFG::KW && Hx == CFG::HX && Wx == CFG::WX && (circular != 0) == CFG::CIRC && C % CFG::G == 0) \
         return launch_staged<CFG>(P, n, B, C, kbs, st);
@@ -648,7 +648,7 @@ extern "C" int hdn_xcorr_dw_f32(const float *x, const float *k, float *out, int 
 }
 
 extern "C" int hdn_xcorr_set_algo(int algo) {
-    if (algo != HDN_XCORR_AUTO && algo != HDN_XCORR_DIRECT && algo != HDN_XCORR_FFT) return HDN_ERR_UNSUPPORTED;
+    if (algo < HDN_XCORR_AUTO || algo > HDN_XCORR_FFT_WS) return HDN_ERR_UNSUPPORTED;
     g_xcorr_algo = algo;
     return HDN_OK;
 }

@@ -94,6 +94,296 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::CTAS)
     }
 }
 
+// ---- software-pipelined variant ----------------------------------------------------------------------------------------------
+// The three-phase kernel above leaves warps at barriers: phase O has half as many FFT tasks as phase R (one complex inverse FFT
+// serves two planes), so half of the CTA idles through it, and every phase ends with the skew of its slowest warp (ncu: 1.0-1.2
+// barrier-stall cycles per issued instruction, the largest stall; 12 resident warps per SM).  Here the CTA has exactly as many warps
+// as phase R and phase O have FFT tasks TOGETHER (6 + 3 at 61x61, 4 + 2 at 29x29 circular and 39x39) and a group takes two rounds:
+//
+//     column round   COL(g)                      all warps (an odd warp out copies the finished tile of g-1 to global memory)
+//     FFT round      O(g)  ||  R(g+1)            inverse row FFTs of this group next to the row FFTs of the NEXT one
+//
+// so every warp runs one FFT task and one column task per group, there are two barriers per group instead of four, and 18
+// instead of 12 warps are resident per SM at 61x61.  Costs: the output tile no longer aliases the row spectra (R(g+1) writes them
+// while O(g) writes the tile; +8.7 KB) and the column stage is cut into 4 instead of 3 row segments per plane.
+template <class Cfg>
+struct PipeCfg {
+    static constexpr int RW = Cfg::R_TASKS / 32, OW = Cfg::O_TASKS / 32, NW = Cfg::NT / 32;
+    static_assert(RW + OW == NW, "a warp per FFT task of R and O together");
+    static_assert(Cfg::COL_TASKS <= Cfg::NT, "one column task per thread");
+    static constexpr int SPARE = Cfg::NT - Cfg::COL_TASKS;  // threads without a column task: they copy the previous tile out
+    static constexpr unsigned long long SMEM = Cfg::SMEM + (unsigned long long)Cfg::OUT_FLOATS * 4;
+    static constexpr int CTAS = SMEM <= 75 * 1024 ? 3 : (SMEM <= 113 * 1024 ? 2 : 1);
+    static_assert(Cfg::OUT_FLOATS % 2 == 0, "tiles are copied as float2");
+};
+
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::NT, PipeCfg<Cfg>::CTAS)
+    xcorr_fft_pipe_kernel(XProblems P, int groups_per_problem, int n_groups, int C, long long k_bstride) {
+    using PC = PipeCfg<Cfg>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *raw = reinterpret_cast<float *>(smem_raw);
+    float2 *XR = reinterpret_cast<float2 *>(raw + Cfg::RAW_FLOATS);
+    float2 *KR = XR + Cfg::G * Cfg::XR_PLANE;
+    float2 *CT = KR + Cfg::G * Cfg::KR_PLANE;
+    float *so = reinterpret_cast<float *>(CT + Cfg::G * Cfg::CT_PLANE);  // its own buffer: O(g) fills it while R(g+1) fills XR
+    uint64_t *full = reinterpret_cast<uint64_t *>(so + Cfg::OUT_FLOATS);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(full, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto locate = [&](int g, int &prob, long long &xoff, long long &koff, long long &ooff) {
+        prob = g / groups_per_problem;
+        const long long plane0 = (long long)(g - prob * groups_per_problem) * Cfg::G;
+        const long long b = plane0 / C, c0 = plane0 - b * C;
+        xoff = plane0 * Cfg::XPL;
+        koff = b * k_bstride + c0 * Cfg::KPL;
+        ooff = plane0 * Cfg::OPL;
+    };
+    auto issue = [&](int g) {  // elected thread only
+        int prob;
+        long long xoff, koff, ooff;
+        locate(g, prob, xoff, koff, ooff);
+        mbar_expect_tx(full, Cfg::RAW_FLOATS * 4);
+        bulk_g2s(raw, P.x[prob] + (xoff & ~3ll), Cfg::XWIN * 4, full);
+        bulk_g2s(raw + Cfg::XWIN, P.k[prob] + (koff & ~3ll), Cfg::KWIN * 4, full);
+    };
+    // one FFT task of the round: phase R of group gr (warps < RW; gr < 0: none) or phase O of the group whose spectra are in CT
+    auto fft_round = [&](int gr, int it_r, bool do_o) {
+        const bool is_r = warp < PC::RW;
+        const int ph = is_r ? FFT_PH_R : FFT_PH_O;
+        if (is_r ? gr < 0 : !do_o) return;
+        int prob = 0;
+        long long xoff = 0, koff = 0, ooff = 0;
+        if (is_r) {
+            locate(gr, prob, xoff, koff, ooff);
+            mbar_wait(full, it_r & 1);
+        }
+        const FftBufs bufs{raw + (int)(xoff & 3), raw + Cfg::XWIN + (int)(koff & 3), XR, KR, CT, so};
+        const int t = is_r ? tid : tid - PC::RW * 32;
+        const int h = fft_task_half<Cfg>(ph, t), unit = fft_task_unit<Cfg>(ph, t);
+        float re[32], im[32];
+        if (fftc_load<Cfg>(ph, bufs, unit, h, re, im)) {
+            if (h) fft::half_twiddle(re, im);
+            fft::fft32_fwd(re, im);
+            fftc_store<Cfg>(ph, bufs, unit, h, re, im);
+        }
+    };
+    auto copy_out = [&](float *dst, int first, int step) {
+        float2 *d2 = reinterpret_cast<float2 *>(dst);  // a group starts at an even plane: 8-byte aligned
+        const float2 *s2 = reinterpret_cast<const float2 *>(so);
+#pragma unroll 2
+        for (int e = first; e < Cfg::OUT_FLOATS / 2; e += step) d2[e] = s2[e];
+    };
+
+    const int g0 = blockIdx.x;
+    if (g0 >= n_groups) return;
+    if (tid == 0) issue(g0);
+    fft_round(g0, 0, false);  // prologue: R(g0) alone.  (A single loop with the prologue as iteration -1 measured 5 % slower.)
+    __syncthreads();
+    if (tid == 0 && g0 + (int)gridDim.x < n_groups) issue(g0 + gridDim.x);
+
+    float *prev_dst = nullptr;
+    int it = 0;
+#pragma unroll 1
+    for (int g = g0; g < n_groups; g += gridDim.x, ++it) {
+        int prob;
+        long long xoff, koff, ooff;
+        locate(g, prob, xoff, koff, ooff);
+        const FftBufs bufs{raw, raw, XR, KR, CT, so};
+        // ---- column round (+ the previous tile on its way out)
+        if (PC::SPARE > 0) {
+            if (tid < Cfg::COL_TASKS) fftc_col<Cfg>(bufs, tid);
+            else if (prev_dst) copy_out(prev_dst, tid - Cfg::COL_TASKS, PC::SPARE > 0 ? PC::SPARE : 1);
+        } else {
+            if (prev_dst) copy_out(prev_dst, tid, Cfg::NT);
+            fftc_col<Cfg>(bufs, tid);
+        }
+        __syncthreads();
+        // ---- FFT round: O(g) next to R(g + grid)
+        const int gn = g + gridDim.x;
+        fft_round(gn < n_groups ? gn : -1, it + 1, true);
+        __syncthreads();
+        if (tid == 0 && gn + (int)gridDim.x < n_groups) issue(gn + gridDim.x);  // R(gn) has consumed the landing buffer
+        prev_dst = P.out[prob] + ooff;
+    }
+    copy_out(prev_dst, tid, Cfg::NT);
+}
+
+template <class Cfg>
+static int launch_fft_pipe(const XProblems &P, int n, int B, int C, long long kbs, cudaStream_t st) {
+    using PC = PipeCfg<Cfg>;
+    static DeviceOnce once;
+    if (int e = once.run([] { return cudaFuncSetAttribute(xcorr_fft_pipe_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PC::SMEM); }))
+        return e;
+    const int gpp = (int)(((long long)B * C) / Cfg::G);
+    const int total = gpp * n;
+    const int slots = sm_count() * PC::CTAS;
+    const int grid = total < slots ? total : slots;
+    xcorr_fft_pipe_kernel<Cfg><<<grid, Cfg::NT, PC::SMEM, st>>>(P, gpp, total, C, kbs);
+    count_launch();
+    return launch_status();
+}
+
+// ---- warp-specialised variant -----------------------------------------------------------------------------------------------
+// One persistent CTA per SM whose warps keep ONE role for the whole launch and hand groups to each other through double-buffered
+// shared memory and mbarriers -- no CTA-wide barrier anywhere:
+//
+//     R warps (one per 32 row-FFT tasks)    RAW[s] -> XR[s], KR[s]      wait raw_full[s], xr_free[s];  arrive xr_full[s], raw_free[s]
+//     COL warps (one per plane x segment)   XR[s], KR[s] -> CT[s]       wait xr_full[s],  ct_free[s];  arrive ct_full[s], xr_free[s]
+//     O warps (one per 32 inverse tasks)    CT[s] -> tile[s]            wait ct_full[s],  so_free[s];  arrive so_full[s], ct_free[s]
+//     one copy warp                         tile[s] -> global           wait so_full[s];               arrive so_free[s]
+//
+// Every role has about the same number of instructions per group and warp (one half-FFT task or one column segment), so in
+// steady state all 18 warps (61x61) issue all the time and a warp only waits when it is really starved.  The landing buffer of
+// group i+2 is requested by the first R thread as soon as all R warps have released stage s.
+template <class Cfg>
+struct WsCfg {
+    static constexpr int RW = Cfg::R_TASKS / 32, CW = Cfg::COL_TASKS / 32, OW = Cfg::O_TASKS / 32, NW = RW + CW + OW + 1, NT = NW * 32;
+    static constexpr int STAGE_FLOATS = Cfg::RAW_FLOATS + 2 * Cfg::G * (Cfg::XR_PLANE + Cfg::KR_PLANE + Cfg::CT_PLANE) + Cfg::OUT_FLOATS;
+    static_assert(Cfg::RAW_FLOATS % 4 == 0 && STAGE_FLOATS % 2 == 0 && Cfg::OUT_FLOATS % 2 == 0, "alignment of the stage's buffers");
+    static constexpr int STAGE_PAD = (STAGE_FLOATS + 31) / 32 * 32;  // 128-byte multiple: the landing buffer of stage 1 stays 16-byte aligned
+    static constexpr unsigned long long SMEM = 2ull * STAGE_PAD * 4 + 16 * 8;
+    static_assert(SMEM <= 227 * 1024, "shared memory budget");
+    enum { RAW_FULL = 0, RAW_FREE = 2, XR_FULL = 4, XR_FREE = 6, CT_FULL = 8, CT_FREE = 10, SO_FULL = 12, SO_FREE = 14 };
+};
+
+template <class Cfg>
+__global__ void __launch_bounds__(WsCfg<Cfg>::NT, 1)
+    xcorr_fft_ws_kernel(XProblems P, int groups_per_problem, int n_groups, int C, long long k_bstride) {
+    using W = WsCfg<Cfg>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *base = reinterpret_cast<float *>(smem_raw);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(base + 2 * W::STAGE_PAD);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&bars[W::RAW_FULL + s], 1);
+            mbar_init(&bars[W::RAW_FREE + s], W::RW * 32);
+            mbar_init(&bars[W::XR_FULL + s], W::RW * 32);
+            mbar_init(&bars[W::XR_FREE + s], W::CW * 32);
+            mbar_init(&bars[W::CT_FULL + s], W::CW * 32);
+            mbar_init(&bars[W::CT_FREE + s], W::OW * 32);
+            mbar_init(&bars[W::SO_FULL + s], W::OW * 32);
+            mbar_init(&bars[W::SO_FREE + s], 32);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto locate = [&](int g, int &prob, long long &xoff, long long &koff, long long &ooff) {
+        prob = g / groups_per_problem;
+        const long long plane0 = (long long)(g - prob * groups_per_problem) * Cfg::G;
+        const long long b = plane0 / C, c0 = plane0 - b * C;
+        xoff = plane0 * Cfg::XPL;
+        koff = b * k_bstride + c0 * Cfg::KPL;
+        ooff = plane0 * Cfg::OPL;
+    };
+    auto stage = [&](int s, int xo, int ko) {
+        float *raw = base + s * W::STAGE_PAD;
+        float2 *XR = reinterpret_cast<float2 *>(raw + Cfg::RAW_FLOATS);
+        float2 *KR = XR + Cfg::G * Cfg::XR_PLANE;
+        float2 *CT = KR + Cfg::G * Cfg::KR_PLANE;
+        float *so = reinterpret_cast<float *>(CT + Cfg::G * Cfg::CT_PLANE);
+        return FftBufs{raw + xo, raw + Cfg::XWIN + ko, XR, KR, CT, so};
+    };
+    auto issue = [&](int g, int s) {  // one thread
+        int prob;
+        long long xoff, koff, ooff;
+        locate(g, prob, xoff, koff, ooff);
+        float *raw = base + s * W::STAGE_PAD;
+        mbar_expect_tx(&bars[W::RAW_FULL + s], Cfg::RAW_FLOATS * 4);
+        bulk_g2s(raw, P.x[prob] + (xoff & ~3ll), Cfg::XWIN * 4, &bars[W::RAW_FULL + s]);
+        bulk_g2s(raw + Cfg::XWIN, P.k[prob] + (koff & ~3ll), Cfg::KWIN * 4, &bars[W::RAW_FULL + s]);
+    };
+    const int g0 = blockIdx.x, step = gridDim.x;
+    if (g0 >= n_groups) return;
+
+    const bool is_r = warp < W::RW, is_o = warp >= W::RW + W::CW && warp < W::RW + W::CW + W::OW;
+    if (is_r || is_o) {  // --------------------------------------- row FFTs (R) and inverse row FFTs (O): ONE copy of the half-FFT code
+        if (tid == 0) {
+            issue(g0, 0);
+            if (g0 + step < n_groups) issue(g0 + step, 1);
+        }
+        const int ph = is_r ? FFT_PH_R : FFT_PH_O;
+        const int t = is_r ? tid : tid - (W::RW + W::CW) * 32;
+        const int h = fft_task_half<Cfg>(ph, t), unit = fft_task_unit<Cfg>(ph, t);
+        // R: wait xr_free / raw_full, arrive xr_full / raw_free;   O: wait so_free / ct_full, arrive so_full / ct_free
+        uint64_t *wait_free = &bars[is_r ? W::XR_FREE : W::SO_FREE], *wait_full = &bars[is_r ? W::RAW_FULL : W::CT_FULL];
+        uint64_t *done_full = &bars[is_r ? W::XR_FULL : W::SO_FULL], *done_free = &bars[is_r ? W::RAW_FREE : W::CT_FREE];
+        int i = 0;
+#pragma unroll 1
+        for (int g = g0; g < n_groups; g += step, ++i) {
+            const int s = i & 1, par = (i >> 1) & 1;
+            if (tid == 0 && i >= 1 && g + step < n_groups) {  // group i+1 lands in stage s^1 once every R warp has released it (groups 0, 1: above)
+                mbar_wait(&bars[W::RAW_FREE + (s ^ 1)], ((i - 1) >> 1) & 1);
+                issue(g + step, s ^ 1);
+            }
+            int xo = 0, ko = 0;
+            if (is_r) {
+                int prob;
+                long long xoff, koff, ooff;
+                locate(g, prob, xoff, koff, ooff);
+                xo = (int)(xoff & 3), ko = (int)(koff & 3);
+            }
+            const FftBufs bufs = stage(s, xo, ko);
+            mbar_wait(wait_free + s, par ^ 1);
+            mbar_wait(wait_full + s, par);
+            float re[32], im[32];
+            if (fftc_load<Cfg>(ph, bufs, unit, h, re, im)) {
+                if (h) fft::half_twiddle(re, im);
+                fft::fft32_fwd(re, im);
+                fftc_store<Cfg>(ph, bufs, unit, h, re, im);
+            }
+            mbar_arrive(done_full + s);
+            mbar_arrive(done_free + s);
+        }
+    } else if (warp < W::RW + W::CW) {  // ------------------------------------------------------------------ column stage
+        const int t = tid - W::RW * 32;
+        int i = 0;
+#pragma unroll 1
+        for (int g = g0; g < n_groups; g += step, ++i) {
+            const int s = i & 1, par = (i >> 1) & 1;
+            const FftBufs bufs = stage(s, 0, 0);
+            mbar_wait(&bars[W::CT_FREE + s], par ^ 1);
+            mbar_wait(&bars[W::XR_FULL + s], par);
+            fftc_col<Cfg>(bufs, t);
+            mbar_arrive(&bars[W::CT_FULL + s]);
+            mbar_arrive(&bars[W::XR_FREE + s]);
+        }
+    } else {  // ------------------------------------------------------------------------------------------------ tiles out
+        int i = 0;
+        for (int g = g0; g < n_groups; g += step, ++i) {
+            const int s = i & 1, par = (i >> 1) & 1;
+            int prob;
+            long long xoff, koff, ooff;
+            locate(g, prob, xoff, koff, ooff);
+            const FftBufs bufs = stage(s, 0, 0);
+            float2 *d2 = reinterpret_cast<float2 *>(P.out[prob] + ooff);  // a group starts at an even plane: 8-byte aligned
+            const float2 *s2 = reinterpret_cast<const float2 *>(bufs.out);
+            mbar_wait(&bars[W::SO_FULL + s], par);
+#pragma unroll 4
+            for (int e = lane; e < Cfg::OUT_FLOATS / 2; e += 32) d2[e] = s2[e];
+            mbar_arrive(&bars[W::SO_FREE + s]);
+        }
+    }
+}
+
+template <class Cfg>
+static int launch_fft_ws(const XProblems &P, int n, int B, int C, long long kbs, cudaStream_t st) {
+    using W = WsCfg<Cfg>;
+    static DeviceOnce once;
+    if (int e = once.run([] { return cudaFuncSetAttribute(xcorr_fft_ws_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W::SMEM); }))
+        return e;
+    const int gpp = (int)(((long long)B * C) / Cfg::G);
+    const int total = gpp * n;
+    const int grid = total < sm_count() ? total : sm_count();
+    xcorr_fft_ws_kernel<Cfg><<<grid, W::NT, W::SMEM, st>>>(P, gpp, total, C, kbs);
+    count_launch();
+    return launch_status();
+}
+
 template <class Cfg>
 static int launch_fft(const XProblems &P, int n, int B, int C, long long kbs, cudaStream_t st) {
     static DeviceOnce once;
@@ -126,20 +416,35 @@ using F256 = FCfg<29, 29, 61, 61, false, HDN_FFT_G1, HDN_FFT_NT1>;    // 256/512
 using F256Lp = FCfg<29, 29, 29, 29, true, 2, HDN_FFT_NT2>;   // 256/512 crops, log-polar branch (INSTANCE_SIZE = 512)
 using FWin15 = FCfg<15, 15, 39, 39, false, 2, HDN_FFT_NT3>;  // 15x15 large-displacement window
 
-#define HDN_FFT_SHAPES(X) X(F256) X(F256Lp) X(FWin15)
+// the pipelined kernel's CTAs: one warp per FFT task of R and O together
+using P256 = FCfg<29, 29, 61, 61, false, 2, 288>;
+using P256Lp = FCfg<29, 29, 29, 29, true, 2, 192>;
+using PWin15 = FCfg<15, 15, 39, 39, false, 2, 192>;
+
+// (three-phase config, pipelined / warp-specialised config, variant that measured fastest on a B200: 1 = three-phase, 2 = pipelined)
+//   61x61 (*) 29x29:       1.035 / 1.081 / 1.297 ms (three-phase / pipelined / warp-specialised), 6 x 64 x 256 planes
+//   29x29 circ (*) 29x29:  0.769 / 0.723 / 0.780 ms
+//   39x39 (*) 15x15:       2.196 / 2.345 / 2.613 ms (6 x 256 x 256 planes)
+#define HDN_FFT_SHAPES(X) X(F256, P256, 1) X(F256Lp, P256Lp, 2) X(FWin15, PWin15, 1)
 
 bool xcorr_fft_applicable(int C, int Hx, int Wx, int Hk, int Wk, int circular) {
-#define HDN_IS(CFG) \
+#define HDN_IS(CFG, PCFG, BEST) \
     if (Hk == CFG::KH && Wk == CFG::KW && Hx == CFG::HX && Wx == CFG::WX && (circular != 0) == CFG::CIRC && C % 4 == 0) return true;
     HDN_FFT_SHAPES(HDN_IS)
 #undef HDN_IS
     return false;
 }
 
-int xcorr_fft_dispatch(const XProblems &P, int n, int B, int C, int Hx, int Wx, int Hk, int Wk, int circular, long long kbs, cudaStream_t st) {
-#define HDN_TRY(CFG) \
+// variant: 0 = the fastest measured kernel of the shape, 1 = three-phase, 2 = pipelined, 3 = warp-specialised
+int xcorr_fft_dispatch(const XProblems &P, int n, int B, int C, int Hx, int Wx, int Hk, int Wk, int circular, long long kbs, int variant,
+                       cudaStream_t st) {
+#define HDN_TRY(CFG, PCFG, BEST) \
     if (Hk == CFG::KH && Wk == CFG::KW && Hx == CFG::HX && Wx == CFG::WX && (circular != 0) == CFG::CIRC && C % 4 == 0) \
-        return launch_fft<CFG>(P, n, B, C, kbs, st);
+        switch (variant ? variant : BEST) { \
+            case 1: return launch_fft<CFG>(P, n, B, C, kbs, st); \
+            case 3: return launch_fft_ws<PCFG>(P, n, B, C, kbs, st); \
+            default: return launch_fft_pipe<PCFG>(P, n, B, C, kbs, st); \
+        }
     HDN_FFT_SHAPES(HDN_TRY)
 #undef HDN_TRY
     return HDN_ERR_UNSUPPORTED;

@@ -82,7 +82,7 @@ def _xcorr(x, kernel, circular, out=None):
     return out
 
 
-XCORR_ALGOS = {"auto": 0, "direct": 1, "fft": 2}
+XCORR_ALGOS = {"auto": 0, "direct": 1, "fft": 2, "fft_phased": 3, "fft_pipe": 4, "fft_ws": 5}
 
 
 def set_xcorr_algo(name):

@@ -71,9 +71,11 @@ int hdn_xcorr_dw_multi_f32(int n, const float *const *x_host, const float *const
 /* Algorithm of K1/K2 for the shapes that have both kernels (29x29 and 15x15 templates, where the direct sum is FMA-bound at
  * 30-140 flop/B): HDN_XCORR_DIRECT = the direct register-tiled sum; HDN_XCORR_FFT / HDN_XCORR_AUTO (default) = the transform-domain
  * kernel (row FFTs + per-frequency column correlation + inverse row FFTs, xcorr_fft.cu), faster on a B200 for all of them.
- * Per calling thread; both give the reference's result to ~3e-7 of max|out|.  hdn_xcorr_uses_fft: 1 if that shape (dense or shared
+ * HDN_XCORR_FFT_PHASED = the same arithmetic in the barrier-separated three-phase kernel (kept for A/B measurements; AUTO / FFT run the
+ * software-pipelined one: inverse FFTs of a group next to the forward FFTs of the next).
+ * Per calling thread; all give the reference's result to ~3e-7 of max|out|.  hdn_xcorr_uses_fft: 1 if that shape (dense or shared
  * template, 16-byte aligned pointers) now takes the FFT kernel -- the same decision hdn_xcorr_dw*_f32 makes. */
-enum hdn_xcorr_algo { HDN_XCORR_AUTO = 0, HDN_XCORR_DIRECT = 1, HDN_XCORR_FFT = 2 };
+enum hdn_xcorr_algo { HDN_XCORR_AUTO = 0, HDN_XCORR_DIRECT = 1, HDN_XCORR_FFT = 2, HDN_XCORR_FFT_PHASED = 3, HDN_XCORR_FFT_PIPE = 4, HDN_XCORR_FFT_WS = 5 };
 int hdn_xcorr_set_algo(int algo);
 int hdn_xcorr_uses_fft(int C, int Hx, int Wx, int Hk, int Wk, int circular, int64_t k_batch_stride);
 

@@ -166,6 +166,35 @@ def test_xcorr_full_size_random_slice_vs_oracle(shape, algo):
             assert np.abs(out[b:b + 1].cpu().numpy() - ref).max() <= 5e-6 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("shape", [(1, 4, 61, 61, 29, 29, 0), (1, 256, 61, 61, 29, 29, 0), (5, 256, 61, 61, 29, 29, 0), (3, 256, 29, 29, 29, 29, 1),
+                                   (1, 8, 29, 29, 29, 29, 1), (7, 256, 39, 39, 15, 15, 0), (13, 64, 61, 61, 29, 29, 0), (64, 256, 61, 61, 29, 29, 0), (64, 256, 29, 29, 29, 29, 1)])
+@pytest.mark.parametrize("variant", ["fft_pipe", "fft_ws", "fft"])
+def test_fft_kernel_variants_equal_the_phased_kernel_bitwise(shape, variant):
+    """The software-pipelined (O(g) next to R(g+1)) and the warp-specialised (roles + mbarriers, no CTA barrier) transform-domain
+    kernels do the arithmetic of the three-phase kernel in the same order, so all agree bit for bit -- at one group, fewer groups than
+    CTAs, one / several groups per CTA, odd counts, dense and shared templates, and through the multi-problem launch."""
+    B, C, Hx, Wx, Hk, Wk, circ = shape
+    fn = ops().xcorr_depthwise_circular if circ else ops().xcorr_depthwise
+    gen = torch.Generator(device=DEV).manual_seed(B * 31 + C + Hx)
+    x = torch.randn((B, C, Hx, Wx), device=DEV, generator=gen)
+    k = torch.randn((B, C, Hk, Wk), device=DEV, generator=gen) * 0.1
+    try:
+        ops().set_xcorr_algo("fft_phased")
+        want, want_shared = fn(x, k), fn(x, k[:1])
+        want_multi = ops().xcorr_depthwise_multi([x, x * 0.5, x + 1.0], [k, k, k * 2.0], circular=bool(circ))
+        ops().set_xcorr_algo(variant)
+        for _ in range(3):  # repeated: a race between the rounds would not repeat itself
+            assert torch.equal(fn(x, k), want)
+        assert torch.equal(fn(x, k[:1]), want_shared)
+        got_multi = ops().xcorr_depthwise_multi([x, x * 0.5, x + 1.0], [k, k, k * 2.0], circular=bool(circ))
+        assert all(torch.equal(a, b) for a, b in zip(got_multi, want_multi))
+        ops().set_xcorr_algo("direct")
+        direct = fn(x, k)
+        assert float((want - direct).abs().max()) <= 5e-6 * float(direct.abs().max())
+    finally:
+        ops().set_xcorr_algo("auto")
+
+
 def test_xcorr_untiled_shape_runs_generic_kernel_and_is_counted():
     """A crop size outside the tiled table (INSTANCE_SIZE 287 -> 33x33 search features) still gives the reference's result,
     and the library counts it (hdn_xcorr_generic_launches) instead of degrading silently."""
