@@ -422,8 +422,8 @@ def m2_block(workload, B, steps=3, warmup=2):
     torch.cuda.empty_cache()
     return {"value": B / ms * 1e3, "unit": UNIT, "ms_per_step": ms, "pairs_per_step": B, "steps": steps, "gflop_per_pair": M2_GFLOP_PER_PAIR[workload],
             "tflops": tf, "stage_ms": stages, "bf16_peak_tflops_sustained": bf16, "frac_of_bf16_peak": tf / bf16 if bf16 else None,
-            "precision": "fp32-accurate: 3xTF32 on tcgen05 (3 tensor-core MACs per MAC) for the stride-1 backbone / neck / head layers, cuDNN fp32 "
-                         "(TF32 off) for the stem, layer1 and the strided layers",
+            "precision": "fp32-accurate: 3xTF32 on tcgen05 (3 tensor-core MACs per MAC) for every 1x1 / 3x3 convolution of both ResNets, the necks and "
+                         "the heads; fp32 FMA direct sums for the 7x7 stems and PreShareFeature; no cuDNN convolution",
             "check": float(out[0].float().sum().item() * 0 + out[2][0, 8].item())}
 
 
