@@ -31,6 +31,7 @@ SIGNATURES = {
     "hdn_dlt_warp_f32": (_ci, [_vp, _vp, _vp, ctypes.POINTER(_f), ctypes.POINTER(_f), _vp, _vp, _ci, _ci, _ci, _ci, _vp]),
     "hdn_conv_gemm_supported": (_ci, [_ci, _ci, _ci, _ci]),
     "hdn_conv_gemm_set_splitk": (_ci, [_ci]),
+    "hdn_conv_gemm_set_pdl": (_ci, [_ci]),
     "hdn_conv_gemm_set_shift": (_ci, [_ci]),
     "hdn_conv_pack_weight_f32": (_ci, [_vp, _vp, _ci, _ci, _vp]),
     "hdn_conv_gemm_f32": (_ci, [_vp, _vp, _vp, _vp, _vp, _vp, _ci, _ci, _ci, _ci, _ci, _ci, _ci, _ci, _ci, _vp]),

@@ -52,6 +52,12 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(co
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int HW = a.H * a.W, HWo = a.Ho * a.Wo;
+    // PROGRAMMATIC DEPENDENT LAUNCH (launch_conv_gemm sets the stream-serialisation attribute): the next convolution of the stream may
+    // start as soon as every CTA of this one is running -- on the SMs this grid leaves free at tracking batch sizes -- and does
+    // everything that does not depend on this kernel's output (barrier init, TMEM allocation, the first weight records, which are
+    // constants) before its producers block in griddepcontrol.wait.  All reads of activations / residuals and all global writes of a
+    // kernel come after its own wait, so the chain N-1 -> N -> N+1 stays ordered.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // SPLIT-K over a thread-block cluster (small problems, tracking batch sizes): the `splitk` CTAs of a cluster own the same output
     // tile and 1/splitk of the K blocks each; their fp32 partial tiles meet in the leader through distributed shared memory.
     const int S = PROJECT ? 1 : a.splitk;
@@ -201,6 +207,7 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(co
         unsigned soff[NBJ];  // this thread's 16-byte slots inside a stage's B tile (canonical K-major layout), in floats
 #pragma unroll
         for (int j = 0; j < NBJ; ++j) soff[j] = (unsigned)((((tid + CG_THREADS * j) / BN) * B_LBO + (bn >> 3) * B_SBO + (bn & 7) * 16) >> 2);
+        asm volatile("griddepcontrol.wait;" ::: "memory");  // the producing kernel(s) have completed and flushed: activations may be read
         int drained = 0;
         auto stage_block = [&](int kb, const float (&v)[NBJ][4]) {
             const int s = kb % STAGES;
@@ -268,6 +275,9 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(co
             // residual add and ReLU applied on the way out (coalesced residual reads as well).
             constexpr int YP = BN + 1;
             float *ys = reinterpret_cast<float *>(smem);
+            // Every producer's last staging store is already ordered before this point through bar_full -> MMA -> commit -> the drain's
+            // wait; the named barrier states that ordering directly (compute-sanitizer's racecheck does not follow the tensor-core hop).
+            asm volatile("bar.sync 1, %0;" ::"n"(CG_THREADS) : "memory");
             if (S > 1) {  // split-K: leave the raw fp32 partial tile in shared memory; the cluster reduces it below
 #pragma unroll
                 for (int e = 0; e < HALF; ++e) ys[row * YP + col_lo + e] = racc[e];
@@ -294,6 +304,7 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(co
             constexpr int YP = BN + 1;
             float *ys = reinterpret_cast<float *>(smem);
             float *w2s = ys + CG_BM * YP;  // [L][128]
+            asm volatile("bar.sync 1, %0;" ::"n"(CG_THREADS) : "memory");  // (ordering already holds; stated for racecheck, see above)
 #pragma unroll
             for (int e = 0; e < HALF; ++e) {
                 float y = fmaf(racc[e], sc, sh);
@@ -354,6 +365,8 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_tf32x3_kernel(co
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)(2 * BN)));
 }
 
+int g_conv_pdl = 1;  // hdn_conv_gemm_set_pdl: programmatic dependent launch of consecutive convolutions (default on)
+
 template <int BN, int STAGES, int RAW, bool PROJECT = false>
 static int launch_conv_gemm(const ConvGemmArgs &a, int nprob, cudaStream_t st) {
     constexpr size_t SMEM = (size_t)STAGES * (2 * CG_BM * CG_BK * 4 + 2 * CG_BK * BN * 4) + 1024;
@@ -364,24 +377,29 @@ static int launch_conv_gemm(const ConvGemmArgs &a, int nprob, cudaStream_t st) {
         return e;
     const int S = a.splitk > 1 ? a.splitk : 1;
     dim3 grid((a.Ho * a.Wo + BN - 1) / BN * S, (a.Cout + CG_BM - 1) / CG_BM, a.B * nprob);
-    if (S == 1) {
-        conv_gemm_tf32x3_kernel<BN, STAGES, RAW, PROJECT><<<grid, CG_THREADS + 64, SMEM, st>>>(a);
-    } else {  // a cluster of S CTAs along x per output tile
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = grid;
-        cfg.blockDim = dim3(CG_THREADS + 64);
-        cfg.dynamicSmemBytes = SMEM;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = S;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_tf32x3_kernel<BN, STAGES, RAW, PROJECT>, a);
-        if (e != cudaSuccess) return (int)e;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(CG_THREADS + 64);
+    cfg.dynamicSmemBytes = SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (S > 1) {  // a cluster of S CTAs along x per output tile
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = S;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
     }
+    if (g_conv_pdl) {  // see the kernel: prologue + first weight records overlap the tail of the previous kernel of the stream
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_tf32x3_kernel<BN, STAGES, RAW, PROJECT>, a);
+    if (e != cudaSuccess) return (int)e;
     count_launch();
     return launch_status();
 }
@@ -404,6 +422,8 @@ __global__ void conv_pack_weight_kernel(const float *__restrict__ wt, float *__r
     }
 }
 
+__global__ void conv_pack_fence_kernel() {}
+
 }  // namespace hdn
 
 using namespace hdn;
@@ -413,7 +433,11 @@ extern "C" int hdn_conv_pack_weight_f32(const float *wt, float *packed, int Cout
     if (Cout < 64 || Cout % 64 || Ktot < CG_BK || Ktot % CG_BK) return HDN_ERR_SHAPE;
     if (reinterpret_cast<uintptr_t>(packed) & 15u) return HDN_ERR_ALIGN;
     conv_pack_weight_kernel<<<sm_count() * 4, 256, 0, (cudaStream_t)stream>>>(wt, packed, Cout, Ktot);
-    count_launch();
+    // A convolution launched right behind this one reads its first weight records BEFORE its griddepcontrol.wait (they are constants
+    // to it).  The empty kernel makes the pack kernel's completion -- full stream-order completion, memory flushed -- the thing
+    // that convolution's launch depends on, instead of a programmatic edge to the pack kernel itself.
+    conv_pack_fence_kernel<<<1, 32, 0, (cudaStream_t)stream>>>();
+    count_launch(2);
     return launch_status();
 }
 
@@ -501,6 +525,11 @@ extern "C" int hdn_head_project_multi_f32(int n, const float *const *x_host, con
     if (!w2_host) return HDN_ERR_NULL;
     return conv_gemm_multi(n, x_host, wpk_host, scale_host, shift_host, nullptr, w2_host, part_host, B, C, C, H, W, 1, 1, 0, 1, L,
                            (cudaStream_t)stream);
+}
+
+extern "C" int hdn_conv_gemm_set_pdl(int enable) {
+    hdn::g_conv_pdl = enable ? 1 : 0;
+    return HDN_OK;
 }
 
 extern "C" int hdn_conv_gemm_set_splitk(int enable) {

@@ -239,6 +239,7 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv3x3_shift_kernel(const
         const int co = co0 + row;
         const float *scp = a.scale[prob], *shp = a.shift[prob], *resp = a.residual[prob];
         const float sc = scp ? __ldg(scp + co) : 1.f, sh = shp ? __ldg(shp + co) : 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(CG_THREADS) : "memory");  // see conv_gemm.cu: states the staging-store -> epilogue ordering for racecheck
 #pragma unroll
         for (int e = 0; e < HALF; ++e) ys[row * YP + col_lo + e] = fmaf(racc[e], sc, sh);
         asm volatile("bar.sync 1, %0;" ::"n"(CG_THREADS) : "memory");

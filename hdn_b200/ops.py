@@ -434,6 +434,11 @@ def set_conv_splitk(enable=True):
     _lib.check(_lib.lib().hdn_conv_gemm_set_splitk(int(bool(enable))), "hdn_conv_gemm_set_splitk")
 
 
+def set_conv_pdl(enable=True):
+    """Programmatic dependent launch between consecutive tcgen05 convolutions (default on); False = plain stream order (A/B runs)."""
+    _lib.check(_lib.lib().hdn_conv_gemm_set_pdl(int(bool(enable))), "hdn_conv_gemm_set_pdl")
+
+
 def set_conv_shift(mode=True):
     """3x3 'valid' layers on the shifted-window kernel (conv_shift.cu).  True / 1 (default): on; 2: on, with weight multicast
     across 2-CTA clusters (correct, measured slower: A/B switch); False / 0: the generic implicit GEMM."""

@@ -153,6 +153,10 @@ int hdn_conv_gemm_ex_f32(const float *x, const float *wpk, const float *scale, c
  * cluster of 2 / 4 / 8 CTAs whose fp32 partial tiles are added in rank order through distributed shared memory (deterministic).
  * enable = 0 switches that off (A/B runs); default on. */
 int hdn_conv_gemm_set_splitk(int enable);
+/* Consecutive convolution launches of a stream are chained by programmatic dependent launch: the next kernel's prologue (barriers,
+ * TMEM allocation, first weight records) overlaps the tail of the previous one; its activation reads and all its writes wait for
+ * the previous kernel's completion (griddepcontrol.wait).  enable = 0: plain stream order (A/B runs); default on. */
+int hdn_conv_gemm_set_pdl(int enable);
 /* 3x3 'valid' layers with W <= 63 (the heads' conv_search / conv_kernel) run a kernel that stages the activations once per
  * 32-channel block and feeds the nine taps as shifted windows of that tile (conv_shift.cu).  mode = 1 (default): on; 2: on, and
  * clusters of two neighbouring pixel tiles share every weight record through TMA multicast (built and correct, measured slower:

@@ -370,3 +370,43 @@ def test_share_feature_and_stems_equal_the_module_path():
             got = convs.conv_bn_act(net.conv1, net.bn1, xin, relu=True)
             want = torch.relu(net.bn1(net.conv1(xin)))
             assert got.shape == want.shape and (got - want).abs().max().item() <= 1e-5 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.parametrize("batch", [1, 3])
+def test_programmatic_dependent_launch_chain_equals_plain_stream_order(batch):
+    """Consecutive tcgen05 convolutions are chained by programmatic dependent launch (the next kernel's prologue and first weight
+    records overlap the previous kernel's tail; activation reads and all writes wait for its completion).  A ResNet-50 forward --
+    53 dependent launches with residual reads and split-K clusters -- must give bit-identical features with the chaining on and
+    off, eagerly (cold: weights packed right before their first use) and as a replayed CUDA graph."""
+    from hdn_b200 import compat, ops, synthetic
+    compat.activate()
+    from hdn.models.backbone.resnet_atrous import resnet50
+    torch.manual_seed(11)
+    with torch.no_grad():
+        net = synthetic.fill_weights(resnet50(used_layers=[2, 3, 4])).cuda().eval()
+        x = torch.randn(batch, 3, 255, 255, device="cuda") * 50
+        try:
+            ops.set_conv_pdl(True)
+            cold = [f.clone() for f in net(x)]          # first call: every layer packs its weight, then launches
+            ops.set_conv_pdl(False)
+            want = [f.clone() for f in net(x)]
+            ops.set_conv_pdl(True)
+            assert all(torch.equal(a, b) for a, b in zip(cold, want))
+            for _ in range(5):
+                assert all(torch.equal(a, b) for a, b in zip(net(x), want))
+            torch.cuda.synchronize()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                net(x)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                outs = net(x)
+            for _ in range(3):
+                x.copy_(x)  # same input; replay must reproduce the eager result
+                graph.replay()
+                torch.cuda.synchronize()
+                assert all(torch.equal(a, b) for a, b in zip(outs, want))
+        finally:
+            ops.set_conv_pdl(True)
