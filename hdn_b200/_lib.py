@@ -40,6 +40,9 @@ SIGNATURES = {
     "hdn_cubic_table_host": (_ci, [_vp]),
     "hdn_warp_affine_cubic_u8": (_ci, [_vp, _vp, _ci, _ci, ctypes.POINTER(_d), _vp, _vp]),
     "hdn_crop_resize_u8": (_ci, [_vp, _ci, _ci, _ci, _ci, _ci, ctypes.POINTER(ctypes.c_uint8), _ci, _ci, ctypes.POINTER(_d), ctypes.POINTER(_d), _vp, _vp]),
+    "hdn_xcorr_spectra_floats": (ctypes.c_int64, [_ci] * 6),
+    "hdn_xcorr_template_spectra_f32": (_ci, [_ci, ctypes.POINTER(_vp), ctypes.POINTER(_vp)] + [_ci] * 6 + [_vp]),
+    "hdn_xcorr_dw_multi_spec_f32": (_ci, [_ci] + [ctypes.POINTER(_vp)] * 3 + [_ci] * 7 + [_vp]),
     "hdn_conv_small_supported": (_ci, [_ci, _ci, _ci, _ci]),
     "hdn_conv_small_f32": (_ci, [_vp] * 5 + [_ci] * 9 + [_vp]),
     "hdn_conv_gemm_ex_f32": (_ci, [_vp, _vp, _vp, _vp, _vp, _vp, _ci, _ci, _ci, _ci, _ci, _ci, _ci, _ci, _ci, _ci, _vp]),

@@ -42,6 +42,11 @@ struct XProblems {
 // xcorr_fft.cu: FFT correlation for the FMA-bound shapes.  Returns HDN_ERR_UNSUPPORTED when the shape has no FFT kernel.
 int xcorr_fft_dispatch(const XProblems &P, int n, int B, int C, int Hx, int Wx, int Hk, int Wk, int circular, long long kbs, int variant, cudaStream_t st);
 bool xcorr_fft_applicable(int C, int Hx, int Wx, int Hk, int Wk, int circular);
+// shared template with cached row spectra (xcorr_fft.cu): size of a template's spectra in floats (0: shape has no such kernel),
+// the producer (P.k = templates, P.out = spectra) and the consumer (P.k = spectra)
+long long xcorr_spectra_floats(int C, int Hx, int Wx, int Hk, int Wk, int circular);
+int xcorr_spectra_dispatch(const XProblems &P, int n, int C, int Hx, int Wx, int Hk, int Wk, int circular, cudaStream_t st);
+int xcorr_fft_spec_dispatch(const XProblems &P, int n, int B, int C, int Hx, int Wx, int Hk, int Wk, int circular, int variant, cudaStream_t st);
 
 // ---- mbarrier + bulk async copy (TMA, 1-D) -------------------------------------------------
 // SASS: cp.async.bulk -> UBLKCP, expect_tx -> SYNCS.ARRIVE.TRANS64 (B200_PROFILING.md).

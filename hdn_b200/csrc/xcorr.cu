@@ -642,6 +642,40 @@ extern "C" int hdn_xcorr_dw_multi_f32(int n, const float *const *x_host, const f
     return xcorr_dispatch(P, n, B, C, Hx, Wx, Hk, Wk, circular, (long long)k_batch_stride, (cudaStream_t)stream);
 }
 
+extern "C" int64_t hdn_xcorr_spectra_floats(int C, int Hx, int Wx, int Hk, int Wk, int circular) {
+    return (int64_t)xcorr_spectra_floats(C, Hx, Wx, Hk, Wk, circular);
+}
+
+static int fill_problems(XProblems &P, int n, const float *const *a, const float *const *b, float *const *c) {
+    if (!a || !b || !c) return HDN_ERR_NULL;
+    if (n < 1 || n > HDN_MAX_PROBLEMS) return HDN_ERR_UNSUPPORTED;
+    for (int i = 0; i < HDN_MAX_PROBLEMS; ++i) P.x[i] = P.k[i] = P.out[i] = nullptr;
+    for (int i = 0; i < n; ++i) {
+        if (!a[i] || !b[i] || !c[i]) return HDN_ERR_NULL;
+        if ((reinterpret_cast<uintptr_t>(a[i]) | reinterpret_cast<uintptr_t>(b[i]) | reinterpret_cast<uintptr_t>(c[i])) & 15u) return HDN_ERR_ALIGN;
+        P.x[i] = a[i];
+        P.k[i] = b[i];
+        P.out[i] = c[i];
+    }
+    return HDN_OK;
+}
+
+extern "C" int hdn_xcorr_template_spectra_f32(int n, const float *const *k_host, float *const *spectra_host, int C, int Hx, int Wx, int Hk,
+                                              int Wk, int circular, hdn_stream_t stream) {
+    XProblems P;
+    if (int e = fill_problems(P, n, k_host, k_host, spectra_host)) return e;
+    return xcorr_spectra_dispatch(P, n, C, Hx, Wx, Hk, Wk, circular, (cudaStream_t)stream);
+}
+
+extern "C" int hdn_xcorr_dw_multi_spec_f32(int n, const float *const *x_host, const float *const *spectra_host, float *const *out_host, int B,
+                                           int C, int Hx, int Wx, int Hk, int Wk, int circular, hdn_stream_t stream) {
+    if (B < 1) return HDN_ERR_SHAPE;
+    XProblems P;
+    if (int e = fill_problems(P, n, x_host, spectra_host, out_host)) return e;
+    const int variant = g_xcorr_algo >= HDN_XCORR_FFT_PHASED ? g_xcorr_algo - HDN_XCORR_FFT_PHASED + 1 : 0;
+    return xcorr_fft_spec_dispatch(P, n, B, C, Hx, Wx, Hk, Wk, circular, variant == 3 ? 0 : variant, (cudaStream_t)stream);
+}
+
 extern "C" int hdn_xcorr_dw_f32(const float *x, const float *k, float *out, int B, int C, int Hx, int Wx, int Hk, int Wk, int circular,
                                 int64_t k_batch_stride, hdn_stream_t stream) {
     return hdn_xcorr_dw_multi_f32(1, &x, &k, &out, B, C, Hx, Wx, Hk, Wk, circular, k_batch_stride, stream);

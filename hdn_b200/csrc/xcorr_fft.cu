@@ -28,21 +28,23 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::CTAS)
     float2 *XR = reinterpret_cast<float2 *>(raw + Cfg::RAW_FLOATS);
     float2 *KR = XR + Cfg::G * Cfg::XR_PLANE;
     float2 *CT = KR + Cfg::G * Cfg::KR_PLANE;
-    uint64_t *full = reinterpret_cast<uint64_t *>(CT + Cfg::G * Cfg::CT_PLANE);
+    uint64_t *full = reinterpret_cast<uint64_t *>(CT + Cfg::G * Cfg::CT_PLANE), *kfull = full + 1;
     float *so = reinterpret_cast<float *>(XR);  // output tile: XR is dead once the column stage is done
     const int tid = threadIdx.x;
     if (tid == 0) {
         mbar_init(full, 1);
+        mbar_init(kfull, 1);
         mbar_fence_init();
     }
     __syncthreads();
-    // group g -> problem, element offsets of its x / k / out planes
+    // group g -> problem, element offsets of its x / k / out planes.  KSPEC: P.k holds the template's row spectra [C][KR_PLANE] complex
+    // (one template for the whole batch), koff = float offset of the group's first channel.
     auto locate = [&](int g, int &prob, long long &xoff, long long &koff, long long &ooff) {
         prob = g / groups_per_problem;
         const long long plane0 = (long long)(g - prob * groups_per_problem) * Cfg::G;
         const long long b = plane0 / C, c0 = plane0 - b * C;
         xoff = plane0 * Cfg::XPL;
-        koff = b * k_bstride + c0 * Cfg::KPL;
+        koff = Cfg::KSPEC ? c0 * (2 * Cfg::KR_PLANE) : b * k_bstride + c0 * Cfg::KPL;
         ooff = plane0 * Cfg::OPL;
     };
     auto issue = [&](int g) {  // elected thread only
@@ -51,16 +53,26 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::CTAS)
         locate(g, prob, xoff, koff, ooff);
         mbar_expect_tx(full, Cfg::RAW_FLOATS * 4);
         bulk_g2s(raw, P.x[prob] + (xoff & ~3ll), Cfg::XWIN * 4, full);
-        bulk_g2s(raw + Cfg::XWIN, P.k[prob] + (koff & ~3ll), Cfg::KWIN * 4, full);
+        if (!Cfg::KSPEC) bulk_g2s(raw + Cfg::XWIN, P.k[prob] + (koff & ~3ll), Cfg::KWIN * 4, full);
     };
-    if (tid == 0 && (int)blockIdx.x < n_groups) issue(blockIdx.x);
+    auto issue_k = [&](int g) {  // KSPEC, elected thread only: the group's spectra land directly in KR (free once the column stage is done)
+        int prob;
+        long long xoff, koff, ooff;
+        locate(g, prob, xoff, koff, ooff);
+        mbar_expect_tx(kfull, Cfg::G * Cfg::KR_PLANE * 8);
+        bulk_g2s(KR, P.k[prob] + koff, Cfg::G * Cfg::KR_PLANE * 8, kfull);
+    };
+    if (tid == 0 && (int)blockIdx.x < n_groups) {
+        issue(blockIdx.x);
+        if (Cfg::KSPEC) issue_k(blockIdx.x);
+    }
 
     int it = 0;
     for (int g = blockIdx.x; g < n_groups; g += gridDim.x, ++it) {
         int prob;
         long long xoff, koff, ooff;
         locate(g, prob, xoff, koff, ooff);
-        const FftBufs bufs{raw + (int)(xoff & 3), raw + Cfg::XWIN + (int)(koff & 3), XR, KR, CT, so};
+        const FftBufs bufs{raw + (int)(xoff & 3), raw + Cfg::XWIN + (Cfg::KSPEC ? 0 : (int)(koff & 3)), XR, KR, CT, so};
         mbar_wait(full, it & 1);
 #pragma unroll 1
         for (int ph = 0; ph < FFT_PHASES; ++ph) {
@@ -82,9 +94,11 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::CTAS)
                     const int gn = g + gridDim.x;
                     if (gn < n_groups) issue(gn);
                 }
+                if (Cfg::KSPEC) mbar_wait(kfull, it & 1);
 #pragma unroll 1
                 for (int t = tid; t < Cfg::COL_TASKS; t += Cfg::NT) fftc_col<Cfg>(bufs, t);
                 __syncthreads();
+                if (Cfg::KSPEC && tid == 0 && g + (int)gridDim.x < n_groups) issue_k(g + gridDim.x);  // KR is free again
             }
         }
         float *dst = P.out[prob] + ooff;
@@ -127,10 +141,11 @@ __global__ void __launch_bounds__(Cfg::NT, PipeCfg<Cfg>::CTAS)
     float2 *KR = XR + Cfg::G * Cfg::XR_PLANE;
     float2 *CT = KR + Cfg::G * Cfg::KR_PLANE;
     float *so = reinterpret_cast<float *>(CT + Cfg::G * Cfg::CT_PLANE);  // its own buffer: O(g) fills it while R(g+1) fills XR
-    uint64_t *full = reinterpret_cast<uint64_t *>(so + Cfg::OUT_FLOATS);
+    uint64_t *full = reinterpret_cast<uint64_t *>(so + Cfg::OUT_FLOATS), *kfull = full + 1;
     const int tid = threadIdx.x, warp = tid >> 5;
     if (tid == 0) {
         mbar_init(full, 1);
+        mbar_init(kfull, 1);
         mbar_fence_init();
     }
     __syncthreads();
@@ -139,7 +154,7 @@ __global__ void __launch_bounds__(Cfg::NT, PipeCfg<Cfg>::CTAS)
         const long long plane0 = (long long)(g - prob * groups_per_problem) * Cfg::G;
         const long long b = plane0 / C, c0 = plane0 - b * C;
         xoff = plane0 * Cfg::XPL;
-        koff = b * k_bstride + c0 * Cfg::KPL;
+        koff = Cfg::KSPEC ? c0 * (2 * Cfg::KR_PLANE) : b * k_bstride + c0 * Cfg::KPL;
         ooff = plane0 * Cfg::OPL;
     };
     auto issue = [&](int g) {  // elected thread only
@@ -148,7 +163,14 @@ __global__ void __launch_bounds__(Cfg::NT, PipeCfg<Cfg>::CTAS)
         locate(g, prob, xoff, koff, ooff);
         mbar_expect_tx(full, Cfg::RAW_FLOATS * 4);
         bulk_g2s(raw, P.x[prob] + (xoff & ~3ll), Cfg::XWIN * 4, full);
-        bulk_g2s(raw + Cfg::XWIN, P.k[prob] + (koff & ~3ll), Cfg::KWIN * 4, full);
+        if (!Cfg::KSPEC) bulk_g2s(raw + Cfg::XWIN, P.k[prob] + (koff & ~3ll), Cfg::KWIN * 4, full);
+    };
+    auto issue_k = [&](int g) {  // KSPEC, elected thread only: ready-made template spectra straight into KR
+        int prob;
+        long long xoff, koff, ooff;
+        locate(g, prob, xoff, koff, ooff);
+        mbar_expect_tx(kfull, Cfg::G * Cfg::KR_PLANE * 8);
+        bulk_g2s(KR, P.k[prob] + koff, Cfg::G * Cfg::KR_PLANE * 8, kfull);
     };
     // one FFT task of the round: phase R of group gr (warps < RW; gr < 0: none) or phase O of the group whose spectra are in CT
     auto fft_round = [&](int gr, int it_r, bool do_o) {
@@ -161,7 +183,7 @@ __global__ void __launch_bounds__(Cfg::NT, PipeCfg<Cfg>::CTAS)
             locate(gr, prob, xoff, koff, ooff);
             mbar_wait(full, it_r & 1);
         }
-        const FftBufs bufs{raw + (int)(xoff & 3), raw + Cfg::XWIN + (int)(koff & 3), XR, KR, CT, so};
+        const FftBufs bufs{raw + (int)(xoff & 3), raw + Cfg::XWIN + (Cfg::KSPEC ? 0 : (int)(koff & 3)), XR, KR, CT, so};
         const int t = is_r ? tid : tid - PC::RW * 32;
         const int h = fft_task_half<Cfg>(ph, t), unit = fft_task_unit<Cfg>(ph, t);
         float re[32], im[32];
@@ -180,7 +202,10 @@ __global__ void __launch_bounds__(Cfg::NT, PipeCfg<Cfg>::CTAS)
 
     const int g0 = blockIdx.x;
     if (g0 >= n_groups) return;
-    if (tid == 0) issue(g0);
+    if (tid == 0) {
+        issue(g0);
+        if (Cfg::KSPEC) issue_k(g0);
+    }
     fft_round(g0, 0, false);  // prologue: R(g0) alone.  (A single loop with the prologue as iteration -1 measured 5 % slower.)
     __syncthreads();
     if (tid == 0 && g0 + (int)gridDim.x < n_groups) issue(g0 + gridDim.x);
@@ -195,15 +220,19 @@ __global__ void __launch_bounds__(Cfg::NT, PipeCfg<Cfg>::CTAS)
         const FftBufs bufs{raw, raw, XR, KR, CT, so};
         // ---- column round (+ the previous tile on its way out)
         if (PC::SPARE > 0) {
-            if (tid < Cfg::COL_TASKS) fftc_col<Cfg>(bufs, tid);
-            else if (prev_dst) copy_out(prev_dst, tid - Cfg::COL_TASKS, PC::SPARE > 0 ? PC::SPARE : 1);
+            if (tid < Cfg::COL_TASKS) {
+                if (Cfg::KSPEC) mbar_wait(kfull, it & 1);
+                fftc_col<Cfg>(bufs, tid);
+            } else if (prev_dst) copy_out(prev_dst, tid - Cfg::COL_TASKS, PC::SPARE > 0 ? PC::SPARE : 1);
         } else {
             if (prev_dst) copy_out(prev_dst, tid, Cfg::NT);
+            if (Cfg::KSPEC) mbar_wait(kfull, it & 1);
             fftc_col<Cfg>(bufs, tid);
         }
         __syncthreads();
         // ---- FFT round: O(g) next to R(g + grid)
         const int gn = g + gridDim.x;
+        if (Cfg::KSPEC && tid == 0 && gn < n_groups) issue_k(gn);  // KR is free again
         fft_round(gn < n_groups ? gn : -1, it + 1, true);
         __syncthreads();
         if (tid == 0 && gn + (int)gridDim.x < n_groups) issue(gn + gridDim.x);  // R(gn) has consumed the landing buffer
@@ -384,6 +413,66 @@ static int launch_fft_ws(const XProblems &P, int n, int B, int C, long long kbs,
     return launch_status();
 }
 
+// ---- template row spectra, once per template ------------------------------------------------------------------------------------
+// K'(u,f) of a template [C,KH,KW] in the layout the KSPEC kernels land in KR: [C][KH][33] complex.  It is phase R itself -- the units
+// (x_j, k_j) with an all-zero x -- so the spectra are the values the per-pair kernels compute (Z = 0 + i*k_j separates exactly).
+// A shared template (k_batch_stride == 0: config 3's broadcast template, the tracker's per-sequence template) pays for its 29 row
+// transforms once instead of once per pair and frame: -31 % of phase R at 61x61, -50 % at 29x29 circular.
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::NT, Cfg::CTAS) xcorr_spectra_kernel(XProblems P, int groups_per_problem, int n_groups) {
+    static_assert(!Cfg::KSPEC, "the producer runs the plain phase R");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *raw = reinterpret_cast<float *>(smem_raw);
+    float2 *XR = reinterpret_cast<float2 *>(raw + Cfg::RAW_FLOATS);
+    float2 *KR = XR + Cfg::G * Cfg::XR_PLANE;
+    float2 *CT = KR + Cfg::G * Cfg::KR_PLANE;
+    uint64_t *full = reinterpret_cast<uint64_t *>(CT + Cfg::G * Cfg::CT_PLANE);
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(full, 1);
+        mbar_fence_init();
+    }
+    for (int e = tid; e < Cfg::XWIN; e += Cfg::NT) raw[e] = 0.f;  // the x rows of every unit
+    __syncthreads();
+    int it = 0;
+    for (int g = blockIdx.x; g < n_groups; g += gridDim.x, ++it) {
+        const int prob = g / groups_per_problem;
+        const long long plane0 = (long long)(g - prob * groups_per_problem) * Cfg::G, koff = plane0 * Cfg::KPL;
+        if (tid == 0) {
+            mbar_expect_tx(full, Cfg::KWIN * 4);
+            bulk_g2s(raw + Cfg::XWIN, P.k[prob] + (koff & ~3ll), Cfg::KWIN * 4, full);
+        }
+        const FftBufs bufs{raw, raw + Cfg::XWIN + (int)(koff & 3), XR, KR, CT, reinterpret_cast<float *>(XR)};
+        mbar_wait(full, it & 1);
+#pragma unroll 1
+        for (int t0 = 0; t0 < Cfg::R_TASKS; t0 += Cfg::NT) {
+            const int t = t0 + tid;
+            const int h = fft_task_half<Cfg>(FFT_PH_R, t), unit = fft_task_unit<Cfg>(FFT_PH_R, t);
+            float re[32], im[32];
+            if (t < Cfg::R_TASKS && fftc_load<Cfg>(FFT_PH_R, bufs, unit, h, re, im)) {
+                if (h) fft::half_twiddle(re, im);
+                fft::fft32_fwd(re, im);
+                fftc_store<Cfg>(FFT_PH_R, bufs, unit, h, re, im);
+            }
+        }
+        __syncthreads();
+        float2 *dst = reinterpret_cast<float2 *>(P.out[prob]) + plane0 * Cfg::KR_PLANE;
+        for (int e = tid; e < Cfg::G * Cfg::KR_PLANE; e += Cfg::NT) dst[e] = KR[e];
+        __syncthreads();  // KR and the landing buffer are reused by the next group
+    }
+}
+
+template <class Cfg>
+static int launch_spectra(const XProblems &P, int n, int C, cudaStream_t st) {
+    static DeviceOnce once;
+    if (int e = once.run([] { return cudaFuncSetAttribute(xcorr_spectra_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM); }))
+        return e;
+    const int gpp = C / Cfg::G, total = gpp * n, slots = sm_count() * Cfg::CTAS;
+    xcorr_spectra_kernel<Cfg><<<total < slots ? total : slots, Cfg::NT, Cfg::SMEM, st>>>(P, gpp, total);
+    count_launch();
+    return launch_status();
+}
+
 template <class Cfg>
 static int launch_fft(const XProblems &P, int n, int B, int C, long long kbs, cudaStream_t st) {
     static DeviceOnce once;
@@ -416,6 +505,11 @@ using F256 = FCfg<29, 29, 61, 61, false, HDN_FFT_G1, HDN_FFT_NT1>;    // 256/512
 using F256Lp = FCfg<29, 29, 29, 29, true, 2, HDN_FFT_NT2>;   // 256/512 crops, log-polar branch (INSTANCE_SIZE = 512)
 using FWin15 = FCfg<15, 15, 39, 39, false, 2, HDN_FFT_NT3>;  // 15x15 large-displacement window
 
+// shared template with ready-made row spectra (KSPEC): three-phase and pipelined CTAs
+using S256 = FCfg<29, 29, 61, 61, false, 2, 192, HDN_FFT_TB, true>;
+using S256P = FCfg<29, 29, 61, 61, false, 2, 224, HDN_FFT_TB, true>;    // 4 R + 3 O warps; 6 column warps + one warp copying tiles out
+using S256Lp = FCfg<29, 29, 29, 29, true, 2, 128, HDN_FFT_TB, true>;
+using S256LpP = FCfg<29, 29, 29, 29, true, 2, 128, HDN_FFT_TB, true>;   // 2 R + 2 O warps, 4 column warps: three CTAs per SM
 // the pipelined kernel's CTAs: one warp per FFT task of R and O together
 using P256 = FCfg<29, 29, 61, 61, false, 2, 288>;
 using P256Lp = FCfg<29, 29, 29, 29, true, 2, 192>;
@@ -448,6 +542,43 @@ int xcorr_fft_dispatch(const XProblems &P, int n, int B, int C, int Hx, int Wx, 
     HDN_FFT_SHAPES(HDN_TRY)
 #undef HDN_TRY
     return HDN_ERR_UNSUPPORTED;
+}
+
+// ---- shared template, cached spectra -----------------------------------------------------------------------------------------
+// variant of the KSPEC kernels picked by variant == 0 (1 = three-phase, 2 = pipelined), by measurement on a B200 (B = 64, 6 problems):
+//   61x61:          three-phase 0.961 ms, pipelined 1.004 ms   (per-pair templates: 1.032 ms)
+//   29x29 circular: three-phase 0.750 ms, pipelined 0.692 ms   (per-pair templates: 0.723 ms)
+// The gain is smaller than the -31 % / -50 % of phase R: a round of the pipelined kernel is one FFT task per warp however many warps
+// phase R needs, and the three-phase kernel only sheds issue pressure (4 of 6 warps busy in phase R).
+#ifndef HDN_FFT_SPEC_K1
+#define HDN_FFT_SPEC_K1 1
+#endif
+#ifndef HDN_FFT_SPEC_K2
+#define HDN_FFT_SPEC_K2 2
+#endif
+
+long long xcorr_spectra_floats(int C, int Hx, int Wx, int Hk, int Wk, int circular) {
+    if (C % 4 != 0 || Hk != 29 || Wk != 29) return 0;
+    if (!circular && Hx == 61 && Wx == 61) return (long long)C * F256::KR_PLANE * 2;
+    if (circular && Hx == 29 && Wx == 29) return (long long)C * F256Lp::KR_PLANE * 2;
+    return 0;
+}
+
+// P.k[i] = template i [C,Hk,Wk];  P.out[i] = its spectra
+int xcorr_spectra_dispatch(const XProblems &P, int n, int C, int Hx, int Wx, int Hk, int Wk, int circular, cudaStream_t st) {
+    if (!xcorr_spectra_floats(C, Hx, Wx, Hk, Wk, circular)) return HDN_ERR_UNSUPPORTED;
+    return circular ? launch_spectra<F256Lp>(P, n, C, st) : launch_spectra<F256>(P, n, C, st);
+}
+
+// P.k[i] = spectra of problem i's (shared) template
+int xcorr_fft_spec_dispatch(const XProblems &P, int n, int B, int C, int Hx, int Wx, int Hk, int Wk, int circular, int variant, cudaStream_t st) {
+    if (!xcorr_spectra_floats(C, Hx, Wx, Hk, Wk, circular)) return HDN_ERR_UNSUPPORTED;
+    if (!circular) {
+        if ((variant ? variant : HDN_FFT_SPEC_K1) == 1) return launch_fft<S256>(P, n, B, C, 0, st);
+        return launch_fft_pipe<S256P>(P, n, B, C, 0, st);
+    }
+    if ((variant ? variant : HDN_FFT_SPEC_K2) == 1) return launch_fft<S256Lp>(P, n, B, C, 0, st);
+    return launch_fft_pipe<S256LpP>(P, n, B, C, 0, st);
 }
 
 }  // namespace hdn

@@ -39,10 +39,12 @@ struct float2 {
 
 namespace hdn {
 
-template <int KH_, int KW_, int HX_, int WX_, bool CIRC_, int G_, int NT_, int TB_ = HDN_FFT_TB>
+// KSPEC_: the template's row spectra K'(u,f) arrive ready-made (computed once per template by the same phase-R code, see
+// xcorr_spectra in xcorr_fft.cu) and land directly in KR -- phase R then transforms x rows only, in pairs (x_j, x_{j + R_PAIRS}).
+template <int KH_, int KW_, int HX_, int WX_, bool CIRC_, int G_, int NT_, int TB_ = HDN_FFT_TB, bool KSPEC_ = false>
 struct FCfg {
     static constexpr int KH = KH_, KW = KW_, HX = HX_, WX = WX_, G = G_, NT = NT_;
-    static constexpr bool CIRC = CIRC_;
+    static constexpr bool CIRC = CIRC_, KSPEC = KSPEC_;
     static constexpr int PH = CIRC ? HX / 2 : 0, PW = CIRC ? WX / 2 : 0;
     static constexpr int HP = HX + 2 * PH, WP = WX + 2 * PW;  // padded input extent
     static constexpr int HO = HP - KH + 1, WO = WP - KW + 1;
@@ -56,15 +58,17 @@ struct FCfg {
     // A group's x / k planes are fetched as 16-byte-aligned windows (TMA bulk copies need 16-byte addresses and sizes): a group of 2
     // planes of odd size starts 0 or 2 floats past a 16-byte boundary, so the window is the group rounded out to multiples of 4 floats.
     // (offset 0: the window ends 2 floats into the next group -- never the last one, whose offset is 2 because B*C % 4 == 0.)
-    static constexpr int XWIN = (G * XPL + (G % 4 && XPL % 2 ? 2 : 0) + 3) / 4 * 4, KWIN = (G * KPL + (G % 4 && KPL % 2 ? 2 : 0) + 3) / 4 * 4;
+    static constexpr int XWIN = (G * XPL + (G % 4 && XPL % 2 ? 2 : 0) + 3) / 4 * 4, KWIN = KSPEC ? 0 : (G * KPL + (G % 4 && KPL % 2 ? 2 : 0) + 3) / 4 * 4;
+    static_assert(!KSPEC || (G * KR_PLANE * 8) % 16 == 0, "a group's spectra are one 16-byte-multiple bulk copy");
     static constexpr int RAW_FLOATS = XWIN + KWIN, OUT_FLOATS = G * OPL;
     // Rows that phase R transforms.  K2's padded plane repeats itself: padded row r is source row (r - PH) mod HX with the SAME
     // replicate-padded columns, so only the HX distinct source rows are transformed and each spectrum is stored at every padded
     // row it stands for (57 padded rows -> 29 transforms at 29x29: phase R drops from two half-empty passes to one full pass).
     static constexpr bool DEDUP = CIRC && HX >= KH;
     static constexpr int XSRC = DEDUP ? HX : HP;
-    static constexpr int R_PAIRS = (XSRC - KH + 1) / 2;       // the x rows without a kernel row are packed in pairs (r, r + R_PAIRS):
-    static constexpr int R_UNITS_PLANE = KH + R_PAIRS;        // consecutive units read consecutive rows (odd pitch: no bank conflicts)
+    static constexpr int R_PAIRS = KSPEC ? (XSRC + 1) / 2 : (XSRC - KH + 1) / 2;  // the x rows without a kernel row are packed in pairs (r, r + R_PAIRS):
+    static constexpr int R_KROWS = KSPEC ? 0 : KH;                                // units (x_j, k_j), j < R_KROWS, come first
+    static constexpr int R_UNITS_PLANE = R_KROWS + R_PAIRS;   // consecutive units read consecutive rows (odd pitch: no bank conflicts)
     static constexpr int R_UNITS = G * R_UNITS_PLANE, O_UNITS = (G / 2) * HO;
     static constexpr int pad32(int n) { return (n + 31) / 32 * 32; }
     // FFT tasks = (unit, half); warps alternate halves so a warp runs one half only:  task t -> h = (t/32) % 2, unit = (t/64)*32 + t%32
@@ -137,7 +141,7 @@ HDN_HD bool fftc_load(int ph, const FftBufs &b, int unit, int h, float (&re)[32]
         if (unit >= Cfg::R_UNITS) return false;
         const int p = unit / Cfg::R_UNITS_PLANE, j = unit - p * Cfg::R_UNITS_PLANE;
         fftc_fold_row<Cfg>(b.rawx + p * Cfg::XPL + fft_x_row<Cfg>(j) * Cfg::WX, true, sgn, re);
-        if (j < Cfg::KH) {  // (x_j, k_j)
+        if (j < Cfg::R_KROWS) {  // (x_j, k_j)
             const float *krow = b.rawk + p * Cfg::KPL + j * Cfg::KW;
 #pragma unroll
             for (int n = 0; n < 32; ++n) {
@@ -183,7 +187,7 @@ template <class Cfg, int H>
 HDN_HD void fftc_store_R(const FftBufs &b, int unit, const float (&re)[32], const float (&im)[32]) {
     using namespace fft;
     const int p = unit / Cfg::R_UNITS_PLANE, j = unit - p * Cfg::R_UNITS_PLANE;
-    const bool ktype = j < Cfg::KH;
+    const bool ktype = j < Cfg::R_KROWS;
     float2 *xr = b.XR + p * Cfg::XR_PLANE;
     // first padded row of x row j (DEDUP: source row j stands for padded rows j + PH - HX, j + PH, j + PH + HX inside [0, HP))
     const int j2 = j + Cfg::R_PAIRS;

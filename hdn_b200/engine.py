@@ -122,9 +122,19 @@ class M1Engine:
 
     # ---- device-resident path ---------------------------------------------------------------------
     def bind(self, inputs):
-        """inputs: dict of DEVICE tensors shaped like make_inputs(...)."""
-        self.inp = inputs
+        """inputs: dict of DEVICE tensors shaped like make_inputs(...).  A template shared by the whole batch (ks / kl of batch size 1:
+        config 3, the tracker) has its row spectra taken here, once per template, for the transform-domain kernels."""
+        self.inp = dict(inputs)
         self.graph = None
+        w = self.w
+        if self.inp["ks"][0].shape[0] == 1 and self.B > 1:
+            spec = ops.xcorr_template_spectra(self.inp["ks"], w["sim_x"], w["sim_x"], False)
+            if spec is not None:
+                self.inp["ks_spec"] = spec
+            if self.full:
+                spec = ops.xcorr_template_spectra(self.inp["kl"], w["lp_x"], w["lp_x"], True)
+                if spec is not None:
+                    self.inp["kl_spec"] = spec
 
     def _launch(self, inp, out, B):
         L = _lib.lib()
@@ -134,15 +144,25 @@ class M1Engine:
         arr = vp * NPROB
         kB = inp["ks"][0].shape[0]
         kbs = 0 if (kB == 1 and B > 1) else C * w["sim_k"] ** 2
-        _lib.check(L.hdn_xcorr_dw_multi_f32(NPROB, arr(*[t.data_ptr() for t in inp["xs"]]), arr(*[t.data_ptr() for t in inp["ks"]]),
-                                            arr(*[t.data_ptr() for t in out["corr"]]), B, C, w["sim_x"], w["sim_x"], w["sim_k"], w["sim_k"], 0,
-                                            kbs, st), "K1")
+        if "ks_spec" in inp:
+            _lib.check(L.hdn_xcorr_dw_multi_spec_f32(NPROB, arr(*[t.data_ptr() for t in inp["xs"]]), arr(*[t.data_ptr() for t in inp["ks_spec"]]),
+                                                     arr(*[t.data_ptr() for t in out["corr"]]), B, C, w["sim_x"], w["sim_x"], w["sim_k"], w["sim_k"],
+                                                     0, st), "K1 (cached template spectra)")
+        else:
+            _lib.check(L.hdn_xcorr_dw_multi_f32(NPROB, arr(*[t.data_ptr() for t in inp["xs"]]), arr(*[t.data_ptr() for t in inp["ks"]]),
+                                                arr(*[t.data_ptr() for t in out["corr"]]), B, C, w["sim_x"], w["sim_x"], w["sim_k"], w["sim_k"], 0,
+                                                kbs, st), "K1")
         if not self.full:
             return
         kbs = 0 if (kB == 1 and B > 1) else C * w["lp_k"] ** 2
-        _lib.check(L.hdn_xcorr_dw_multi_f32(NPROB, arr(*[t.data_ptr() for t in inp["xl"]]), arr(*[t.data_ptr() for t in inp["kl"]]),
-                                            arr(*[t.data_ptr() for t in out["corr_lp"]]), B, C, w["lp_x"], w["lp_x"], w["lp_k"], w["lp_k"], 1,
-                                            kbs, st), "K2")
+        if "kl_spec" in inp:
+            _lib.check(L.hdn_xcorr_dw_multi_spec_f32(NPROB, arr(*[t.data_ptr() for t in inp["xl"]]), arr(*[t.data_ptr() for t in inp["kl_spec"]]),
+                                                     arr(*[t.data_ptr() for t in out["corr_lp"]]), B, C, w["lp_x"], w["lp_x"], w["lp_k"], w["lp_k"],
+                                                     1, st), "K2 (cached template spectra)")
+        else:
+            _lib.check(L.hdn_xcorr_dw_multi_f32(NPROB, arr(*[t.data_ptr() for t in inp["xl"]]), arr(*[t.data_ptr() for t in inp["kl"]]),
+                                                arr(*[t.data_ptr() for t in out["corr_lp"]]), B, C, w["lp_x"], w["lp_x"], w["lp_k"], w["lp_k"], 1,
+                                                kbs, st), "K2")
         p = lambda t: vp(t.data_ptr())  # noqa: E731
         _lib.check(L.hdn_logpolar_f32(p(inp["img"]), None, 0.0, p(out["x_lp"]), B, 3, w["img"], w["img"], w["S"], st), "K3")
         _lib.check(L.hdn_dlt_warp_f32(p(inp["src"]), p(inp["off"]), p(inp["gray"]), None, None, p(out["H"]), p(out["warp"]), B, 1, 127, 127, st),

@@ -158,7 +158,7 @@ class HeadEngine:
                     "center": e(B, 2), "idx_lp": e(B, dt=torch.int64), "pscore_lp": e(B, dt=torch.float64), "score_lp": e(B), "sim_lp": e(B, 4),
                     "H": e(B, 3, 3), "x_lp": e(B, 3, n["S"], n["S"]), "warp": e(B, 1, 127, 127)}
         self.window = torch.from_numpy(np.outer(np.hanning(self.N), np.hanning(self.N)).flatten()).to(dev)
-        self.k_sim = self.k_lp = None
+        self.k_sim = self.k_lp = self.k_sim_spec = self.k_lp_spec = None
         self.inp = None
         self.launches_per_chunk = 11
 
@@ -170,6 +170,10 @@ class HeadEngine:
             return ops.conv_gemm_multi(xs, w.packed["kernel"], w.raw["kernel_scale"], w.raw["kernel_shift"], ksize=3, relu=True, valid=True)
         self.k_sim = kernels(self.w_sim, zf)
         self.k_lp = kernels(self.w_lp, zf_lp)
+        # a template shared by the batch: its row spectra for the transform-domain correlation, once (None: no such kernel for the shape)
+        shared = self.k_sim[0].shape[0] == 1
+        self.k_sim_spec = ops.xcorr_template_spectra(self.k_sim, self.s_sim_hw, self.s_sim_hw, False) if shared else None
+        self.k_lp_spec = ops.xcorr_template_spectra(self.k_lp, self.s_lp_hw, self.s_lp_hw, True) if shared else None
         return self
 
     def bind(self, inputs):
@@ -188,14 +192,17 @@ class HeadEngine:
         p = lambda t: vp(t.data_ptr())  # noqa: E731
         fl3 = ctypes_floats
 
-        def head(w, xf, S, F, P, ks, circular, s_hw, k_hw, N, Lloc, maps, scores, window, winf):
+        def head(w, xf, S, F, P, ks, circular, s_hw, k_hw, N, Lloc, maps, scores, window, winf, spec=None):
             xs = [xf[i // 2][s0:s0 + b] for i in range(NPROB)]
             _lib.check(L.hdn_conv_gemm_multi_f32(NPROB, pa(xs), pa(w.packed["search"]), pa(w.raw["search_scale"]), pa(w.raw["search_shift"]), pa(S), b,
                                                  C, C, s_hw + 2, s_hw + 2, 3, 1, 1, 1, st), "conv_search")
             kB = ks[0].shape[0]
             kk = [k if kB == 1 else k[lo:hi] for k in ks]
             kbs = 0 if (kB == 1 and b > 1) else C * k_hw * k_hw
-            _lib.check(L.hdn_xcorr_dw_multi_f32(NPROB, pa(S), pa(kk), pa(F), b, C, s_hw, s_hw, k_hw, k_hw, int(circular), kbs, st), "xcorr")
+            if spec is not None:
+                _lib.check(L.hdn_xcorr_dw_multi_spec_f32(NPROB, pa(S), pa(spec), pa(F), b, C, s_hw, s_hw, k_hw, k_hw, int(circular), st), "xcorr (spectra)")
+            else:
+                _lib.check(L.hdn_xcorr_dw_multi_f32(NPROB, pa(S), pa(kk), pa(F), b, C, s_hw, s_hw, k_hw, k_hw, int(circular), kbs, st), "xcorr")
             if Lloc == 2:
                 _lib.check(L.hdn_head_project_multi_f32(NPROB, pa(F), pa(w.packed["hidden"]), pa(w.raw["hidden_scale"]), pa(w.raw["hidden_shift"]),
                                                         pa(w.raw["w2"]), pa(P), b, C, N, N, 2, st), "head project")
@@ -213,9 +220,9 @@ class HeadEngine:
                                             b, Lloc, N, st), "head score")
 
         head(self.w_sim, inp["xf"], self.S, self.F, self.P, self.k_sim, False, self.s_sim_hw, self.k_sim_hw, self.N, 2, (o["cls"], o["loc"]),
-             (o["idx"], o["pscore"], o["score"], o["center"]), self.window, WIN_INFL)
+             (o["idx"], o["pscore"], o["score"], o["center"]), self.window, WIN_INFL, self.k_sim_spec)
         head(self.w_lp, inp["xf_lp"], self.S_lp, self.F_lp, self.P_lp, self.k_lp, True, self.s_lp_hw, self.k_lp_hw, self.N_lp, 4,
-             (o["cls_lp"], o["loc_lp"]), (o["idx_lp"], o["pscore_lp"], o["score_lp"], o["sim_lp"]), None, 0.0)
+             (o["cls_lp"], o["loc_lp"]), (o["idx_lp"], o["pscore_lp"], o["score_lp"], o["sim_lp"]), None, 0.0, self.k_lp_spec)
         n = self.n
         k3 = L.hdn_logpolar_u8 if inp["img"].dtype == torch.uint8 else L.hdn_logpolar_f32
         _lib.check(k3(p(inp["img"][s0:s0 + b]), None, 0.0, p(o["x_lp"][lo:hi]), b, 3, n["img"], n["img"], n["S"], st), "K3")

@@ -4,6 +4,7 @@ Each callable replaces the reference function cited in its docstring; torch is u
 device memory and the current stream.  CPU tensors are rejected -- there is no CPU fallback.
 """
 import ctypes
+import os
 import math
 
 import torch
@@ -120,6 +121,47 @@ def xcorr_depthwise_multi(xs, kernels, circular=False, outs=None):
         st = _lib.lib().hdn_xcorr_dw_multi_f32(n, arr(*[x.data_ptr() for x in xs]), arr(*[k.data_ptr() for k in kernels]),
                                                arr(*[o.data_ptr() for o in outs]), B, C, Hx, Wx, Hk, Wk, int(circular), kbs, _stream())
     _lib.check(st, "hdn_xcorr_dw_multi_f32")
+    return outs
+
+
+TEMPLATE_SPECTRA = os.environ.get("HDN_B200_TEMPLATE_SPECTRA", "1") != "0"  # cached row spectra for shared templates (A/B switch)
+
+
+def xcorr_template_spectra(kernels, Hx, Wx, circular=False):
+    """Row spectra of n <= 8 SHARED templates [1,C,Hk,Wk] (one launch), for xcorr_depthwise_multi(..., spectra=...): a template that
+    serves many pairs / frames has its row transforms taken once (hdn_xcorr_template_spectra_f32).  -> list of 1-D float32 tensors, or
+    None when the shape has no cached-spectra kernel (everything but the 29x29 templates at 256/512 crops) or the switch is off."""
+    kernels = [_dev(k, "kernel") for k in kernels]
+    Bk, C, Hk, Wk = kernels[0].shape
+    if Bk != 1 or any(tuple(k.shape) != (1, C, Hk, Wk) for k in kernels):
+        raise RuntimeError("xcorr_template_spectra: templates must be [1,C,Hk,Wk] and share one shape")
+    nf = int(_lib.lib().hdn_xcorr_spectra_floats(C, Hx, Wx, Hk, Wk, int(circular))) if TEMPLATE_SPECTRA else 0
+    if nf == 0 or any(k.data_ptr() % 16 for k in kernels):
+        return None
+    spectra = [torch.empty(nf, device=kernels[0].device, dtype=torch.float32) for _ in kernels]
+    n = len(kernels)
+    arr = _vp * n
+    with _on_device(kernels[0]):
+        st = _lib.lib().hdn_xcorr_template_spectra_f32(n, arr(*[k.data_ptr() for k in kernels]), arr(*[t.data_ptr() for t in spectra]), C, Hx, Wx,
+                                                       Hk, Wk, int(circular), _stream())
+    _lib.check(st, "hdn_xcorr_template_spectra_f32")
+    return spectra
+
+
+def xcorr_depthwise_multi_spec(xs, spectra, Hk, Wk, circular=False, outs=None):
+    """xcorr_depthwise_multi for a shared template given by its cached row spectra (xcorr_template_spectra)."""
+    n = len(xs)
+    xs = [_dev(x, "x") for x in xs]
+    B, C, Hx, Wx = xs[0].shape
+    if any(tuple(x.shape) != (B, C, Hx, Wx) for x in xs) or len(spectra) != n:
+        raise RuntimeError("xcorr_depthwise_multi_spec: all problems must share one shape")
+    Ho, Wo = xcorr_out_hw(Hx, Wx, Hk, Wk, circular)
+    outs = [_out(None if outs is None else outs[i], (B, C, Ho, Wo), xs[0], "outs[%d]" % i) for i in range(n)]
+    arr = _vp * n
+    with _on_device(xs[0]):
+        st = _lib.lib().hdn_xcorr_dw_multi_spec_f32(n, arr(*[x.data_ptr() for x in xs]), arr(*[t.data_ptr() for t in spectra]),
+                                                    arr(*[o.data_ptr() for o in outs]), B, C, Hx, Wx, Hk, Wk, int(circular), _stream())
+    _lib.check(st, "hdn_xcorr_dw_multi_spec_f32")
     return outs
 
 

@@ -79,6 +79,18 @@ enum hdn_xcorr_algo { HDN_XCORR_AUTO = 0, HDN_XCORR_DIRECT = 1, HDN_XCORR_FFT = 
 int hdn_xcorr_set_algo(int algo);
 int hdn_xcorr_uses_fft(int C, int Hx, int Wx, int Hk, int Wk, int circular, int64_t k_batch_stride);
 
+/* Shared template with cached row spectra (29x29 templates at 256/512 crops: 61x61 plain, 29x29 circular).  A template that serves
+ * many pairs -- config 3's broadcast template, the tracker's per-sequence template (hdn/tracker/hdn_tracker_proj_e2e.py:86-118 computes
+ * it once in init) -- has its 29 row transforms taken ONCE: hdn_xcorr_template_spectra_f32 writes K'(u,f) of n templates [C,Hk,Wk]
+ * into spectra buffers of hdn_xcorr_spectra_floats(...) floats each (0 = the shape has no such kernel), and
+ * hdn_xcorr_dw_multi_spec_f32 is hdn_xcorr_dw_multi_f32 with k_batch_stride == 0 reading those spectra instead of the templates
+ * (same result to fp32 rounding: ~3e-7 of max|out|).  All pointers 16-byte aligned, C % 4 == 0. */
+int64_t hdn_xcorr_spectra_floats(int C, int Hx, int Wx, int Hk, int Wk, int circular);
+int hdn_xcorr_template_spectra_f32(int n, const float *const *k, float *const *spectra, int C, int Hx, int Wx, int Hk, int Wk, int circular,
+                                   hdn_stream_t stream);
+int hdn_xcorr_dw_multi_spec_f32(int n, const float *const *x, const float *const *spectra, float *const *out, int B, int C, int Hx, int Wx,
+                                int Hk, int Wk, int circular, hdn_stream_t stream);
+
 /* 1 if (shape, 16-byte aligned pointers) takes the TMA-staged kernel, 0 if it takes the generic one-thread-per-output kernel. */
 int hdn_xcorr_is_staged(int C, int Hx, int Wx, int Hk, int Wk, int circular, int64_t k_batch_stride);
 /* How many correlation launches of this process fell to the generic kernel (shape outside the tiled table, unaligned pointers or a

@@ -151,7 +151,7 @@ def test_fused_head_tail_equals_reference_ops(B, N, L):
     assert torch.equal(buf[:20 * B + 4 * B * L], buf2[:20 * B + 4 * B * L])  # (the buffer's tail is alignment padding)
 
 
-@pytest.mark.parametrize("workload,B,chunk,shared,u8", [("127/255", 5, 2, False, False), ("127/255", 3, 4, True, True), ("256/512", 2, 1, False, True)])
+@pytest.mark.parametrize("workload,B,chunk,shared,u8", [("127/255", 5, 2, False, False), ("127/255", 3, 4, True, True), ("256/512", 2, 1, False, True), ("256/512", 3, 2, True, True)])
 def test_head_engine_equals_cpu_port(workload, B, chunk, shared, u8):
     """The fused chain from neck features (HeadEngine: conv_search -> correlation -> 1x1 tail -> level sum + K6, K3, K5 + K4),
     device-resident and through the pinned-host pipeline, against the CPU port of the reference's own torch calls

@@ -195,6 +195,74 @@ def test_fft_kernel_variants_equal_the_phased_kernel_bitwise(shape, variant):
         ops().set_xcorr_algo("auto")
 
 
+@pytest.mark.parametrize("shape", [(1, 256, 61, 61, 0), (5, 256, 61, 61, 0), (64, 256, 61, 61, 0), (1, 8, 29, 29, 1), (7, 256, 29, 29, 1), (64, 256, 29, 29, 1)])
+@pytest.mark.parametrize("variant", ["auto", "fft_phased", "fft_pipe"])
+def test_shared_template_with_cached_spectra_equals_the_per_pair_path(shape, variant):
+    """A shared template's row spectra taken once (hdn_xcorr_template_spectra_f32) and consumed by hdn_xcorr_dw_multi_spec_f32 give the
+    result of the per-pair kernels (which re-transform the template for every pair) to fp32 rounding, the C oracle's within the parity
+    tolerance, for both kernel schedules, 3 problems per launch, repeated (no race between the spectra landing and the column stage)."""
+    B, C, Hx, Wx, circ = shape
+    Hk = Wk = 29
+    fn = ops().xcorr_depthwise_circular if circ else ops().xcorr_depthwise
+    gen = torch.Generator(device=DEV).manual_seed(B * 17 + C + Hx)
+    xs = [torch.randn((B, C, Hx, Wx), device=DEV, generator=gen) + 0.3 * i for i in range(3)]
+    ks = [torch.randn((1, C, Hk, Wk), device=DEV, generator=gen) * 0.1 for _ in range(3)]
+    spectra = ops().xcorr_template_spectra(ks, Hx, Wx, bool(circ))
+    assert spectra is not None and len(spectra) == 3
+    try:
+        ops().set_xcorr_algo("fft_phased")
+        want = [fn(x, k) for x, k in zip(xs, ks)]
+        ops().set_xcorr_algo(variant)
+        first = None
+        for _ in range(3):
+            got = ops().xcorr_depthwise_multi_spec(xs, spectra, Hk, Wk, bool(circ))
+            for g, w_ in zip(got, want):
+                assert float((g - w_).abs().max()) <= 2e-6 * float(w_.abs().max())
+            if first is None:
+                first = [g.clone() for g in got]
+            assert all(torch.equal(a, b) for a, b in zip(got, first))
+    finally:
+        ops().set_xcorr_algo("auto")
+    b = B // 2
+    ref = c_oracle.xcorr_dw(xs[1][b:b + 1].cpu().numpy(), ks[1].cpu().numpy(), bool(circ))
+    assert_close(first[1][b:b + 1].cpu().numpy(), ref, what="cached spectra %s" % (shape,))
+    assert np.abs(first[1][b:b + 1].cpu().numpy() - ref).max() <= 5e-6 * np.abs(ref).max()
+
+
+def test_m1_engine_shared_template_takes_the_cached_spectra_path():
+    """M1Engine.bind gives a batch-shared template its row spectra once; the chain's results equal the per-pair path's (arg-max indices
+    bit-exact, maps to fp32 rounding) and a per-pair-template batch never takes that path."""
+    from hdn_b200 import engine
+    host = engine.make_inputs("256/512", 4, seed=3, shared_template=True)
+    dev_in = {k: ([t.to(DEV) for t in v] if isinstance(v, list) else v.to(DEV)) for k, v in host.items()}
+    eng = engine.M1Engine("256/512", 4, DEV, shared_template=True, use_graph=False)
+    eng.bind(dev_in)
+    assert "ks_spec" in eng.inp and "kl_spec" in eng.inp
+    got = {k: ([t.clone() for t in v] if isinstance(v, list) else v.clone()) for k, v in eng.run().items()}
+    try:
+        ops().TEMPLATE_SPECTRA = False
+        eng.bind(dev_in)
+        assert "ks_spec" not in eng.inp
+        want = eng.run()
+    finally:
+        ops().TEMPLATE_SPECTRA = True
+    for key in ("corr", "corr_lp"):
+        for a, b in zip(got[key], want[key]):
+            assert float((a - b).abs().max()) <= 2e-6 * float(b.abs().max())
+    assert torch.equal(got["idx"], want["idx"]) and torch.equal(got["idx_lp"], want["idx_lp"]) and torch.equal(got["H"], want["H"])
+    per_pair = engine.make_inputs("256/512", 4, seed=3, shared_template=False)
+    eng.bind({k: ([t.to(DEV) for t in v] if isinstance(v, list) else v.to(DEV)) for k, v in per_pair.items()})
+    assert "ks_spec" not in eng.inp
+
+
+def test_template_spectra_only_where_a_kernel_exists():
+    k = torch.randn((1, 256, 5, 5), device=DEV)
+    assert ops().xcorr_template_spectra([k], 29, 29, False) is None            # native 127/255: direct kernels, nothing to cache
+    assert ops().xcorr_template_spectra([torch.randn((1, 256, 15, 15), device=DEV)], 39, 39, False) is None
+    with pytest.raises((ValueError, RuntimeError)):
+        ops().xcorr_template_spectra([torch.randn((2, 256, 29, 29), device=DEV)], 61, 61, False)  # per-pair templates have no shared spectra
+
+
 def test_xcorr_untiled_shape_runs_generic_kernel_and_is_counted():
     """A crop size outside the tiled table (INSTANCE_SIZE 287 -> 33x33 search features) still gives the reference's result,
     and the library counts it (hdn_xcorr_generic_launches) instead of degrading silently."""
