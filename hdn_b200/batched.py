@@ -12,7 +12,6 @@ to cuDNN/cuBLAS choosing different (fp32) algorithms for different batch sizes.
 """
 from concurrent.futures import ThreadPoolExecutor
 
-import numpy as np
 
 from hdn_b200 import compat
 

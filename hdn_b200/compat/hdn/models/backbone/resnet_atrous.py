@@ -15,7 +15,7 @@ import math
 
 import torch.nn as nn
 
-from hdn_b200.convs import conv3x3, conv_bn_act
+from hdn_b200.convs import conv_bn_act
 
 __all__ = ["ResNet", "resnet18", "resnet34", "resnet50"]
 

@@ -25,7 +25,7 @@ import numpy as np
 import torch
 
 from hdn.core.config import cfg
-from hdn.tracker.base_tracker import crop_window, to_model_tensor
+from hdn.tracker.base_tracker import crop_window
 from hdn.tracker.hdn_tracker import decode_center, decode_logpolar, hdnTracker
 from hdn.utils.point import Point
 from hdn.utils.transform import img_rot_around_center, rot_scale_around_center_shift_tran

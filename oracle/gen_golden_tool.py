@@ -31,7 +31,7 @@ OUT = os.path.join(REPO, "tests", "golden", "pot_results")
 
 
 def main():
-    from hdn_b200 import pot_fixture, synthetic
+    from hdn_b200 import pot_fixture
     import gen_golden_model as G
     tmp = tempfile.mkdtemp(prefix="hdn_tool_")
     try:

@@ -3,7 +3,6 @@ calls the reference's tracker makes (hdn_tracker_proj_e2e.py:154, base_tracker.p
 oracle the device-side pre-processing kernels (hdn_b200/csrc/preproc.cu) are checked against."""
 import cv2
 import numpy as np
-import pytest
 
 from oracle import cv_port
 

@@ -93,7 +93,6 @@ def test_homo_warp_quirks():
 
 
 def test_linspace_matches_torch():
-    import ctypes
     for n in (127, 24, 40, 5):
         ref = torch.linspace(-1.0, 1.0, n).numpy()
         step = np.float32(2.0) / np.float32(n - 1)
