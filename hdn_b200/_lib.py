@@ -32,6 +32,7 @@ SIGNATURES = {
     "hdn_conv_gemm_supported": (_ci, [_ci, _ci, _ci, _ci]),
     "hdn_conv_gemm_set_splitk": (_ci, [_ci]),
     "hdn_conv_gemm_set_pdl": (_ci, [_ci]),
+    "hdn_conv_gemm_set_ts": (_ci, [_ci]),
     "hdn_conv_gemm_set_shift": (_ci, [_ci]),
     "hdn_conv_pack_weight_f32": (_ci, [_vp, _vp, _ci, _ci, _vp]),
     "hdn_conv_gemm_f32": (_ci, [_vp, _vp, _vp, _vp, _vp, _vp, _ci, _ci, _ci, _ci, _ci, _ci, _ci, _ci, _ci, _vp]),
@@ -67,6 +68,8 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)  # AttributeError if the ABI and the binding drift apart
             fn.restype, fn.argtypes = res, args
+        if "HDN_B200_CONV_TS" in os.environ:  # A/B switch of the large-launch convolution kernel (see hdn_conv_gemm_set_ts)
+            L.hdn_conv_gemm_set_ts(int(os.environ["HDN_B200_CONV_TS"] != "0"))
         _lib = L
     return _lib
 

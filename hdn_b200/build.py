@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libhdn_b200.so")
-SOURCES = ["api.cu", "xcorr.cu", "xcorr_fft.cu", "warp.cu", "score.cu", "conv_gemm.cu", "conv_shift.cu", "conv_small.cu", "preproc.cu"]
+SOURCES = ["api.cu", "xcorr.cu", "xcorr_fft.cu", "warp.cu", "score.cu", "conv_gemm.cu", "conv_gemm_ts.cu", "conv_shift.cu", "conv_small.cu", "preproc.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
 
 

@@ -447,6 +447,7 @@ extern "C" int hdn_conv_gemm_supported(int Cin, int Cout, int ksize, int dilatio
 
 static int g_conv_splitk = 1;  // hdn_conv_gemm_set_splitk (A/B switch; the result is deterministic either way)
 static int g_conv_shift = 1;   // hdn_conv_gemm_set_shift: conv_shift.cu for 3x3 'valid' layers (A/B switch)
+static int g_conv_ts = 1;      // hdn_conv_gemm_set_ts: conv_gemm_ts.cu (activations in tensor memory) for the large launches (A/B switch; default on)
 
 static int conv_gemm_multi(int n, const float *const *x, const float *const *wpk, const float *const *scale, const float *const *shift,
                            const float *const *residual, const float *const *w2, float *const *out, int B, int Cin, int Cout, int H, int W,
@@ -484,7 +485,7 @@ static int conv_gemm_multi(int n, const float *const *x, const float *const *wpk
     const int mtiles = (Cout + CG_BM - 1) / CG_BM;
     const long long tiles128 = (long long)((a.Ho * a.Wo + 127) / 128) * mtiles * B * n;
     // small problems (tracking batch sizes): narrower pixel tiles put more CTAs on the 148 SMs ...
-    if (tiles128 >= 2 * sm_count()) return launch_conv_gemm<128, 3, 0>(a, n, st);
+    if (tiles128 >= 2 * sm_count()) return g_conv_ts ? launch_conv_gemm_ts(a, n, st) : launch_conv_gemm<128, 3, 0>(a, n, st);
     // ... and when even those leave most SMs idle (a 15x15 or 31x31 map at batch 1), K is split over a cluster of 2 / 4 / 8 CTAs
     const long long ctas = (long long)((a.Ho * a.Wo + 63) / 64) * mtiles * B * n;
     const int nkb = a.taps * Cin / CG_BK;
@@ -525,6 +526,11 @@ extern "C" int hdn_head_project_multi_f32(int n, const float *const *x_host, con
     if (!w2_host) return HDN_ERR_NULL;
     return conv_gemm_multi(n, x_host, wpk_host, scale_host, shift_host, nullptr, w2_host, part_host, B, C, C, H, W, 1, 1, 0, 1, L,
                            (cudaStream_t)stream);
+}
+
+extern "C" int hdn_conv_gemm_set_ts(int enable) {
+    g_conv_ts = enable ? 1 : 0;
+    return HDN_OK;
 }
 
 extern "C" int hdn_conv_gemm_set_pdl(int enable) {

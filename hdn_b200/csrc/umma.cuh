@@ -66,6 +66,8 @@ struct ConvGemmArgs {
     int stride;       // 1 or 2
 };
 
+// conv_gemm_ts.cu: the large launches with the activations in tensor memory (A operand from TMEM)
+int launch_conv_gemm_ts(const ConvGemmArgs &a, int nprob, cudaStream_t st);
 // conv_shift.cu: 3x3 'valid' convolutions with the activations staged ONCE per channel block (9 shifted operand windows).
 bool conv_shift_applicable(const ConvGemmArgs &a, int ksize, int valid);
 int launch_conv_shift(const ConvGemmArgs &a, int nprob, cudaStream_t st);

@@ -476,6 +476,11 @@ def set_conv_splitk(enable=True):
     _lib.check(_lib.lib().hdn_conv_gemm_set_splitk(int(bool(enable))), "hdn_conv_gemm_set_splitk")
 
 
+def set_conv_ts(enable=True):
+    """Large convolution launches with the activations in tensor memory (conv_gemm_ts.cu); False = shared-memory operands (A/B runs)."""
+    _lib.check(_lib.lib().hdn_conv_gemm_set_ts(int(bool(enable))), "hdn_conv_gemm_set_ts")
+
+
 def set_conv_pdl(enable=True):
     """Programmatic dependent launch between consecutive tcgen05 convolutions (default on); False = plain stream order (A/B runs)."""
     _lib.check(_lib.lib().hdn_conv_gemm_set_pdl(int(bool(enable))), "hdn_conv_gemm_set_pdl")

@@ -169,6 +169,10 @@ int hdn_conv_gemm_set_splitk(int enable);
  * TMEM allocation, first weight records) overlaps the tail of the previous one; its activation reads and all its writes wait for
  * the previous kernel's completion (griddepcontrol.wait).  enable = 0: plain stream order (A/B runs); default on. */
 int hdn_conv_gemm_set_pdl(int enable);
+/* Large launches (>= 2 CTAs per SM of 128 x 128 tiles) run conv_gemm_ts.cu: the split activations go from registers straight into
+ * tensor memory and the MMAs take their A operand from there, so shared memory carries the weight records only.  enable = 0: the
+ * shared-memory-operand kernel for every launch (A/B runs). */
+int hdn_conv_gemm_set_ts(int enable);
 /* 3x3 'valid' layers with W <= 63 (the heads' conv_search / conv_kernel) run a kernel that stages the activations once per
  * 32-channel block and feeds the nine taps as shifted windows of that tile (conv_shift.cu).  mode = 1 (default): on; 2: on, and
  * clusters of two neighbouring pixel tiles share every weight record through TMA multicast (built and correct, measured slower:

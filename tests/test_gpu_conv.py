@@ -410,3 +410,50 @@ def test_programmatic_dependent_launch_chain_equals_plain_stream_order(batch):
                 assert all(torch.equal(a, b) for a, b in zip(outs, want))
         finally:
             ops.set_conv_pdl(True)
+
+
+TS_CASES = [  # B, Cin, Cout, H, W, k, stride, pad, dilation  -- all large enough (>= 2 x 148 tiles of 128 x 128) to take the big-launch path
+    (40, 512, 256, 31, 31, 1, 1, 0, 1),
+    (24, 256, 256, 31, 31, 3, 1, 2, 2),
+    (12, 512, 512, 31, 31, 3, 1, 4, 4),
+    (48, 128, 128, 63, 63, 3, 2, 1, 1),
+    (12, 64, 64, 63, 63, 3, 1, 1, 1),
+    (10, 64, 256, 63, 63, 1, 1, 0, 1),
+    (40, 256, 512, 31, 31, 1, 2, 0, 1),
+    (3, 1024, 2048, 63, 63, 1, 1, 0, 1),
+]
+
+
+@pytest.mark.parametrize("case", TS_CASES)
+def test_conv_gemm_with_activations_in_tensor_memory(case):
+    """conv_gemm_ts.cu (A operand = split activations written by tcgen05.st into TMEM, B = packed weight records in shared memory,
+    pixel-major accumulator, transpose-free epilogue) against fp64 and against the shared-memory-operand kernel it replaces for large
+    launches: same 3xTF32 terms, same chunking, so fp32-accurate and equal to the other kernel up to the MMA's internal summation."""
+    from hdn_b200 import ops
+    B, Cin, Cout, H, W, k, stride, pad, d = case
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(Cin + Cout + H + k)
+    x = torch.randn(B, Cin, H, W, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, k, k, device="cuda", generator=g) * (2.0 / (Cin * k * k)) ** 0.5
+    scale = 1 + 0.1 * torch.randn(Cout, device="cuda", generator=g)
+    shift = 0.1 * torch.randn(Cout, device="cuda", generator=g)
+    wp = ops.pack_conv_weight(w)
+    y64 = F.conv2d(x[:2].double(), w.double(), stride=stride, padding=pad, dilation=d) * scale.double().view(1, -1, 1, 1) + shift.double().view(1, -1, 1, 1)
+    res = torch.randn((B,) + tuple(y64.shape[1:]), device="cuda", generator=g)
+    want64 = F.relu(y64 + res[:2].double())
+    try:
+        ops.set_conv_ts(False)
+        old = ops.conv_gemm(x, wp, scale, shift, res, ksize=k, dilation=d, relu=True, stride=stride, padding=pad, cout=Cout)
+        ops.set_conv_ts(True)
+        new = ops.conv_gemm(x, wp, scale, shift, res, ksize=k, dilation=d, relu=True, stride=stride, padding=pad, cout=Cout)
+        again = ops.conv_gemm(x, wp, scale, shift, res, ksize=k, dilation=d, relu=True, stride=stride, padding=pad, cout=Cout)
+        plain = ops.conv_gemm(x, wp, ksize=k, dilation=d, stride=stride, padding=pad, cout=Cout)
+    finally:
+        ops.set_conv_ts(True)
+    den = float(want64.abs().max())
+    assert tuple(new.shape) == tuple(old.shape)
+    assert torch.equal(new, again)
+    assert float((new[:2].double() - want64).abs().max()) / den < 1e-5
+    assert float((new - old).abs().max()) / den < 5e-6
+    want_plain = F.conv2d(x[:1].double(), w.double(), stride=stride, padding=pad, dilation=d)
+    assert float((plain[:1].double() - want_plain).abs().max()) / float(want_plain.abs().max()) < 1e-5
