@@ -476,16 +476,20 @@ static int conv_gemm_multi(int n, const float *const *x, const float *const *wpk
     a.B = B; a.L = L; a.splitk = 1;
     a.Cin = Cin; a.Cout = Cout; a.H = H; a.W = W; a.taps = ksize * ksize; a.dil = dilation; a.relu = relu;
     a.Ho = Ho_; a.Wo = Wo_; a.off = (ksize / 2) * dilation - pad; a.stride = stride;
-    // 3x3 'valid' layers (the heads' conv_search / conv_kernel): activations staged once per channel block, taps = shifted windows
+    const int mtiles = (Cout + CG_BM - 1) / CG_BM;
+    const long long tiles128 = (long long)((a.Ho * a.Wo + 127) / 128) * mtiles * B * n;
+    // large launches (>= 2 CTAs per SM of 128 x 128 tiles): activation operand in tensor memory (conv_gemm_ts.cu).  It also beats the
+    // shifted-window kernel below on the heads' batched conv_search launches (fused chain 14.05 -> 13.29 ms per 64 pairs).
+    if (!w2 && g_conv_ts && tiles128 >= 2 * sm_count()) return launch_conv_gemm_ts(a, n, st);
+    // 3x3 'valid' layers (the heads' conv_search / conv_kernel) at tracking batch sizes: activations staged once per channel block,
+    // taps = shifted windows
     if (!w2 && g_conv_shift && conv_shift_applicable(a, ksize, valid)) return launch_conv_shift(a, n, st);
     if (w2) {  // fused second 1x1: narrow pixel tiles (the projection's staging pitch), L <= 8
         if (L < 1 || L > 8) return HDN_ERR_UNSUPPORTED;
         return launch_conv_gemm<64, 4, 0, true>(a, n, st);
     }
-    const int mtiles = (Cout + CG_BM - 1) / CG_BM;
-    const long long tiles128 = (long long)((a.Ho * a.Wo + 127) / 128) * mtiles * B * n;
     // small problems (tracking batch sizes): narrower pixel tiles put more CTAs on the 148 SMs ...
-    if (tiles128 >= 2 * sm_count()) return g_conv_ts ? launch_conv_gemm_ts(a, n, st) : launch_conv_gemm<128, 3, 0>(a, n, st);
+    if (tiles128 >= 2 * sm_count()) return launch_conv_gemm<128, 3, 0>(a, n, st);
     // ... and when even those leave most SMs idle (a 15x15 or 31x31 map at batch 1), K is split over a cluster of 2 / 4 / 8 CTAs
     const long long ctas = (long long)((a.Ho * a.Wo + 63) / 64) * mtiles * B * n;
     const int nkb = a.taps * Cin / CG_BK;

@@ -13,6 +13,9 @@ wl = sys.argv[1] if len(sys.argv) > 1 else "256/512"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 chunks = [int(c) for c in sys.argv[3].split(",")] if len(sys.argv) > 3 else [2, 4, 8]
 IT = int(os.environ.get("HEAD_BENCH_ITERS", "10"))
+if "HEAD_BENCH_SHIFT" in os.environ:  # 0: conv_search through the generic implicit GEMM (tensor-memory-operand kernel for large launches)
+    from hdn_b200 import ops as _ops
+    _ops.set_conv_shift(int(os.environ["HEAD_BENCH_SHIFT"]))
 dev = torch.device("cuda", 0)
 host = he.make_inputs(wl, B, seed=1, pin=True, u8_crop=True)
 up = lambda v: [t.to(dev) for t in v] if isinstance(v, list) else v.to(dev)  # noqa: E731

@@ -270,9 +270,10 @@ def test_sanitizer_smoke_shapes():
 
 def test_lockstep_batch_equals_single_sequence_tracking():
     """4 sequences advanced in lock-step (one batched network call per stage) == each tracked alone.  Every kernel computes a pair's
-    outputs in the same order whatever the batch size -- except that batch-1 convolutions split K over a cluster (another fp32
-    summation order), and the free-running tracker of UNTRAINED weights turns a last-bit difference at a near-tie of the arg-max
-    into pixels.  So: split-K off -> the trajectories must agree within fp32 noise over all frames; split-K on -> on the first frame."""
+    outputs in the same order whatever the batch size -- except that the convolution DISPATCH depends on the launch size (batch-1
+    layers split K over a cluster, large launches take the tensor-memory-operand kernel: other fp32 summation orders), and the
+    free-running tracker of UNTRAINED weights turns a last-bit difference at a near-tie of the arg-max into pixels.  So: with the
+    size-dependent kernels off the trajectories must agree within fp32 noise over all frames; with the default dispatch on the first."""
     import synth
     from hdn.tracker.tracker_builder import build_tracker
     from hdn_b200 import ops, runner
@@ -281,12 +282,14 @@ def test_lockstep_batch_equals_single_sequence_tracking():
     diag = float(np.hypot(*seqs[0][0][0].shape[:2]))
     try:
         ops.set_conv_splitk(False)
+        ops.set_conv_ts(False)
         polys, _ = runner.track_lockstep(model, seqs)
         for s, (frames, gt) in enumerate(seqs):
             alone, _ = runner.track_sequence(build_tracker(model), frames, gt)
             assert np.abs(polys[s] - alone).max() <= 1e-3 * diag, s
     finally:
         ops.set_conv_splitk(True)
+        ops.set_conv_ts(True)
     polys, _ = runner.track_lockstep(model, seqs)
     for s, (frames, gt) in enumerate(seqs):
         alone, _ = runner.track_sequence(build_tracker(model), frames, gt)
