@@ -26,6 +26,8 @@
 //   * a dedicated warp's elected lane issues 4 k-steps x 3 tcgen05.mma (kind::tf32, M=128, N=BN, K=8) per block and commits
 //     them to the mbarrier that frees the stage.
 // Epilogue: tcgen05.ld (32 lanes x 32b x 16 columns) -> y = acc*scale[co] + shift[co] (+ residual) (ReLU) -> global NCHW.
+#include <cstdlib>
+
 #include "umma.cuh"
 
 namespace hdn {
@@ -480,7 +482,8 @@ static int conv_gemm_multi(int n, const float *const *x, const float *const *wpk
     const long long tiles128 = (long long)((a.Ho * a.Wo + 127) / 128) * mtiles * B * n;
     // large launches (>= 2 CTAs per SM of 128 x 128 tiles): activation operand in tensor memory (conv_gemm_ts.cu).  It also beats the
     // shifted-window kernel below on the heads' batched conv_search launches (fused chain 14.05 -> 13.29 ms per 64 pairs).
-    if (!w2 && g_conv_ts && tiles128 >= 2 * sm_count()) return launch_conv_gemm_ts(a, n, st);
+    static const int ts_min_pct = getenv("HDN_B200_TS_MIN_TILES_PCT") ? atoi(getenv("HDN_B200_TS_MIN_TILES_PCT")) : 60;  // % of the SM count (sweep: DESIGN.md K7d)
+    if (!w2 && g_conv_ts && tiles128 * 100 >= (long long)ts_min_pct * sm_count()) return launch_conv_gemm_ts(a, n, st);
     // 3x3 'valid' layers (the heads' conv_search / conv_kernel) at tracking batch sizes: activations staged once per channel block,
     // taps = shifted windows
     if (!w2 && g_conv_shift && conv_shift_applicable(a, ksize, valid)) return launch_conv_shift(a, n, st);
