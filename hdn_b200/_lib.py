@@ -69,7 +69,7 @@ def lib():
             fn = getattr(L, name)  # AttributeError if the ABI and the binding drift apart
             fn.restype, fn.argtypes = res, args
         if "HDN_B200_CONV_TS" in os.environ:  # A/B switch of the large-launch convolution kernel (see hdn_conv_gemm_set_ts)
-            L.hdn_conv_gemm_set_ts(int(os.environ["HDN_B200_CONV_TS"] != "0"))
+            L.hdn_conv_gemm_set_ts(int(os.environ["HDN_B200_CONV_TS"]))
         _lib = L
     return _lib
 

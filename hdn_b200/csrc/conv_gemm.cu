@@ -449,7 +449,7 @@ extern "C" int hdn_conv_gemm_supported(int Cin, int Cout, int ksize, int dilatio
 
 static int g_conv_splitk = 1;  // hdn_conv_gemm_set_splitk (A/B switch; the result is deterministic either way)
 static int g_conv_shift = 1;   // hdn_conv_gemm_set_shift: conv_shift.cu for 3x3 'valid' layers (A/B switch)
-static int g_conv_ts = 1;      // hdn_conv_gemm_set_ts: conv_gemm_ts.cu (activations in tensor memory) for the large launches (A/B switch; default on)
+static int g_conv_ts = 2;      // hdn_conv_gemm_set_ts: conv_gemm_ts.cu (activations in tensor memory); 0 = off, 1 = large launches only, 2 = every launch (default)
 
 static int conv_gemm_multi(int n, const float *const *x, const float *const *wpk, const float *const *scale, const float *const *shift,
                            const float *const *residual, const float *const *w2, float *const *out, int B, int Cin, int Cout, int H, int W,
@@ -491,11 +491,19 @@ static int conv_gemm_multi(int n, const float *const *x, const float *const *wpk
         if (L < 1 || L > 8) return HDN_ERR_UNSUPPORTED;
         return launch_conv_gemm<64, 4, 0, true>(a, n, st);
     }
+    const int nkb = a.taps * Cin / CG_BK;
+    if (!w2 && g_conv_ts == 2) {  // (A/B) the tensor-memory-operand kernel for the small launches as well, K split over a cluster
+        int split = 1;
+        if (g_conv_splitk != 0)
+            for (int s2 = 8; s2 >= 2; s2 /= 2)
+                if (nkb % s2 == 0 && nkb / s2 >= 4 && tiles128 * s2 <= sm_count() + sm_count() / 4) { split = s2; break; }
+        a.splitk = split;
+        return launch_conv_gemm_ts(a, n, st);
+    }
     // small problems (tracking batch sizes): narrower pixel tiles put more CTAs on the 148 SMs ...
     if (tiles128 >= 2 * sm_count()) return launch_conv_gemm<128, 3, 0>(a, n, st);
     // ... and when even those leave most SMs idle (a 15x15 or 31x31 map at batch 1), K is split over a cluster of 2 / 4 / 8 CTAs
     const long long ctas = (long long)((a.Ho * a.Wo + 63) / 64) * mtiles * B * n;
-    const int nkb = a.taps * Cin / CG_BK;
     int split = 1;
     if (g_conv_splitk != 0)
         for (int s2 = 8; s2 >= 2; s2 /= 2)
@@ -536,7 +544,7 @@ extern "C" int hdn_head_project_multi_f32(int n, const float *const *x_host, con
 }
 
 extern "C" int hdn_conv_gemm_set_ts(int enable) {
-    g_conv_ts = enable ? 1 : 0;
+    g_conv_ts = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
     return HDN_OK;
 }
 

@@ -45,6 +45,9 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
                  "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
                  : "memory");
 }
+__device__ __forceinline__ void ts_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_ts_kernel(const __grid_constant__ ConvGemmArgs a) {
@@ -59,8 +62,16 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_ts_kernel(const 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int HW = a.H * a.W, HWo = a.Ho * a.Wo;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // see conv_gemm.cu
-    const int pix0 = blockIdx.x * CG_BM, co0 = blockIdx.y * TS_BN, prob = blockIdx.z / a.B, img = blockIdx.z - prob * a.B;
-    const int nkb = a.taps * a.Cin / CG_BK;
+    // SPLIT-K over a thread-block cluster (tracking batch sizes, see conv_gemm.cu): the `splitk` CTAs of a cluster own one output tile
+    // and 1/splitk of the K blocks each; the leader adds the peers' fp32 partial tiles through distributed shared memory, in rank order.
+    const int S = a.splitk > 1 ? a.splitk : 1;
+    uint32_t crank = 0;
+    if (S > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const int pix0 = (S > 1 ? (int)blockIdx.x / S : (int)blockIdx.x) * CG_BM, co0 = blockIdx.y * TS_BN, prob = blockIdx.z / a.B,
+              img = blockIdx.z - prob * a.B;
+    const int nkb_all = a.taps * a.Cin / CG_BK;
+    const int nkb = nkb_all / S;       // K blocks of THIS CTA ...
+    const int kb0 = (int)crank * nkb;  // ... starting at global block kb0
     const int nchunks = (nkb + CG_KCB - 1) / CG_KCB;
 
     if (tid == 0) {
@@ -118,10 +129,11 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_ts_kernel(const 
             }
         }
         __syncwarp();
+        if (S > 1) { ts_cluster_sync(); ts_cluster_sync(); }  // the producers' two split-K barriers (every thread of the cluster takes part)
     } else if (warp == CG_THREADS / 32 + 1) {
         // ============================== weight loader: one 32 KB TMA bulk copy per K block (constants: no dependency wait) ==============================
         if (elect_one()) {
-            const float *wsrc = a.wpk[prob] + (size_t)blockIdx.y * nkb * (2 * TS_W_TILE / 4);
+            const float *wsrc = a.wpk[prob] + ((size_t)blockIdx.y * nkb_all + kb0) * (2 * TS_W_TILE / 4);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % TS_WSTAGES;
                 if (kb >= TS_WSTAGES) mbar_wait(&w_free[s], ((kb / TS_WSTAGES) - 1) & 1);
@@ -130,6 +142,7 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_ts_kernel(const 
             }
         }
         __syncwarp();
+        if (S > 1) { ts_cluster_sync(); ts_cluster_sync(); }
     } else {
         // ============================== producers: thread = pixel (TMEM lane), 16 of the K block's 32 channels ==============================
         const float *xb = a.x[prob] + (size_t)img * a.Cin * HW;
@@ -174,7 +187,13 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_ts_kernel(const 
                 asm volatile("" : "+r"(toff[e]));
             }
         }
-        int ld_ci0 = 0, ld_ty = 0, ld_tx = 0;  // position of the NEXT block to load (blocks are loaded in order)
+        int ld_ci0, ld_ty, ld_tx;  // position of the NEXT block to load (blocks are loaded in order)
+        {
+            const int k0 = kb0 * CG_BK, tap = k0 / a.Cin;
+            ld_ci0 = k0 - tap * a.Cin;
+            ld_ty = tap / 3;
+            ld_tx = tap - 3 * ld_ty;
+        }
         auto load_block = [&](float (&v)[16]) {
             const int dy = a.taps == 1 ? 0 : (ld_ty - 1) * a.dil, dx = a.taps == 1 ? 0 : (ld_tx - 1) * a.dil;
             const bool ok = (unsigned)(b_r + dy) < (unsigned)a.H && (unsigned)(b_c + dx) < (unsigned)a.W;
@@ -224,8 +243,33 @@ __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_ts_kernel(const 
         }
         while (drained < nchunks) drain(drained++);
 
+        if (S > 1) {
+            // ---- split-K: the peers park their partial tile in the (dead) weight stages as ys[channel][pixel]; the leader adds them to
+            //      its registers through distributed shared memory, ranks in ascending order (deterministic) ----
+            float *ys = reinterpret_cast<float *>(smem);
+            if (crank != 0) {
+#pragma unroll
+                for (int e = 0; e < HALF; ++e) ys[(col_lo + e) * CG_BM + row] = racc[e];
+            }
+            ts_cluster_sync();
+            if (crank == 0) {
+                const uint32_t ys_s = smem_u32(ys) + (uint32_t)(col_lo * CG_BM + row) * 4u;
+                for (int peer = 1; peer < S; ++peer) {
+                    uint32_t remote;
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(ys_s), "r"(peer));
+#pragma unroll
+                    for (int e = 0; e < HALF; ++e) {
+                        float v;
+                        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote + (uint32_t)(e * CG_BM * 4)) : "memory");
+                        racc[e] += v;
+                    }
+                }
+            }
+            ts_cluster_sync();  // nobody leaves (and frees its shared memory) before the leader has read every partial tile
+        }
+
         // ---- epilogue: lane = pixel, so a warp's store of one channel is 32 consecutive pixels of the NCHW plane ----
-        if (bp < HWo && co0 + col_lo < a.Cout) {  // (Cout = 64 layers run in a zero-padded 128-row record: their upper half stores nothing)
+        if (crank == 0 && bp < HWo && co0 + col_lo < a.Cout) {  // (Cout = 64 layers run in a zero-padded 128-row record: their upper half stores nothing)
             const float *resp = a.residual[prob];
             const size_t base = ((size_t)img * a.Cout + co0 + col_lo) * HWo + bp;
             float *o = a.out[prob] + base;
@@ -261,12 +305,20 @@ int launch_conv_gemm_ts(const ConvGemmArgs &a, int nprob, cudaStream_t st) {
     static DeviceOnce once;
     if (int e = once.run([] { return cudaFuncSetAttribute(conv_gemm_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TS_SMEM); })) return e;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((a.Ho * a.Wo + CG_BM - 1) / CG_BM, (a.Cout + TS_BN - 1) / TS_BN, a.B * nprob);
+    const int S = a.splitk > 1 ? a.splitk : 1;
+    cfg.gridDim = dim3((a.Ho * a.Wo + CG_BM - 1) / CG_BM * S, (a.Cout + TS_BN - 1) / TS_BN, a.B * nprob);
     cfg.blockDim = dim3(CG_THREADS + 64);
     cfg.dynamicSmemBytes = TS_SMEM;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     int na = 0;
+    if (S > 1) {  // a cluster of S CTAs along x per output tile
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = S;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
     if (g_conv_pdl) {
         attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[na].val.programmaticStreamSerializationAllowed = 1;

@@ -478,7 +478,7 @@ def set_conv_splitk(enable=True):
 
 def set_conv_ts(enable=True):
     """Large convolution launches with the activations in tensor memory (conv_gemm_ts.cu); False = shared-memory operands (A/B runs)."""
-    _lib.check(_lib.lib().hdn_conv_gemm_set_ts(int(bool(enable))), "hdn_conv_gemm_set_ts")
+    _lib.check(_lib.lib().hdn_conv_gemm_set_ts(int(enable)), "hdn_conv_gemm_set_ts")  # 2: small launches as well (split-K clusters)
 
 
 def set_conv_pdl(enable=True):

@@ -444,12 +444,12 @@ def test_conv_gemm_with_activations_in_tensor_memory(case):
     try:
         ops.set_conv_ts(False)
         old = ops.conv_gemm(x, wp, scale, shift, res, ksize=k, dilation=d, relu=True, stride=stride, padding=pad, cout=Cout)
-        ops.set_conv_ts(True)
+        ops.set_conv_ts(2)
         new = ops.conv_gemm(x, wp, scale, shift, res, ksize=k, dilation=d, relu=True, stride=stride, padding=pad, cout=Cout)
         again = ops.conv_gemm(x, wp, scale, shift, res, ksize=k, dilation=d, relu=True, stride=stride, padding=pad, cout=Cout)
         plain = ops.conv_gemm(x, wp, ksize=k, dilation=d, stride=stride, padding=pad, cout=Cout)
     finally:
-        ops.set_conv_ts(True)
+        ops.set_conv_ts(2)
     den = float(want64.abs().max())
     assert tuple(new.shape) == tuple(old.shape)
     assert torch.equal(new, again)
@@ -457,3 +457,38 @@ def test_conv_gemm_with_activations_in_tensor_memory(case):
     assert float((new - old).abs().max()) / den < 5e-6
     want_plain = F.conv2d(x[:1].double(), w.double(), stride=stride, padding=pad, dilation=d)
     assert float((plain[:1].double() - want_plain).abs().max()) / float(want_plain.abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("case", [(1, 256, 256, 31, 31, 3, 1, 2, 2), (1, 1024, 256, 31, 31, 1, 1, 0, 1), (2, 512, 512, 15, 15, 3, 1, 1, 1), (1, 128, 128, 63, 63, 3, 2, 1, 1),
+                                  (1, 512, 2048, 31, 31, 1, 1, 0, 1), (3, 256, 256, 7, 7, 3, 1, 0, 1), (1, 64, 64, 32, 32, 3, 1, 1, 1)])
+def test_conv_gemm_ts_split_k_clusters(case):
+    """The tensor-memory-operand kernel at tracking batch sizes (set_conv_ts(2)): K split over a cluster of 2 / 4 / 8 CTAs, the leader adds
+    the peers' partial tiles to its registers through distributed shared memory.  fp32-accurate, deterministic, equal to the default
+    dispatch up to the summation order."""
+    from hdn_b200 import ops
+    B, Cin, Cout, H, W, k, stride, pad, d = case
+    g = torch.Generator(device="cuda").manual_seed(Cin * 3 + Cout + H + k)
+    x = torch.randn(B, Cin, H, W, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, k, k, device="cuda", generator=g) * (2.0 / (Cin * k * k)) ** 0.5
+    scale = 1 + 0.1 * torch.randn(Cout, device="cuda", generator=g)
+    shift = 0.1 * torch.randn(Cout, device="cuda", generator=g)
+    wp = ops.pack_conv_weight(w)
+    y64 = F.conv2d(x.double(), w.double(), stride=stride, padding=pad, dilation=d) * scale.double().view(1, -1, 1, 1) + shift.double().view(1, -1, 1, 1)
+    res = torch.randn(y64.shape, device="cuda", generator=g)
+    want = F.relu(y64 + res.double())
+    try:
+        ops.set_conv_ts(0)
+        ref = ops.conv_gemm(x, wp, scale, shift, res, ksize=k, dilation=d, relu=True, stride=stride, padding=pad, cout=Cout)
+        ops.set_conv_ts(2)
+        new = ops.conv_gemm(x, wp, scale, shift, res, ksize=k, dilation=d, relu=True, stride=stride, padding=pad, cout=Cout)
+        again = ops.conv_gemm(x, wp, scale, shift, res, ksize=k, dilation=d, relu=True, stride=stride, padding=pad, cout=Cout)
+        ops.set_conv_splitk(False)
+        nosplit = ops.conv_gemm(x, wp, scale, shift, res, ksize=k, dilation=d, relu=True, stride=stride, padding=pad, cout=Cout)
+    finally:
+        ops.set_conv_ts(2)
+        ops.set_conv_splitk(True)
+    den = float(want.abs().max())
+    assert torch.equal(new, again)
+    assert float((new.double() - want).abs().max()) / den < 1e-5
+    assert float((nosplit.double() - want).abs().max()) / den < 1e-5
+    assert float((new - ref).abs().max()) / den < 5e-6

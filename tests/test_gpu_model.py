@@ -289,7 +289,7 @@ def test_lockstep_batch_equals_single_sequence_tracking():
             assert np.abs(polys[s] - alone).max() <= 1e-3 * diag, s
     finally:
         ops.set_conv_splitk(True)
-        ops.set_conv_ts(True)
+        ops.set_conv_ts(2)
     polys, _ = runner.track_lockstep(model, seqs)
     for s, (frames, gt) in enumerate(seqs):
         alone, _ = runner.track_sequence(build_tracker(model), frames, gt)
