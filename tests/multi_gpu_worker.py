@@ -23,7 +23,9 @@ def main(out_dir, B_total):
         for t in zf + zf_lp:
             t.zero_()
     shard.broadcast_template_pack(zf + zf_lp, src=0)
-    eng = he.HeadEngine("127/255", hi - lo, dev, chunk=2)
+    # chunk = 1: every launch then has the same size whatever the rank count.  (The convolution dispatch -- split-K cluster size, kernel
+    # choice -- depends on the launch size, so only equal-sized launches are comparable bit for bit.)
+    eng = he.HeadEngine("127/255", hi - lo, dev, chunk=1)
     eng.set_template(zf, zf_lp)
     eng.bind({k: ([t[lo:hi].to(dev) for t in host[k]] if isinstance(host[k], list) else host[k][lo:hi].to(dev)) for k in he.FRAME_KEYS})
     out = eng.run()

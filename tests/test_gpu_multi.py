@@ -1,7 +1,8 @@
 """GPU (needs >= 2 devices; skipped otherwise): "N GPUs == 1 GPU" on the CUDA path, launched with torchrun over
 NCCL.  The batch is block-split over 2 ranks, the template pack is broadcast from rank 0 (the path's one collective besides the
 result gather), and the stitched per-rank results must equal the single-GPU run element-wise -- bit for bit, since every pair is
-computed by the same kernels in the same order whatever rank owns it."""
+computed by the same kernels in the same order whatever rank owns it (the worker launches one pair at a time: kernel choice and
+split-K cluster size depend on the launch size, so only equal-sized launches are comparable bit for bit)."""
 import os
 import subprocess
 import sys
