@@ -50,6 +50,9 @@ __device__ __forceinline__ void ts_cluster_sync() {
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// (320 threads are allocated as 12 warps' worth of registers, so 168 per thread is the ceiling: __maxnreg__(200) compiles without
+// spills but fails to launch.  The projection epilogue of conv_gemm.cu was ported to this operand placement as well and measured no
+// faster -- those launches are epilogue-bound -- so it stays where it is.)
 __global__ void __launch_bounds__(CG_THREADS + 64, 1) conv_gemm_ts_kernel(const __grid_constant__ ConvGemmArgs a) {
     constexpr uint32_t W_SBO = 128, W_LBO = (CG_BM / 8) * 128;  // the packed record's K-major tile: 8-row groups 128 B apart, K chunks of 4 W_LBO apart
     // kind::tf32, fp32 accumulate, A and B K-major, M = 128 (pixels), N = 128 (channels)
