@@ -2,7 +2,7 @@
 # last verification pass of round 2 (lean): all GPU tests, smoke, default bench line, stream (one sequence at a time / lock-step 8)
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-T=r2f
+T=lean
 timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/${T}_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/${T}_pytest.log
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/${T}_smoke.log
 timeout 900 python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err
