@@ -70,6 +70,40 @@ def test_xcorr_algorithm_selector(lib):
     assert lib.hdn_xcorr_set_algo(7) == -4
 
 
+def test_round2_entry_points_validate_without_device(lib):
+    """The convolution, spectra and pre-processing entry points reject bad arguments before touching the device."""
+    null, one = ctypes.c_void_p(0), ctypes.c_void_p(16)
+    # few-channel convolution: supported shapes, NULL, padding beyond k/2, too many input channels
+    assert lib.hdn_conv_small_supported(3, 64, 7, 2) == 1 and lib.hdn_conv_small_supported(2, 64, 7, 2) == 1
+    assert lib.hdn_conv_small_supported(1, 4, 3, 1) == 1 and lib.hdn_conv_small_supported(8, 1, 3, 1) == 1
+    assert lib.hdn_conv_small_supported(16, 4, 3, 1) == 0 and lib.hdn_conv_small_supported(3, 48, 7, 2) == 0 and lib.hdn_conv_small_supported(3, 64, 5, 1) == 0
+    assert lib.hdn_conv_small_f32(null, one, None, None, one, 1, 3, 64, 31, 31, 7, 2, 0, 1, null) == -1
+    assert lib.hdn_conv_small_f32(one, one, None, None, one, 1, 3, 64, 31, 31, 7, 2, 4, 1, null) == -2
+    assert lib.hdn_conv_small_f32(one, one, None, None, one, 1, 16, 4, 31, 31, 3, 1, 1, 1, null) == -4
+    assert lib.hdn_conv_small_f32(one, one, None, None, one, 1, 3, 64, 5, 5, 7, 2, 0, 1, null) == -2       # no output pixel
+    # tcgen05 convolution: geometry of hdn_conv_gemm_ex_f32
+    assert lib.hdn_conv_gemm_supported(256, 256, 3, 2) == 1 and lib.hdn_conv_gemm_supported(64, 64, 3, 1) == 1
+    assert lib.hdn_conv_gemm_supported(48, 128, 1, 1) == 0 and lib.hdn_conv_gemm_supported(256, 2, 1, 1) == 0
+    assert lib.hdn_conv_gemm_ex_f32(one, one, None, None, None, one, 1, 256, 256, 15, 15, 3, 3, 1, 1, 1, null) == -4   # stride 3
+    assert lib.hdn_conv_gemm_ex_f32(one, one, None, None, None, one, 1, 256, 256, 15, 15, 3, 1, 3, 2, 1, null) == -4   # padding > dilation * (k / 2)
+    assert lib.hdn_conv_gemm_ex_f32(null, one, None, None, None, one, 1, 256, 256, 15, 15, 3, 1, 1, 1, 1, null) == -1
+    for mode in (0, 1, 2, 7, -3):  # clamped to {0, 1, 2}
+        assert lib.hdn_conv_gemm_set_ts(mode) == 0
+    assert lib.hdn_conv_gemm_set_ts(2) == 0 and lib.hdn_conv_gemm_set_pdl(1) == 0 and lib.hdn_conv_gemm_set_splitk(1) == 0
+    # cached template spectra: only the 29x29-template shapes at 256/512 crops have the kernels
+    assert lib.hdn_xcorr_spectra_floats(256, 61, 61, 29, 29, 0) == 256 * 29 * 33 * 2
+    assert lib.hdn_xcorr_spectra_floats(256, 29, 29, 29, 29, 1) == 256 * 29 * 33 * 2
+    assert lib.hdn_xcorr_spectra_floats(256, 29, 29, 5, 5, 0) == 0 and lib.hdn_xcorr_spectra_floats(6, 61, 61, 29, 29, 0) == 0
+    arr = (ctypes.c_void_p * 1)
+    assert lib.hdn_xcorr_template_spectra_f32(1, arr(16), arr(32), 256, 29, 29, 5, 5, 0, null) == -4
+    assert lib.hdn_xcorr_template_spectra_f32(1, arr(16), arr(0), 256, 61, 61, 29, 29, 0, null) == -1
+    assert lib.hdn_xcorr_template_spectra_f32(1, arr(20), arr(32), 256, 61, 61, 29, 29, 0, null) == -3         # 16-byte alignment
+    assert lib.hdn_xcorr_dw_multi_spec_f32(1, arr(16), arr(32), arr(48), 0, 256, 61, 61, 29, 29, 0, null) == -2
+    assert lib.hdn_xcorr_dw_multi_spec_f32(9, arr(16), arr(32), arr(48), 1, 256, 61, 61, 29, 29, 0, null) == -4
+    # pre-processing
+    assert lib.hdn_warp_perspective_u8(null, one, 8, 8, (ctypes.c_double * 9)(*([1.0, 0, 0, 0, 1.0, 0, 0, 0, 1.0])), null) == -1
+
+
 def test_ops_reject_cpu_tensors():
     import torch
     from hdn_b200 import ops
